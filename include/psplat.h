@@ -1,0 +1,122 @@
+/*
+ * psplat.h -- C ABI of libpsplat.so, the B200 (sm_100a) Gaussian-splatting renderer that
+ * replaces the arithmetic behind pose-splatter's renderer API.
+ *
+ * Boundary.  The reference has no native code; its "FFI" for this path is
+ *   - src/gaussian_renderer.py:196-208  -> gsplat.rendering.rasterization (third-party CUDA)  [3D]
+ *   - src/gaussian_renderer.py:326-328  -> GaussianRenderer2D._render_vectorized (torch ops)  [2D]
+ * Each entry point below names the reference interface it replaces.  All pointers are
+ * plain DEVICE pointers (fp32 / int32 / int64, C-contiguous), sizes are ints, the stream is
+ * a cudaStream_t passed as void*.  No torch types.  Every function returns 0 on success or
+ * a non-zero code with a message available from ps_last_error() (thread-local).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PSPLAT_H
+#define PSPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_ABI_VERSION 1
+
+#define PS_MODE_2D 2 /* GaussianRenderer2D, rows of 9 floats  (src/gaussian_renderer.py:214-334) */
+#define PS_MODE_3D 3 /* GaussianRenderer3D, rows of 14 floats (src/gaussian_renderer.py:110-211) */
+
+#define PS_FLAG_SAVE_FOR_BACKWARD 1 /* keep the state ps_backward needs                        */
+#define PS_FLAG_KEEP_BINNING 2      /* also keep sort keys / unsorted pairs for the debug taps */
+
+/* what ps_saved_copy can read back (bit-exact parity taps) */
+#define PS_TAP_ISECT_KEYS 1    /* int64 [M]   sorted keys  view<<(32+tile_bits) | tile<<32 | low */
+#define PS_TAP_FLATTEN_IDS 2   /* int32 [M]   sorted values view*N + gaussian                     */
+#define PS_TAP_TILE_OFFSETS 3  /* int32 [V*n_tiles + 1] first sorted index of every (view, tile)  */
+#define PS_TAP_LAST_IDS 4      /* int32 [V,H,W] 1 + index of last contributing entry              */
+#define PS_TAP_TILES_TOUCHED 5 /* int32 [V*N]                                                    */
+#define PS_TAP_REC0 6          /* float4 [V*N] 3D: x,y,rx,ry     2D: u,v,rect(lo),rect(hi)        */
+#define PS_TAP_REC1 7          /* float4 [V*N] 3D: A,B,C,opacity 2D: cos,sin,iax,iay             */
+#define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,depth   2D: r,g,b,opacity               */
+#define PS_TAP_UNSORTED_KEYS 9 /* int64 [M] emission order                                       */
+#define PS_TAP_UNSORTED_IDS 10 /* int32 [M] emission order                                       */
+
+typedef struct ps_ctx ps_ctx;     /* per-device context (stream-ordered scratch pool, pinned mailbox) */
+typedef struct ps_saved ps_saved; /* state of one forward kept for its backward / taps               */
+
+typedef struct ps_render_desc {
+    int32_t mode;      /* PS_MODE_2D | PS_MODE_3D                                            */
+    int32_t width;     /* image width  (renderer.width,  src/gaussian_renderer.py:47)        */
+    int32_t height;    /* image height (renderer.height, :48)                                 */
+    int32_t n_frames;  /* F: parameter sets                                                   */
+    int32_t n_gauss;   /* N: Gaussians per frame (rows of gaussian_params)                    */
+    int32_t n_views;   /* V: (frame, camera) views rendered by this call                      */
+    int32_t flags;     /* PS_FLAG_*                                                           */
+    float near_plane;  /* 3D, gsplat default 0.01  (src/model.py:351)                         */
+    float far_plane;   /* 3D, gsplat default 1e10  (src/model.py:352)                         */
+    float radius_clip; /* 3D, 0.0 at :196-208, 2.0 in the legacy splat (src/model.py:339)     */
+    float eps2d;       /* 3D, gsplat default 0.3                                              */
+} ps_render_desc;
+
+typedef struct ps_saved_info {
+    int64_t n_isect;   /* M = sum of tiles touched                                            */
+    int32_t tile_bits; /* floor(log2(n_tiles)) + 1                                            */
+    int32_t view_bits;
+    int32_t tiles_x, tiles_y;
+    int32_t n_views, n_gauss, n_frames, mode, width, height;
+    int32_t sort_passes; /* radix passes executed                                             */
+    int32_t reserved;
+} ps_saved_info;
+
+int ps_abi_version(void);
+const char *ps_last_error(void);
+
+/* Context for one CUDA device. */
+int ps_ctx_create(int device, ps_ctx **out);
+int ps_ctx_destroy(ps_ctx *ctx);
+
+/*
+ * Forward render of V views.
+ * Replaces: GaussianRenderer3D.render (src/gaussian_renderer.py:157-211, i.e. the adapter
+ * activations :183-193 + gsplat rasterization :196-208) and GaussianRenderer2D.render
+ * (:269-334 incl. _render_vectorized :336-427).  One reference call is V = F = 1.
+ *   params      [F, N, 14|9]  raw gaussian_params rows (activations are applied inside)
+ *   view_frame  [V] int32     which parameter set each view renders
+ *   viewmats    [V, 4, 4]     world->camera, row-major (3D; may be NULL in 2D)
+ *   Ks          [V, 3, 3]     intrinsics, row-major      (3D; may be NULL in 2D)
+ *   background  [3]           renderer.background_color (:53-56)
+ * Outputs (caller-allocated): rgb [V,H,W,3], alpha [V,H,W], n_contrib [V,H,W] int32 or NULL.
+ * *saved receives the state for ps_backward when PS_FLAG_SAVE_FOR_BACKWARD is set (else NULL).
+ */
+int ps_forward(ps_ctx *ctx, const ps_render_desc *desc, const float *params, const int32_t *view_frame,
+               const float *viewmats, const float *Ks, const float *background, float *rgb, float *alpha,
+               int32_t *n_contrib, ps_saved **saved, void *stream);
+
+/*
+ * Backward of ps_forward: d_params [F,N,P] = dL/d gaussian_params given d_rgb [V,H,W,3] and
+ * d_alpha [V,H,W].  Replaces autograd through :183-211 / :314-427 (gsplat's
+ * rasterize_to_pixels_bwd + fully_fused_projection_bwd in 3D).  The input pointers must be
+ * the ones given to the forward.  d_params is overwritten (not accumulated into).
+ */
+int ps_backward(ps_ctx *ctx, ps_saved *saved, const float *params, const int32_t *view_frame, const float *viewmats,
+                const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
+                void *stream);
+
+int ps_saved_info_get(const ps_saved *saved, ps_saved_info *out);
+/* Copy one tap (PS_TAP_*) into dst (device or host pointer), at most `bytes`; waits on the stream. */
+int ps_saved_copy(ps_ctx *ctx, const ps_saved *saved, int what, void *dst, size_t bytes, void *stream);
+int ps_saved_release(ps_ctx *ctx, ps_saved *saved, void *stream);
+
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+int64_t ps_ctx_launch_count(const ps_ctx *ctx);
+
+/*
+ * Device probe of the arithmetic contract (PSM-1): y[5][n] = exp, log(|x|+1e-30), sigmoid, sin, cos
+ * of x[n], computed by the same device functions the kernels use.  For the bit-exactness tests.
+ */
+int ps_math_probe(ps_ctx *ctx, const float *x, int n, float *y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSPLAT_H */

@@ -1,0 +1,5 @@
+"""pose_splatter_b200: B200-native (sm_100a) Gaussian-splatting renderer behind pose-splatter's renderer API."""
+from .gaussian_renderer import GaussianRenderer, GaussianRenderer2D, GaussianRenderer3D, create_renderer
+from .batched import render_views
+
+__all__ = ["GaussianRenderer", "GaussianRenderer2D", "GaussianRenderer3D", "create_renderer", "render_views"]

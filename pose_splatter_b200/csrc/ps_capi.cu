@@ -1,0 +1,334 @@
+// ps_capi.cu -- C ABI of libpsplat.so (include/psplat.h): context, stream-ordered scratch,
+// and the stage orchestration  project -> scan -> [M to host] -> emit -> radix sort ->
+// tile ranges -> rasterize  (forward)  /  rasterize-backward -> projection-backward.
+// No torch types, no CPU fallback: every entry point needs a CUDA device.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "ps_contract.cuh"
+#include "ps_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PS_CUDA(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define PS_LAUNCH(ctx, call)                                                   \
+    do {                                                                       \
+        int n_ = (call);                                                       \
+        if (n_ < 0) return fail(3, "kernel launch failed in %s: %s", #call, cudaGetErrorString(cudaGetLastError())); \
+        (ctx)->launches += n_;                                                 \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t count, cudaStream_t s)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMallocAsync((void **)p, count * sizeof(T), s);
+}
+
+template <typename T>
+void dev_free(T *&p, cudaStream_t s)
+{
+    if (p) cudaFreeAsync((void *)p, s);
+    p = nullptr;
+}
+
+} // namespace
+
+struct ps_ctx {
+    int device;
+    int64_t launches;
+    int64_t *h_total; // pinned mailbox for M
+    int64_t *d_total;
+};
+
+struct ps_saved {
+    PsGeometry g;
+    PsTable t;
+    int64_t M;
+    int sort_passes;
+    uint64_t *keys;     // sorted (kept only with PS_FLAG_KEEP_BINNING)
+    uint32_t *vals;     // sorted
+    uint64_t *keys_raw; // emission order (debug)
+    uint32_t *vals_raw;
+    int32_t *offsets;   // [V*n_tiles + 1]
+    int32_t *last;      // [V,H,W]
+    float *t_pen;       // [V,H,W]
+};
+
+extern "C" {
+
+int ps_abi_version(void) { return PS_ABI_VERSION; }
+const char *ps_last_error(void) { return g_err; }
+
+int ps_ctx_create(int device, ps_ctx **out)
+{
+    if (!out) return fail(1, "ps_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(2, "ps_ctx_create: no CUDA device (%s); libpsplat has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(1, "ps_ctx_create: device %d out of range (%d devices)", device, n);
+    PS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(2, "ps_ctx_create: device %d is sm_%d%d; libpsplat is built for sm_100a only", device, prop.major, prop.minor);
+    ps_ctx *c = new (std::nothrow) ps_ctx();
+    if (!c) return fail(4, "ps_ctx_create: out of host memory");
+    c->device = device;
+    c->launches = 0;
+    PS_CUDA(cudaMallocHost((void **)&c->h_total, sizeof(int64_t)));
+    PS_CUDA(cudaMalloc((void **)&c->d_total, sizeof(int64_t)));
+    // keep freed scratch in the pool instead of returning it to the driver between calls
+    cudaMemPool_t pool;
+    PS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    PS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    *out = c;
+    return 0;
+}
+
+int ps_ctx_destroy(ps_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(ctx->h_total);
+    cudaFree(ctx->d_total);
+    delete ctx;
+    return 0;
+}
+
+int64_t ps_ctx_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static void saved_free(ps_saved *sv, cudaStream_t s)
+{
+    dev_free(sv->t.rec0, s); dev_free(sv->t.rec1, s); dev_free(sv->t.rec2, s);
+    dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.block_sums, s);
+    dev_free(sv->keys, s); dev_free(sv->vals, s); dev_free(sv->keys_raw, s); dev_free(sv->vals_raw, s);
+    dev_free(sv->offsets, s); dev_free(sv->last, s); dev_free(sv->t_pen, s);
+}
+
+int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
+               const float *viewmats, const float *Ks, const float *background, float *rgb, float *alpha,
+               int32_t *n_contrib, ps_saved **saved, void *stream)
+{
+    if (saved) *saved = nullptr;
+    if (!ctx || !d) return fail(1, "ps_forward: NULL context or descriptor");
+    if (d->mode != PS_MODE_2D && d->mode != PS_MODE_3D) return fail(1, "ps_forward: unknown mode %d", d->mode);
+    if (d->width <= 0 || d->height <= 0 || d->width > 32767 || d->height > 32767)
+        return fail(1, "ps_forward: image size %dx%d unsupported", d->width, d->height);
+    if (d->n_views < 0 || d->n_gauss < 0 || d->n_frames < 0) return fail(1, "ps_forward: negative size");
+    if (d->n_views > 65535) return fail(1, "ps_forward: at most 65535 views per call (got %d)", d->n_views);
+    if (d->n_views > 0 && (!view_frame || !background || !rgb || !alpha)) return fail(1, "ps_forward: NULL buffer");
+    if (d->n_views > 0 && d->n_gauss > 0 && !params) return fail(1, "ps_forward: NULL params");
+    if (d->mode == PS_MODE_3D && d->n_views > 0 && (!viewmats || !Ks)) return fail(1, "ps_forward: 3D needs viewmats and Ks");
+    if ((int64_t)d->n_views * d->n_gauss > 0x7fffffffLL) return fail(1, "ps_forward: V*N exceeds 2^31");
+    const bool save = (d->flags & PS_FLAG_SAVE_FOR_BACKWARD) != 0;
+    const bool keep = (d->flags & PS_FLAG_KEEP_BINNING) != 0;
+    if ((save || keep) && !saved) return fail(1, "ps_forward: saved is NULL but a SAVE/KEEP flag is set");
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+
+    ps_saved *sv = new (std::nothrow) ps_saved();
+    if (!sv) return fail(4, "ps_forward: out of host memory");
+    memset(sv, 0, sizeof *sv);
+    PsGeometry &g = sv->g;
+    g.mode = d->mode; g.W = d->width; g.H = d->height; g.F = d->n_frames; g.N = d->n_gauss; g.V = d->n_views;
+    g.tiles_x = (g.W + PS_TILE - 1) / PS_TILE; g.tiles_y = (g.H + PS_TILE - 1) / PS_TILE;
+    g.n_tiles = g.tiles_x * g.tiles_y;
+    g.tile_bits = ps_tile_bits(g.n_tiles);
+    g.view_bits = 0;
+    while ((1 << g.view_bits) < g.V) ++g.view_bits;
+    g.near_plane = d->near_plane; g.far_plane = d->far_plane; g.radius_clip = d->radius_clip; g.eps2d = d->eps2d;
+
+    int rc = 0;
+    uint64_t *keys_alt = nullptr;
+    uint32_t *vals_alt = nullptr, *hist = nullptr;
+    // everything below jumps to `out` on error so scratch is always returned to the pool
+#define PS_TRY(expr) do { rc = (expr); if (rc) goto out; } while (0)
+#define PS_TRY_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); goto out; } } while (0)
+#define PS_TRY_LAUNCH(call) do { int n_ = (call); if (n_ < 0) { rc = fail(3, "kernel launch failed in %s: %s", #call, cudaGetErrorString(cudaGetLastError())); goto out; } ctx->launches += n_; } while (0)
+    {
+        const size_t VN = (size_t)g.V * g.N;
+        const size_t nblk = (size_t)g.V * ((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK);
+        const size_t npix = (size_t)g.V * g.H * g.W;
+        sv->M = 0;
+        if (VN > 0) {
+            PS_TRY_CUDA(dev_alloc(&sv->t.rec0, VN, s));
+            PS_TRY_CUDA(dev_alloc(&sv->t.rec1, VN, s));
+            PS_TRY_CUDA(dev_alloc(&sv->t.rec2, VN, s));
+            PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
+            PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
+            PS_TRY_CUDA(dev_alloc(&sv->t.block_sums, nblk + 1, s));
+            PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, s));
+            PS_TRY_LAUNCH(ps_launch_scan_block_sums(g, sv->t, ctx->d_total, s));
+            PS_TRY_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the sort
+            sv->M = *ctx->h_total;
+            if (sv->M > 0x7fffffffLL) { rc = fail(1, "ps_forward: %lld tile intersections exceed 2^31", (long long)sv->M); goto out; }
+        }
+        const int64_t M = sv->M;
+        PS_TRY_CUDA(dev_alloc(&sv->offsets, (size_t)g.V * g.n_tiles + 1, s));
+        if (M > 0) {
+            PS_TRY_CUDA(dev_alloc(&sv->keys, (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&sv->vals, (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&keys_alt, (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&vals_alt, (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&hist, ps_sort_hist_elems(M), s));
+            PS_TRY_LAUNCH(ps_launch_emit(g, sv->t, sv->keys, sv->vals, s));
+            if (keep) {
+                PS_TRY_CUDA(dev_alloc(&sv->keys_raw, (size_t)M, s));
+                PS_TRY_CUDA(dev_alloc(&sv->vals_raw, (size_t)M, s));
+                PS_TRY_CUDA(cudaMemcpyAsync(sv->keys_raw, sv->keys, sizeof(uint64_t) * M, cudaMemcpyDeviceToDevice, s));
+                PS_TRY_CUDA(cudaMemcpyAsync(sv->vals_raw, sv->vals, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, s));
+            }
+            // 3D sorts depth bits + tile + view; 2D emits rows in order, so only tile + view bits
+            const int bit_lo = (g.mode == PS_MODE_3D) ? 0 : 32;
+            const int bit_hi = 32 + g.tile_bits + g.view_bits;
+            PS_TRY_LAUNCH(ps_launch_sort(sv->keys, sv->vals, keys_alt, vals_alt, M, bit_lo, bit_hi, hist, &sv->sort_passes, s));
+            if (sv->sort_passes & 1) {
+                uint64_t *tk = sv->keys; sv->keys = keys_alt; keys_alt = tk;
+                uint32_t *tv = sv->vals; sv->vals = vals_alt; vals_alt = tv;
+            }
+        }
+        PS_TRY_LAUNCH(ps_launch_tile_ranges(g, sv->keys, M, sv->offsets, s));
+        if (npix > 0) {
+            if (save) {
+                PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
+                PS_TRY_CUDA(dev_alloc(&sv->t_pen, npix, s));
+            } else if (keep) {
+                PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
+            }
+            PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->vals, sv->offsets, background, rgb, alpha, n_contrib,
+                                               sv->last, sv->t_pen, s));
+        }
+    }
+out:
+    dev_free(keys_alt, s); dev_free(vals_alt, s); dev_free(hist, s);
+    if (rc == 0 && !keep) { dev_free(sv->keys, s); dev_free(sv->t.tile_rect, s); dev_free(sv->t.block_sums, s); }
+    if (rc != 0 || !(save || keep)) {
+        saved_free(sv, s);
+        delete sv;
+        sv = nullptr;
+    }
+    if (saved) *saved = sv;
+    return rc;
+#undef PS_TRY
+#undef PS_TRY_CUDA
+#undef PS_TRY_LAUNCH
+}
+
+int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *view_frame, const float *viewmats,
+                const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
+                void *stream)
+{
+    if (!ctx || !sv) return fail(1, "ps_backward: NULL context or saved state");
+    const PsGeometry &g = sv->g;
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    const int P = g.mode == PS_MODE_3D ? 14 : 9;
+    const size_t n_out = (size_t)g.F * g.N * P;
+    if (n_out == 0) return 0;
+    if (!d_params) return fail(1, "ps_backward: NULL d_params");
+    PS_CUDA(cudaMemsetAsync(d_params, 0, n_out * sizeof(float), s));
+    const size_t VN = (size_t)g.V * g.N;
+    if (VN == 0 || sv->M == 0 || (size_t)g.H * g.W == 0) return 0;
+    if (!sv->last || !sv->t_pen) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
+    if (!d_rgb || !d_alpha || !params || !view_frame || !background) return fail(1, "ps_backward: NULL buffer");
+    float *acc = nullptr;
+    PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE, s));
+    int rc = 0;
+    do {
+        if (cudaMemsetAsync(acc, 0, VN * PS_ACC_STRIDE * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
+        int n = ps_launch_raster_bwd(g, sv->t, sv->vals, sv->offsets, background, sv->last, sv->t_pen, d_rgb, d_alpha, acc, s);
+        if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        ctx->launches += n;
+        n = ps_launch_project_bwd(g, params, view_frame, viewmats, Ks, sv->t, acc, d_params, s);
+        if (n < 0) { rc = fail(3, "ps_backward: project_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        ctx->launches += n;
+    } while (0);
+    dev_free(acc, s);
+    return rc;
+}
+
+int ps_saved_info_get(const ps_saved *sv, ps_saved_info *out)
+{
+    if (!sv || !out) return fail(1, "ps_saved_info_get: NULL argument");
+    memset(out, 0, sizeof *out);
+    out->n_isect = sv->M;
+    out->tile_bits = sv->g.tile_bits; out->view_bits = sv->g.view_bits;
+    out->tiles_x = sv->g.tiles_x; out->tiles_y = sv->g.tiles_y;
+    out->n_views = sv->g.V; out->n_gauss = sv->g.N; out->n_frames = sv->g.F;
+    out->mode = sv->g.mode; out->width = sv->g.W; out->height = sv->g.H;
+    out->sort_passes = sv->sort_passes;
+    return 0;
+}
+
+int ps_saved_copy(ps_ctx *ctx, const ps_saved *sv, int what, void *dst, size_t bytes, void *stream)
+{
+    if (!ctx || !sv || !dst) return fail(1, "ps_saved_copy: NULL argument");
+    const PsGeometry &g = sv->g;
+    const size_t VN = (size_t)g.V * g.N, npix = (size_t)g.V * g.H * g.W;
+    const void *src = nullptr;
+    size_t have = 0;
+    switch (what) {
+        case PS_TAP_ISECT_KEYS: src = sv->keys; have = sizeof(uint64_t) * (size_t)sv->M; break;
+        case PS_TAP_FLATTEN_IDS: src = sv->vals; have = sizeof(uint32_t) * (size_t)sv->M; break;
+        case PS_TAP_TILE_OFFSETS: src = sv->offsets; have = sizeof(int32_t) * ((size_t)g.V * g.n_tiles + 1); break;
+        case PS_TAP_LAST_IDS: src = sv->last; have = sizeof(int32_t) * npix; break;
+        case PS_TAP_TILES_TOUCHED: src = sv->t.tiles_touched; have = sizeof(int32_t) * VN; break;
+        case PS_TAP_REC0: src = sv->t.rec0; have = sizeof(float4) * VN; break;
+        case PS_TAP_REC1: src = sv->t.rec1; have = sizeof(float4) * VN; break;
+        case PS_TAP_REC2: src = sv->t.rec2; have = sizeof(float4) * VN; break;
+        case PS_TAP_UNSORTED_KEYS: src = sv->keys_raw; have = sizeof(uint64_t) * (size_t)sv->M; break;
+        case PS_TAP_UNSORTED_IDS: src = sv->vals_raw; have = sizeof(uint32_t) * (size_t)sv->M; break;
+        default: return fail(1, "ps_saved_copy: unknown tap %d", what);
+    }
+    if (have == 0) return 0;
+    if (!src) return fail(1, "ps_saved_copy: tap %d was not kept (PS_FLAG_KEEP_BINNING / SAVE_FOR_BACKWARD)", what);
+    if (bytes < have) return fail(1, "ps_saved_copy: destination holds %zu bytes, tap %d needs %zu", bytes, what, have);
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_CUDA(cudaMemcpyAsync(dst, src, have, cudaMemcpyDefault, s));
+    PS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ps_saved_release(ps_ctx *ctx, ps_saved *sv, void *stream)
+{
+    if (!sv) return 0;
+    if (ctx) cudaSetDevice(ctx->device);
+    saved_free(sv, (cudaStream_t)stream);
+    delete sv;
+    return 0;
+}
+
+int ps_math_probe(ps_ctx *ctx, const float *x, int n, float *y, void *stream)
+{
+    if (!ctx) return fail(1, "ps_math_probe: NULL context");
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_LAUNCH(ctx, ps_launch_math_probe(x, n, y, (cudaStream_t)stream));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,357 @@
+// ps_raster.cu -- per-tile rasterizers (SURVEY.md 2.2 K5', K6'), both gaussian modes.
+//
+// One CTA per (view, 16x16 tile): 8 warps, each owning an 8x4 pixel block.  The tile's sorted
+// list is staged through shared memory 256 splat records (48 B each) at a time.  Each warp
+// first culls the staged batch against its own 8x4 block (one record per lane, ballot), then
+// walks only the surviving records in list order, so the per-pixel work is proportional to the
+// splats that can touch the block, not to the tile list (the hot tiles of this workload list
+// ~all N Gaussians).  Culling never changes a result: it only removes pairs whose
+// alpha test (3D) / rectangle test (2D) is guaranteed to fail.
+//   forward : front-to-back compositing with early termination            [FP32 pipe + smem]
+//   backward: reverse replay from last_id; transmittance recovered by division starting from
+//             the saved "T before the last contributor"; per-splat gradients are reduced across
+//             the warp (multi-value butterfly), accumulated per CTA in shared memory and flushed
+//             with one vector red.global.add.v4.f32 triple per (tile, splat)  [FP32 pipe + smem]
+// Replaces gsplat rasterize_to_pixels_3dgs_fwd/bwd (absent from the reference tree) and the
+// torch element-wise loop src/gaussian_renderer.py:379-425 plus its autograd.
+#include "ps_contract.cuh"
+#include "ps_internal.h"
+
+namespace {
+
+constexpr int RB = PS_RASTER_BATCH;
+constexpr float CULL_MARGIN = 1.0f;  // px of slack on the 3D rectangle test (exact in real arithmetic)
+constexpr float SIGMA_SKIP = 5.6f;   // sigma above ln(255) can never pass alpha >= 1/255 (opacity <= 1)
+
+struct TileCtx {
+    int view, tile, start, end;
+    int px, py;   // this lane's pixel
+    int bx, by;   // warp block origin
+    bool inside;
+};
+
+__device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *offsets)
+{
+    TileCtx c;
+    const int lin = blockIdx.x;
+    c.view = lin / g.n_tiles;
+    c.tile = lin - c.view * g.n_tiles;
+    const int ty = c.tile / g.tiles_x, tx = c.tile - ty * g.tiles_x;
+    c.start = offsets[lin];
+    c.end = offsets[lin + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    c.bx = tx * PS_TILE + (wid & 1) * 8;
+    c.by = ty * PS_TILE + (wid >> 1) * 4;
+    c.px = c.bx + (lane & 7);
+    c.py = c.by + (lane >> 3);
+    c.inside = c.px < g.W && c.py < g.H;
+    return c;
+}
+
+// does staged record (r0) possibly touch this warp's 8x4 pixel block?
+template <int MODE>
+__device__ __forceinline__ bool block_hit(const float4 &r0, int bx, int by)
+{
+    if (MODE == PS_MODE_3D) {
+        // pixel centres of the block span [bx+.5, bx+7.5] x [by+.5, by+3.5]
+        return fabsf(r0.x - ((float)bx + 4.0f)) <= r0.z + (3.5f + CULL_MARGIN) &&
+               fabsf(r0.y - ((float)by + 2.0f)) <= r0.w + (1.5f + CULL_MARGIN);
+    } else {
+        const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
+        const int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
+        return x0 <= bx + 7 && x1 >= bx && y0 <= by + 3 && y1 >= by;
+    }
+}
+
+__device__ __forceinline__ void stage_batch(const PsTable &t, const uint32_t *__restrict__ vals, int first, int count,
+                                            float4 *s_r0, float4 *s_r1, float4 *s_r2, uint32_t *id_out)
+{
+    if ((int)threadIdx.x < count) {
+        const uint32_t id = __ldg(vals + first + threadIdx.x);
+        s_r0[threadIdx.x] = __ldg(t.rec0 + id);
+        s_r1[threadIdx.x] = __ldg(t.rec1 + id);
+        s_r2[threadIdx.x] = __ldg(t.rec2 + id);
+        if (id_out) *id_out = id;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
+                  const float *__restrict__ background, float *__restrict__ rgb, float *__restrict__ alpha,
+                  int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, float *__restrict__ t_pen)
+{
+    __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB];
+    const TileCtx c = tile_ctx(g, offsets);
+    const int lane = threadIdx.x & 31;
+    const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
+    const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
+    float T = 1.0f, Tpen = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    int cnt = 0, lastpos = c.start;
+    bool done = !c.inside;
+    const int nbatch = (c.end - c.start + RB - 1) / RB;
+    for (int b = 0; b < nbatch; ++b) {
+        // barrier: everyone is finished with the previous batch; also the CTA-wide early exit
+        if (__syncthreads_count(done) == (int)blockDim.x) break;
+        const int first = c.start + b * RB;
+        const int nvalid = min(RB, c.end - first);
+        stage_batch(t, vals, first, nvalid, s_r0, s_r1, s_r2, nullptr);
+        __syncthreads();
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int k = 0; k * 32 < nvalid; ++k) {
+            const int j = k * 32 + lane;
+            uint32_t mask = __ballot_sync(0xffffffffu, j < nvalid && block_hit<MODE>(s_r0[j], c.bx, c.by));
+            while (mask) {
+                const int e = k * 32 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 r0 = s_r0[e], r1 = s_r1[e];
+                if (MODE == PS_MODE_3D) {
+                    float dx, dy;
+                    const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
+                    const bool cand = !done && sg >= 0.0f && sg <= SIGMA_SKIP;
+                    if (!__any_sync(0xffffffffu, cand)) continue;
+                    const float a = fminf(PS_ALPHA_MAX, psm_mul(r1.w, psm_exp(-sg)));
+                    if (cand && a >= PS_ALPHA_MIN) {
+                        const float nT = psm_mul(T, psm_sub(1.0f, a));
+                        if (nT <= PS_T_STOP_3D) {
+                            done = true;
+                        } else {
+                            const float4 r2 = s_r2[e];
+                            const float vis = psm_mul(a, T);
+                            cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                            Tpen = T; T = nT; ++cnt; lastpos = first + e + 1;
+                        }
+                    }
+                } else {
+                    const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
+                    const bool in = !done && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
+                                    c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
+                    if (!__any_sync(0xffffffffu, in)) continue;
+                    float dxr, dyr;
+                    const float4 r2 = s_r2[e];
+                    const float q = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
+                    const float gv = psm_mul(r2.w, psm_exp(-q));
+                    if (in) {
+                        const float contrib = psm_mul(gv, T);
+                        cr = psm_fma(contrib, r2.x, cr); cg = psm_fma(contrib, r2.y, cg); cb = psm_fma(contrib, r2.z, cb);
+                        Tpen = T; T = psm_mul(T, psm_sub(1.0f, gv)); ++cnt; lastpos = first + e + 1;
+                        if (T <= PS_T_STOP_2D) done = true;
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    if (c.inside) {
+        const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
+        const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
+        rgb[3 * p + 0] = psm_fma(T, b0, cr);
+        rgb[3 * p + 1] = psm_fma(T, b1, cg);
+        rgb[3 * p + 2] = psm_fma(T, b2, cb);
+        alpha[p] = psm_sub(1.0f, T);
+        if (n_contrib) n_contrib[p] = cnt;
+        if (last) last[p] = lastpos;
+        if (t_pen) t_pen[p] = Tpen;
+    }
+}
+
+// Sum 9 per-lane values over the warp.  v[0..7] go through a halving butterfly (16+8+4+2+2
+// instructions instead of 8 x 10); afterwards lane L holds the total of value (L >> 2) in v[0].
+// v8 is reduced with the plain 5-step butterfly (every lane gets the total).
+__device__ __forceinline__ void warp_reduce9(float (&v)[8], float &v8, int lane)
+{
+    const uint32_t full = 0xffffffffu;
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi ? v[i] : v[i + 4];
+            const float keep = hi ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = hi ? v[i] : v[i + 2];
+            const float keep = hi ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 2);
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v8 += __shfl_xor_sync(full, v8, d);
+}
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
+                  const float *__restrict__ background, const int32_t *__restrict__ last,
+                  const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
+                  float *__restrict__ acc)
+{
+    __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB];
+    __shared__ float s_grad[RB * 9];
+    __shared__ int s_touched[RB];
+    __shared__ int s_tile_end;
+    const TileCtx c = tile_ctx(g, offsets);
+    if (c.end == c.start) return;
+    const int lane = threadIdx.x & 31;
+    const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
+    const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
+    int my_last = c.start;
+    float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
+    if (c.inside) {
+        const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
+        my_last = last[p];
+        Tcur = t_pen[p];
+        w0 = d_rgb[3 * p]; w1 = d_rgb[3 * p + 1]; w2 = d_rgb[3 * p + 2];
+        S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
+    }
+    if (threadIdx.x == 0) s_tile_end = c.start;
+    __syncthreads();
+    {
+        int m = my_last;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) atomicMax(&s_tile_end, m);
+    }
+    __syncthreads();
+    const int tile_end = s_tile_end;
+    const int nbatch = (tile_end - c.start + RB - 1) / RB;
+    for (int b = nbatch - 1; b >= 0; --b) {
+        __syncthreads(); // previous batch fully flushed
+        const int first = c.start + b * RB;
+        const int nvalid = min(RB, tile_end - first);
+        uint32_t my_id = 0;
+        stage_batch(t, vals, first, nvalid, s_r0, s_r1, s_r2, &my_id);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s_grad[i * RB + threadIdx.x] = 0.0f;
+        s_touched[threadIdx.x] = 0;
+        __syncthreads();
+        if (__any_sync(0xffffffffu, my_last > first)) {
+            for (int k = (nvalid - 1) / 32; k >= 0; --k) {
+                const int j = k * 32 + lane;
+                uint32_t mask = __ballot_sync(0xffffffffu, j < nvalid && block_hit<MODE>(s_r0[j], c.bx, c.by));
+                while (mask) {
+                    const int bit = 31 - __clz(mask);
+                    mask &= ~(1u << bit);
+                    const int e = k * 32 + bit;
+                    const int pos = first + e;
+                    const bool active = pos < my_last;
+                    const float4 r0 = s_r0[e], r1 = s_r1[e];
+                    float v[8], v8 = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+                    if (MODE == PS_MODE_3D) {
+                        float dx, dy;
+                        const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
+                        const bool cand = active && sg >= 0.0f && sg <= SIGMA_SKIP;
+                        if (!__any_sync(0xffffffffu, cand)) continue;
+                        const float ex = psm_exp(-sg);
+                        const float oe = psm_mul(r1.w, ex);
+                        const float a = fminf(PS_ALPHA_MAX, oe);
+                        const bool contrib = cand && a >= PS_ALPHA_MIN;
+                        if (!__any_sync(0xffffffffu, contrib)) continue;
+                        if (contrib) {
+                            const float4 r2 = s_r2[e];
+                            const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - a);
+                            Tcur = Tb;
+                            const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+                            const float v_alpha = Tb * (cw - S);
+                            const float vis = a * Tb;
+                            v[0] = vis * w0; v[1] = vis * w1; v[2] = vis * w2;
+                            S = S + a * (cw - S);
+                            if (oe <= PS_ALPHA_MAX) {
+                                const float v_sigma = -oe * v_alpha;
+                                v[3] = 0.5f * v_sigma * dx * dx;
+                                v[4] = v_sigma * dx * dy;
+                                v[5] = 0.5f * v_sigma * dy * dy;
+                                v[6] = v_sigma * (r1.x * dx + r1.y * dy);
+                                v[7] = v_sigma * (r1.y * dx + r1.z * dy);
+                                v8 = ex * v_alpha;
+                            }
+                        }
+                    } else {
+                        const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
+                        const bool contrib = active && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
+                                             c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
+                        if (!__any_sync(0xffffffffu, contrib)) continue;
+                        if (contrib) {
+                            float dxr, dyr;
+                            const float4 r2 = s_r2[e];
+                            const float q = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
+                            const float gv = psm_mul(r2.w, psm_exp(-q));
+                            const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - gv);
+                            Tcur = Tb;
+                            const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+                            const float dLdg = Tb * (cw - S);
+                            const float cn = gv * Tb;
+                            v[0] = cn * w0; v[1] = cn * w1; v[2] = cn * w2;
+                            const float Gq = -gv * dLdg;
+                            const float ddxr = 2.0f * dxr * r1.z * Gq, ddyr = 2.0f * dyr * r1.w * Gq;
+                            v[3] = ddxr; v[4] = ddyr;
+                            v[5] = ddxr * dyr - ddyr * dxr;
+                            v[6] = dxr * dxr * Gq;
+                            v[7] = dyr * dyr * Gq;
+                            v8 = Gq;
+                            S = S + gv * (cw - S);
+                        }
+                    }
+                    warp_reduce9(v, v8, lane);
+                    if ((lane & 3) == 0) atomicAdd(&s_grad[e * 9 + (lane >> 2)], v[0]);
+                    if (lane == 1) { atomicAdd(&s_grad[e * 9 + 8], v8); s_touched[e] = 1; }
+                }
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nvalid && s_touched[threadIdx.x]) {
+            float *dst = acc + (size_t)my_id * PS_ACC_STRIDE;
+            const float *sg = s_grad + threadIdx.x * 9; // [entry][9]: conflict-free for the atomics and for this read
+            red_add_v4(dst, sg[0], sg[1], sg[2], sg[3]);
+            red_add_v4(dst + 4, sg[4], sg[5], sg[6], sg[7]);
+            atomicAdd(dst + 8, sg[8]);
+        }
+    }
+}
+
+} // namespace
+
+int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
+                         const float *background, float *rgb, float *alpha, int32_t *n_contrib, int32_t *last,
+                         float *t_pen, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)g.V * (unsigned)g.n_tiles;
+    if (grid == 0) return 0;
+    if (g.mode == PS_MODE_3D)
+        raster_fwd_kernel<PS_MODE_3D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, rgb, alpha, n_contrib, last, t_pen);
+    else
+        raster_fwd_kernel<PS_MODE_2D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, rgb, alpha, n_contrib, last, t_pen);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
+                         const float *background, const int32_t *last, const float *t_pen, const float *d_rgb,
+                         const float *d_alpha, float *acc, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)g.V * (unsigned)g.n_tiles;
+    if (grid == 0) return 0;
+    if (g.mode == PS_MODE_3D)
+        raster_bwd_kernel<PS_MODE_3D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, last, t_pen, d_rgb, d_alpha, acc);
+    else
+        raster_bwd_kernel<PS_MODE_2D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, last, t_pen, d_rgb, d_alpha, acc);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}

@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (pose_splatter_b200._capi / batched),
+against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): sort keys, tile ranges and per-pixel contributor counts
+bit-exact; rendered RGB / alpha within 1e-4 max-abs; gradients within 1e-3 relative
+(per parameter column, normalised by the column's max-abs gradient).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, GRAD_TOL, RGB_TOL, bits, column_rel_err, golden_cotangents, records_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _mods():
+    from oracle import oracle as ora
+    from pose_splatter_b200 import _capi, batched, synth
+    return ora, _capi, batched, synth
+
+
+def _run_product(mode, params, view_frame, W, H, bg, viewmats=None, Ks=None, w_rgb=None, w_a=None, **opts):
+    """forward (+ backward) through the C ABI with all debug taps kept."""
+    _, _capi, batched, _ = _mods()
+    p = params.to(DEV).contiguous()
+    vf = view_frame.to(DEV).int()
+    vm = None if viewmats is None else viewmats.to(DEV).contiguous()
+    Kd = None if Ks is None else Ks.to(DEV).contiguous()
+    bgd = torch.as_tensor(bg, dtype=torch.float32, device=DEV)
+    rgb, alpha, counts, saved = batched.forward_raw(mode, p, vf, vm, Kd, bgd, W, H,
+                                                    _capi.FLAG_SAVE_FOR_BACKWARD | _capi.FLAG_KEEP_BINNING, True, opts)
+    out = dict(rgb=rgb.cpu().numpy(), alpha=alpha.cpu().numpy(), n_contrib=counts.cpu().numpy(), saved=saved)
+    if w_rgb is not None:
+        d = batched.backward_raw(saved, p, vf, vm, Kd, bgd, w_rgb.to(DEV).contiguous(), w_a.to(DEV).contiguous())
+        out["d_params"] = d.cpu().numpy()
+    return out
+
+
+def _compare(mode, params, view_frame, W, H, bg, viewmats=None, Ks=None, seed_w=5, check_grad=True, **opts):
+    ora, _capi, batched, synth = _mods()
+    V = len(view_frame)
+    w_rgb, w_a = synth.cotangents(V, H, W, seed=seed_w)
+    got = _run_product(mode, params, view_frame, W, H, bg, viewmats, Ks, w_rgb, w_a, **opts)
+    want = ora.render_views(mode, params.numpy(), view_frame.numpy(), W, H, np.asarray(bg, np.float32),
+                            None if viewmats is None else viewmats.numpy(), None if Ks is None else Ks.numpy(),
+                            w_rgb.numpy(), w_a.numpy(), **opts)
+    sv = got["saved"]
+    info = sv.info()
+    N = params.shape[1]
+    # --- projection records: bit-exact
+    rec = torch.cat([sv.tap("rec0"), sv.tap("rec1"), sv.tap("rec2")], 1).cpu().numpy().reshape(V, N, 12)
+    touched = sv.tap("tiles_touched").cpu().numpy().reshape(V, N)
+    for v in range(V):
+        r_want, _ = records_from_oracle(mode, want["views"][v]["tab"])
+        assert np.array_equal(touched[v], want["views"][v]["tab"]["tiles"]), f"tiles_touched differ (view {v})"
+        assert np.array_equal(bits(rec[v]), bits(r_want)), f"splat records differ (view {v})"
+    # --- binning: bit-exact
+    assert int(info.n_isect) == len(want["keys"])
+    assert np.array_equal(sv.tap("isect_keys").cpu().numpy(), want["keys"]), "sorted keys differ"
+    assert np.array_equal(sv.tap("flatten_ids").cpu().numpy(), want["vals"]), "sorted values differ"
+    assert np.array_equal(sv.tap("tile_offsets").cpu().numpy(), want["offsets"]), "tile ranges differ"
+    # --- raster: counts bit-exact, images to tolerance
+    assert np.array_equal(got["n_contrib"], want["n_contrib"]), "per-pixel contributor counts differ"
+    last_want = np.stack([want["views"][v]["last"] + want["offsets"][v * (len(want["offsets"]) - 1) // V]
+                          for v in range(V)])
+    assert np.array_equal(sv.tap("last_ids").cpu().numpy(), last_want), "last ids differ"
+    assert np.abs(got["rgb"] - want["rgb"]).max() <= RGB_TOL
+    assert np.abs(got["alpha"] - want["alpha"]).max() <= RGB_TOL
+    if check_grad:
+        rel = column_rel_err(got["d_params"], want["d_params"])
+        assert rel.max() <= GRAD_TOL, f"gradient column errors {rel}"
+    return got, want
+
+
+def test_math_contract_bit_exact_on_device():
+    ora, _capi, _, _ = _mods()
+    x = np.concatenate([np.linspace(-30, 30, 100001), np.random.default_rng(0).normal(size=50000) * 200]).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    y = torch.empty(5, len(x), dtype=torch.float32, device=DEV)
+    dev = torch.device(DEV, torch.cuda.current_device())
+    _capi.check(_capi.load().ps_math_probe(_capi.context(dev), _capi.ptr(xd), len(x), _capi.ptr(y), _capi.stream_ptr(dev)), "probe")
+    torch.cuda.synchronize()
+    want = ora.math_probe(x)
+    y = y.cpu().numpy()
+    for k, name in enumerate(("exp", "log", "sigmoid", "sin", "cos")):
+        assert np.array_equal(bits(y[k]), bits(want[name])), name
+
+
+@pytest.mark.parametrize("cam,N,W,H", [(0, 500, 72, 64), (3, 3000, 288, 256), (1, 777, 100, 59)])
+def test_3d_single_view(cam, N, W, H):
+    _, _, _, synth = _mods()
+    vm, Ks = synth.ring_cameras(6, ds=1152.0 / W)
+    p = synth.gaussians_3d(N, 10 + cam)[None]
+    _compare("3d", p, torch.zeros(1, dtype=torch.int32), W, H, (1.0, 1.0, 1.0), vm[cam:cam + 1], Ks[cam:cam + 1])
+
+
+def test_3d_dense_overlap_early_stop_and_clamp():
+    _, _, _, synth = _mods()
+    W, H = 96, 80
+    vm, Ks = synth.ring_cameras(6, ds=12.0)
+    p = synth.gaussians_3d(1500, 77)
+    p[:, 3:6] += 1.0          # bigger splats: deep stacks, T falls below 1e-4
+    p[:200, 13] = 9.0         # opacity ~ 1 -> alpha clamp 0.999
+    got, want = _compare("3d", p[None], torch.zeros(1, dtype=torch.int32), W, H, (0.2, 0.5, 0.9), vm[2:3], Ks[2:3])
+    assert (want["alpha"] > 1 - 2e-4).any(), "case must exercise the early stop"
+
+
+def test_3d_batched_views_two_frames():
+    _, _, _, synth = _mods()
+    d = synth.make_views("c2", n_frames=2, n_cams=6, seed=3, n=1200)
+    _compare("3d", d["params"], d["view_frame"], d["width"], d["height"], (1.0, 1.0, 1.0), d["viewmats"], d["Ks"])
+
+
+def test_3d_adversarial_randn_eye_viewmat():
+    """The one 3D render the reference tests do (tests/test_gaussian_renderer.py:207-229): randn rows,
+    eye(4) viewmat, fx=fy=256: half behind the camera, some at z~0 with huge radii."""
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(1, 100, 14, generator=g)
+    K = torch.tensor([[[256.0, 0, 128], [0, 256.0, 128], [0, 0, 1]]])
+    _compare("3d", p, torch.zeros(1, dtype=torch.int32), 256, 256, (0.0, 0.0, 0.0), torch.eye(4)[None], K)
+
+
+def test_3d_radius_clip_legacy_splat_options():
+    _, _, _, synth = _mods()
+    vm, Ks = synth.ring_cameras(6, ds=8.0)
+    p = synth.gaussians_3d(800, 5)[None]
+    _compare("3d", p, torch.zeros(1, dtype=torch.int32), 144, 128, (1.0, 1.0, 1.0), vm[:1], Ks[:1], radius_clip=2.0)
+
+
+@pytest.mark.parametrize("name", ["ref2d_random_96x80", "ref2d_adversarial_70x50", "ref2d_c1_192x171",
+                                  "ref2d_dense_small_sigma_33x47"])
+def test_2d_against_reference_goldens(name):
+    """CUDA 2D path vs fixtures produced by running the reference class itself (make_golden.py)."""
+    z = np.load(GOLDEN / f"{name}.npz")
+    W, H = int(z["W"]), int(z["H"])
+    w_rgb, w_a = golden_cotangents(int(z["seed_w"]), H, W)
+    got = _run_product("2d", torch.from_numpy(z["params"])[None], torch.zeros(1, dtype=torch.int32), W, H, z["bg"],
+                       w_rgb=w_rgb[None], w_a=w_a[None])
+    assert np.abs(got["rgb"][0] - z["rgb"]).max() <= RGB_TOL
+    assert np.abs(got["alpha"][0] - z["alpha"]).max() <= RGB_TOL
+    rel = column_rel_err(got["d_params"][0], z["grad"])
+    assert rel.max() <= GRAD_TOL, rel
+
+
+@pytest.mark.parametrize("name", ["ref2d_random_96x80", "ref2d_adversarial_70x50", "ref2d_c1_192x171"])
+def test_2d_against_oracle_bit_exact_binning(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    _compare("2d", torch.from_numpy(z["params"])[None], torch.zeros(1, dtype=torch.int32), int(z["W"]), int(z["H"]), z["bg"])
+
+
+def test_2d_projected_views_batched():
+    _, _, _, synth = _mods()
+    d = synth.make_views("c3", n_frames=1, n_cams=3, seed=2, n=1500)
+    _compare("2d", d["params"], d["view_frame"], d["width"], d["height"], (1.0, 1.0, 1.0))
+
+
+def test_2d_shared_params_across_views_sums_gradients():
+    """The reference model feeds one [N,9] to every camera: gradients of the views add up."""
+    z = np.load(GOLDEN / "ref2d_random_96x80.npz")
+    p = torch.from_numpy(z["params"])[None]
+    _compare("2d", p, torch.zeros(3, dtype=torch.int32), int(z["W"]), int(z["H"]), z["bg"])
+
+
+@pytest.mark.parametrize("mode,P", [("2d", 9), ("3d", 14)])
+def test_empty_input_is_background(mode, P):
+    _, _, batched, _ = _mods()
+    bg = torch.tensor([0.25, 0.5, 0.75], device=DEV)
+    p = torch.zeros(1, 0, P, device=DEV)
+    rgb, alpha, counts, _ = batched.forward_raw(mode, p, torch.zeros(1, dtype=torch.int32, device=DEV),
+                                                torch.eye(4, device=DEV)[None], torch.eye(3, device=DEV)[None], bg, 50, 37,
+                                                0, True)
+    assert torch.allclose(rgb, bg.view(1, 1, 1, 3).expand_as(rgb), atol=1e-5)
+    assert float(alpha.abs().max()) == 0.0 and int(counts.max()) == 0
+
+
+def test_autograd_function_matches_raw_backward():
+    _, _, batched, synth = _mods()
+    d = synth.make_views("c2", 1, 2, seed=4, n=600)
+    p = d["params"].to(DEV).requires_grad_(True)
+    bg = torch.ones(3, device=DEV)
+    rgb, alpha = batched.render_views("3d", p, d["view_frame"].to(DEV), d["width"], d["height"], bg,
+                                      d["viewmats"].to(DEV), d["Ks"].to(DEV))
+    w_rgb, w_a = synth.cotangents(2, d["height"], d["width"], 9)
+    ((rgb * w_rgb.to(DEV)).sum() + (alpha * w_a.to(DEV)).sum()).backward()
+    got = _run_product("3d", d["params"], d["view_frame"], d["width"], d["height"], (1.0, 1.0, 1.0), d["viewmats"], d["Ks"],
+                       w_rgb, w_a)
+    rel = column_rel_err(p.grad.cpu().numpy(), got["d_params"])
+    assert rel.max() < 1e-4  # same kernels; only atomic ordering differs
