@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd rendered views/s of the renderer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c5_3d|c5_2d] [--frames F]
+    python bench.py --impl reference ...      # CPU arm: the oracle port on the box's host cores
+
+One "step" = forward + backward of F frames x 6 cameras of synthetic Gaussians through the
+C ABI (libpsplat.so).  `value` is measured with the inputs resident in HBM, on the device with
+CUDA events, max over ranks; `e2e` goes through the public API (render_views + autograd) from
+pinned HOST buffers with the host<->device copies inside the timed region.  N > 1: one process
+per GPU (torchrun), whole frames sharded across ranks (weak scaling, no data-path collective);
+--split-frames shards single views instead and all-reduces d_params over NCCL.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "fwd+bwd rendered views/s (6-cam, 576\u00d7512 2D / 288\u00d7256 3D GS) at 1/2/4/8 B200"
+FLOPS_PER_PAIR = {"raster_fwd": 27.0, "raster_bwd": 60.0}  # SURVEY.md 8d-d4 pair model (FP32 ops per evaluated pair)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", help="BASELINE.json config: c2 = 3D 288x256 (default), c3 = 2D 576x512")
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (x6 cameras = views); 0 = workload default")
+    ap.add_argument("--split-frames", action="store_true", help="shard views (not frames): NCCL all-reduce of d_params")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n", type=int, default=0, help="override Gaussians per frame (debug only; invalidates the metric)")
+    return ap.parse_args()
+
+
+FRAMES_DEFAULT = {"c1": 64, "c2": 64, "c3": 16, "c5_3d": 8, "c5_2d": 4}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: oracle port on host cores (the reference has no native build; its 3D arithmetic is gsplat CUDA)
+# ------------------------------------------------------------------------------------------
+def cpu_views_per_second(workload, n_views, threads, n_override=0):
+    """Times the CPU oracle (oracle/ps_oracle.c: the reference's algorithm restated in C) on `n_views` views
+    of the workload, `threads` views in flight (ctypes releases the GIL). Returns (views/s, seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as ora
+    from pose_splatter_b200 import synth
+    n_frames = max(1, (n_views + 5) // 6)
+    d = synth.make_views(workload, n_frames, 6, seed=99, n=n_override or None)
+    W, H, mode = d["width"], d["height"], d["mode"]
+    w_rgb, w_a = synth.cotangents(n_views, H, W, seed=5)
+    params = d["params"].numpy()
+    vf = d["view_frame"].numpy()
+    vms, Ks = d["viewmats"].numpy(), d["Ks"].numpy()
+    bg = np.ones(3, np.float32)
+    ora.lib()
+
+    def one(v):
+        ora.render(mode, params[int(vf[v])], W, H, bg, vms[v], Ks[v], w_rgb[v].numpy(), w_a[v].numpy())
+
+    one(0)  # warm-up (page in the library, first-touch)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(n_views)))
+    dt = time.perf_counter() - t0
+    return n_views / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wl = args.workload
+    per_step = max(cores, 6) if wl in ("c1", "c2") else max(2, min(cores, 6))
+    from pose_splatter_b200 import synth
+    cfg = synth.WORKLOADS[wl]
+    vals = []
+    for _ in range(args.warmup):
+        cpu_views_per_second(wl, min(per_step, cores), cores, args.n)
+    t_total, v_total = 0.0, 0
+    for _ in range(args.steps):
+        vps, dt = cpu_views_per_second(wl, per_step, cores, args.n)
+        vals.append(vps)
+        t_total += dt
+        v_total += per_step
+    value = v_total / t_total
+    sample = f"{per_step} views per step of workload {wl} (full size: N={args.n or cfg['n']}, {cfg['width']}x{cfg['height']}, fwd+bwd)"
+    out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": workload_name(wl), "views_per_step": per_step, "mode": cfg["mode"]},
+           "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "CPU oracle port (oracle/ps_oracle.c) of the reference algorithm on all host cores; the reference "
+                   "ships no native code and its 3D arithmetic (gsplat) is CUDA-only, so there is no reference CPU build"}
+    print(json.dumps(out), flush=True)
+
+
+def workload_name(wl):
+    from pose_splatter_b200 import synth
+    c = synth.WORKLOADS[wl]
+    idx = {"c1": 0, "c2": 1, "c3": 2, "c5_3d": 4, "c5_2d": 4}[wl]
+    return f"BASELINE.json configs[{idx}] ({wl}): {c['mode'].upper()} GS fwd+bwd, 6 cameras at {c['width']}x{c['height']}, N={c['n']} synthetic Gaussians per frame"
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pose_splatter_b200 import _capi, batched, synth
+    from pose_splatter_b200 import dist as psd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: pose_splatter_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    cfg = synth.WORKLOADS[wl]
+    mode, W, H = cfg["mode"], cfg["width"], cfg["height"]
+    F = args.frames or FRAMES_DEFAULT[wl]
+    n_cams = 6
+    n_sets = 4  # rotate distinct input batches so no step finds its inputs in L2
+
+    # --- synthetic inputs: rank r renders frames {r, r+world, ...} of a global sequence (weak scaling)
+    sets = []
+    for k in range(n_sets):
+        d = synth.make_views(wl, F, n_cams, seed=1000 * rank + k, n=args.n or None)
+        if args.split_frames and world > 1:
+            # every rank holds all frames' parameters but renders only its views (v % world == rank)
+            d = synth.make_views(wl, F, n_cams, seed=k, n=args.n or None)
+            mine = torch.tensor(psd.shard_views(F, n_cams, rank, world, "view"), dtype=torch.long)
+            if mode == "3d":
+                d["view_frame"], d["viewmats"], d["Ks"] = d["view_frame"][mine], d["viewmats"][mine], d["Ks"][mine]
+            else:
+                d["params"], d["view_frame"] = d["params"][mine], torch.arange(len(mine)).int()
+                d["viewmats"], d["Ks"] = d["viewmats"][mine], d["Ks"][mine]
+        sets.append(d)
+    V = int(sets[0]["view_frame"].shape[0])
+    host = [dict(params=s["params"].pin_memory(), view_frame=s["view_frame"].pin_memory(),
+                 viewmats=s["viewmats"].pin_memory(), Ks=s["Ks"].pin_memory()) for s in sets]
+    devs = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    bg = torch.ones(3, device=dev)
+    w_rgb, w_a = synth.cotangents(V, H, W, seed=7)
+    w_rgb, w_a = w_rgb.to(dev), w_a.to(dev)
+    need_reduce = args.split_frames and world > 1 and mode == "3d"
+    input_mb = sum(sum(t.numel() * t.element_size() for t in h.values()) for h in host) / 2**20
+
+    def step_resident(k):
+        s = devs[k % n_sets]
+        rgb, alpha, _, saved = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H,
+                                                   _capi.FLAG_SAVE_FOR_BACKWARD)
+        d_params = batched.backward_raw(saved, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, w_rgb, w_a)
+        saved.release()
+        if need_reduce:
+            psd.reduce_frame_grads(d_params)
+        return d_params
+
+    out_host = torch.empty_like(host[0]["params"]).pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+
+    def step_e2e(k):
+        h = host[k % n_sets]
+        p = h["params"].to(dev, non_blocking=True).requires_grad_(True)
+        vf = h["view_frame"].to(dev, non_blocking=True)
+        vm = h["viewmats"].to(dev, non_blocking=True)
+        Kd = h["Ks"].to(dev, non_blocking=True)
+        rgb, alpha = batched.render_views(mode, p, vf, W, H, bg, vm, Kd)
+        loss = (rgb * w_rgb).sum() + (alpha * w_a).sum()
+        loss.backward()
+        g = p.grad
+        if need_reduce:
+            psd.reduce_frame_grads(g)
+        out_host.copy_(g, non_blocking=True)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            _capi.set_profiling(dev, True)
+            _capi.stage_times(dev, reset=True)
+        l0 = _capi.launch_count(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            fn(k)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        stages = None
+        if profile:
+            stages = _capi.stage_times(dev, reset=True)
+            _capi.set_profiling(dev, False)
+        return psd.max_over_ranks(ms, dev), _capi.launch_count(dev) - l0, stages
+
+    for k in range(max(3, args.warmup)):
+        step_resident(k)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches, stages = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    for k in range(max(3, args.warmup)):
+        step_e2e(k)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # pair counts of one step (untimed) for the FP32 roofline of the rasterizers
+    s0 = devs[0]
+    _capi.raster_stats(dev, reset=True)
+    batched.forward_raw(mode, s0["params"], s0["view_frame"], s0["viewmats"], s0["Ks"], bg, W, H, _capi.FLAG_RASTER_STATS)
+    stats = _capi.raster_stats(dev, reset=True)
+    _, _, _, sv = batched.forward_raw(mode, s0["params"], s0["view_frame"], s0["viewmats"], s0["Ks"], bg, W, H,
+                                      _capi.FLAG_SAVE_FOR_BACKWARD)
+    info = sv.info()
+    M = int(info.n_isect)
+    sort_passes = int(info.sort_passes)
+    sv.release()
+    fp32_peak = _capi.fp32_peak_tflops(dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    views_total = V * world * args.steps
+    value = views_total / (ms_total * 1e-3)
+    e2e_value = views_total / (ms_e2e * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    stage_ms = {k: (v[0] / max(1, v[1]), v[1]) for k, v in stages.items()}  # average per launch
+    per_step = {k: v[0] / args.steps for k, v in stages.items()}
+    dom = max(("raster_fwd", "raster_bwd"), key=lambda k: per_step[k])
+    dom_ms = stage_ms[dom][0]
+    achieved_tf = stats["pairs_evaluated"] * FLOPS_PER_PAIR[dom] / (dom_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
+                "peak_source": "FFMA micro-benchmark run in this process (ps_fp32_peak_probe); no tensor cores on this path",
+                "work": f"{stats['pairs_evaluated']} evaluated (pixel,Gaussian) pairs per launch x {FLOPS_PER_PAIR[dom]:.0f} FP32 ops",
+                "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / args.steps)}
+    bits = 32 + info.tile_bits + info.view_bits - (0 if mode == "3d" else 32)
+    sort_bytes = M * (12 + 8 + 24 * sort_passes + 8)  # emit write + hist reads + scatter r/w per pass + range scan
+    sort_ms = stage_ms["emit"][0] + stage_ms["sort"][0] + stage_ms["ranges"][0]
+    proj_bytes = V * cfg["n"] * ((56 if mode == "3d" else 36) + 48 + 8 + 4)
+    roof_hbm = {"bound": "hbm", "kernel": "emit+radix_sort+tile_ranges", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": (sort_bytes / (sort_ms * 1e-3) / 1e9) / hbm_peak if sort_ms else None,
+                "traffic": None, "peak_source": hbm_src, "work": f"M={M} pairs, {sort_passes} radix passes over {bits} key bits",
+                "avg_launch_ms": sort_ms,
+                "project": {"achieved": proj_bytes / (stage_ms['project'][0] * 1e-3) / 1e9 if stage_ms['project'][0] else None,
+                            "unit": "GB/s", "avg_launch_ms": stage_ms["project"][0]}}
+    out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(wl), "mode": mode, "views_per_step_per_gpu": V, "frames_per_step_per_gpu": F,
+                      "cameras": n_cams, "gaussians_per_frame": args.n or cfg["n"], "isect_per_step": M,
+                      "parallelism": f"views sharded over {world} GPU(s), " + ("views split, NCCL all-reduce of d_params" if need_reduce else "whole frames per rank, no collective"),
+                      "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
+           "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / args.steps,
+                   "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0].values())),
+                   "d2h_bytes_per_step": int(out_host.numel() * 4 + 4)},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm,
+           "stage_ms_per_step": per_step, "pairs": stats, "fp32_peak_tflops": fp32_peak}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_views = cores * (4 if wl in ("c1", "c2") else 1)
+        vps, dt = cpu_views_per_second(wl, sample_views, cores, args.n)
+        out["cpu_baseline"] = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
+                               "sample": f"{sample_views} views of the same workload (full N, full resolution, fwd+bwd), {dt:.1f} s on {cores} threads"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

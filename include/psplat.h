@@ -28,6 +28,18 @@ extern "C" {
 
 #define PS_FLAG_SAVE_FOR_BACKWARD 1 /* keep the state ps_backward needs                        */
 #define PS_FLAG_KEEP_BINNING 2      /* also keep sort keys / unsorted pairs for the debug taps */
+#define PS_FLAG_RASTER_STATS 4      /* count (pixel, Gaussian) pairs in the forward rasterizer (bench only) */
+
+/* stages timed by ps_ctx_set_profiling (CUDA events on the launching stream) */
+#define PS_STAGE_PROJECT 0
+#define PS_STAGE_SCAN 1
+#define PS_STAGE_EMIT 2
+#define PS_STAGE_SORT 3
+#define PS_STAGE_RANGES 4
+#define PS_STAGE_RASTER_FWD 5
+#define PS_STAGE_RASTER_BWD 6
+#define PS_STAGE_PROJECT_BWD 7
+#define PS_N_STAGES 8
 
 /* what ps_saved_copy can read back (bit-exact parity taps) */
 #define PS_TAP_ISECT_KEYS 1    /* int64 [M]   sorted keys  view<<(32+tile_bits) | tile<<32 | low */
@@ -109,6 +121,20 @@ int ps_saved_release(ps_ctx *ctx, ps_saved *saved, void *stream);
 
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 int64_t ps_ctx_launch_count(const ps_ctx *ctx);
+
+/*
+ * Measurement hooks (bench.py).  With profiling on, every stage is bracketed by CUDA events on
+ * the launching stream; ps_ctx_stage_times synchronises, adds the finished intervals to
+ * ms[PS_N_STAGES] / calls[PS_N_STAGES] (totals since the last reset) and optionally resets.
+ */
+int ps_ctx_set_profiling(ps_ctx *ctx, int on);
+int ps_ctx_stage_times(ps_ctx *ctx, double *ms, int64_t *calls, int reset);
+/* pairs[0] = pairs evaluated (lane passed the warp-level cull and was still active),
+ * pairs[1] = contributing pairs, pairs[2] = tile-list entries walked by warps after culling,
+ * pairs[3] = tile-list entries staged; accumulated by forwards run with PS_FLAG_RASTER_STATS. */
+int ps_ctx_raster_stats(ps_ctx *ctx, uint64_t *pairs, int reset, void *stream);
+/* FP32 FFMA micro-benchmark on this device: returns achieved TFLOP/s (2 flops per FMA) in *tflops. */
+int ps_fp32_peak_probe(ps_ctx *ctx, double *tflops, void *stream);
 
 /*
  * Device probe of the arithmetic contract (PSM-1): y[5][n] = exp, log(|x|+1e-30), sigmoid, sin, cos

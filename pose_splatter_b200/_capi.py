@@ -17,7 +17,11 @@ TAPS = dict(isect_keys=1, flatten_ids=2, tile_offsets=3, last_ids=4, tiles_touch
 LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 
 EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy", "ps_forward", "ps_backward",
-           "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe")
+           "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
+           "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe")
+
+STAGES = ("project", "scan", "emit", "sort", "ranges", "raster_fwd", "raster_bwd", "project_bwd")
+FLAG_RASTER_STATS = 4
 
 
 class RenderDesc(ctypes.Structure):
@@ -63,6 +67,10 @@ def load() -> ctypes.CDLL:
     lib.ps_ctx_launch_count.argtypes = [vp]
     lib.ps_ctx_launch_count.restype = ctypes.c_int64
     lib.ps_math_probe.argtypes = [vp, vp, ip, vp, vp]
+    lib.ps_ctx_set_profiling.argtypes = [vp, ip]
+    lib.ps_ctx_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ip]
+    lib.ps_ctx_raster_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ip, vp]
+    lib.ps_fp32_peak_probe.argtypes = [vp, ctypes.POINTER(ctypes.c_double), vp]
     _lib = lib
     return lib
 
@@ -88,6 +96,31 @@ def context(device: torch.device) -> ctypes.c_void_p:
 
 def launch_count(device: torch.device) -> int:
     return int(load().ps_ctx_launch_count(context(device)))
+
+
+def set_profiling(device: torch.device, on: bool):
+    check(load().ps_ctx_set_profiling(context(device), int(on)), "ps_ctx_set_profiling")
+
+
+def stage_times(device: torch.device, reset: bool = True):
+    """{stage: (total ms, calls)} measured with CUDA events on the launching stream."""
+    ms = (ctypes.c_double * len(STAGES))()
+    calls = (ctypes.c_int64 * len(STAGES))()
+    check(load().ps_ctx_stage_times(context(device), ms, calls, int(reset)), "ps_ctx_stage_times")
+    return {name: (float(ms[i]), int(calls[i])) for i, name in enumerate(STAGES)}
+
+
+def raster_stats(device: torch.device, reset: bool = True):
+    out = (ctypes.c_uint64 * 4)()
+    check(load().ps_ctx_raster_stats(context(device), out, int(reset), stream_ptr(device)), "ps_ctx_raster_stats")
+    return dict(pairs_evaluated=int(out[0]), pairs_contributing=int(out[1]), entries_walked=int(out[2]),
+                entries_staged=int(out[3]))
+
+
+def fp32_peak_tflops(device: torch.device) -> float:
+    out = ctypes.c_double()
+    check(load().ps_fp32_peak_probe(context(device), ctypes.byref(out), stream_ptr(device)), "ps_fp32_peak_probe")
+    return float(out.value)
 
 
 def stream_ptr(device: torch.device) -> ctypes.c_void_p:

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "ps_contract.cuh"
 #include "ps_internal.h"
@@ -54,12 +55,43 @@ void dev_free(T *&p, cudaStream_t s)
 
 } // namespace
 
+struct PsSpan { int stage; cudaEvent_t a, b; };
+
 struct ps_ctx {
     int device;
     int64_t launches;
     int64_t *h_total; // pinned mailbox for M
     int64_t *d_total;
+    unsigned long long *d_stats; // [4] pair counters (PS_FLAG_RASTER_STATS)
+    bool profiling;
+    std::vector<PsSpan> pending;
+    std::vector<cudaEvent_t> spare;
+    double stage_ms[PS_N_STAGES];
+    int64_t stage_calls[PS_N_STAGES];
 };
+
+namespace {
+// brackets one stage with CUDA events on the launching stream when profiling is on
+struct StageTimer {
+    ps_ctx *ctx; cudaStream_t s; PsSpan span; bool on;
+    StageTimer(ps_ctx *c, int stage, cudaStream_t st) : ctx(c), s(st), on(c->profiling)
+    {
+        if (!on) return;
+        span.stage = stage;
+        for (cudaEvent_t *e : { &span.a, &span.b }) {
+            if (!ctx->spare.empty()) { *e = ctx->spare.back(); ctx->spare.pop_back(); }
+            else if (cudaEventCreate(e) != cudaSuccess) { on = false; return; }
+        }
+        cudaEventRecord(span.a, s);
+    }
+    ~StageTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(span.b, s);
+        ctx->pending.push_back(span);
+    }
+};
+} // namespace
 
 struct ps_saved {
     PsGeometry g;
@@ -97,8 +129,12 @@ int ps_ctx_create(int device, ps_ctx **out)
     if (!c) return fail(4, "ps_ctx_create: out of host memory");
     c->device = device;
     c->launches = 0;
+    c->profiling = false;
+    for (int i = 0; i < PS_N_STAGES; ++i) { c->stage_ms[i] = 0.0; c->stage_calls[i] = 0; }
     PS_CUDA(cudaMallocHost((void **)&c->h_total, sizeof(int64_t)));
     PS_CUDA(cudaMalloc((void **)&c->d_total, sizeof(int64_t)));
+    PS_CUDA(cudaMalloc((void **)&c->d_stats, 4 * sizeof(unsigned long long)));
+    PS_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
     // keep freed scratch in the pool instead of returning it to the driver between calls
     cudaMemPool_t pool;
     PS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -114,6 +150,9 @@ int ps_ctx_destroy(ps_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaFreeHost(ctx->h_total);
     cudaFree(ctx->d_total);
+    cudaFree(ctx->d_stats);
+    for (auto &sp : ctx->pending) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->spare) cudaEventDestroy(e);
     delete ctx;
     return 0;
 }
@@ -180,8 +219,8 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.block_sums, nblk + 1, s));
-            PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, s));
-            PS_TRY_LAUNCH(ps_launch_scan_block_sums(g, sv->t, ctx->d_total, s));
+            { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, s)); }
+            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_block_sums(g, sv->t, ctx->d_total, s)); }
             PS_TRY_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the sort
             sv->M = *ctx->h_total;
@@ -195,7 +234,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             PS_TRY_CUDA(dev_alloc(&keys_alt, (size_t)M, s));
             PS_TRY_CUDA(dev_alloc(&vals_alt, (size_t)M, s));
             PS_TRY_CUDA(dev_alloc(&hist, ps_sort_hist_elems(M), s));
-            PS_TRY_LAUNCH(ps_launch_emit(g, sv->t, sv->keys, sv->vals, s));
+            { StageTimer tm(ctx, PS_STAGE_EMIT, s); PS_TRY_LAUNCH(ps_launch_emit(g, sv->t, sv->keys, sv->vals, s)); }
             if (keep) {
                 PS_TRY_CUDA(dev_alloc(&sv->keys_raw, (size_t)M, s));
                 PS_TRY_CUDA(dev_alloc(&sv->vals_raw, (size_t)M, s));
@@ -205,13 +244,13 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             // 3D sorts depth bits + tile + view; 2D emits rows in order, so only tile + view bits
             const int bit_lo = (g.mode == PS_MODE_3D) ? 0 : 32;
             const int bit_hi = 32 + g.tile_bits + g.view_bits;
-            PS_TRY_LAUNCH(ps_launch_sort(sv->keys, sv->vals, keys_alt, vals_alt, M, bit_lo, bit_hi, hist, &sv->sort_passes, s));
+            { StageTimer tm(ctx, PS_STAGE_SORT, s); PS_TRY_LAUNCH(ps_launch_sort(sv->keys, sv->vals, keys_alt, vals_alt, M, bit_lo, bit_hi, hist, &sv->sort_passes, s)); }
             if (sv->sort_passes & 1) {
                 uint64_t *tk = sv->keys; sv->keys = keys_alt; keys_alt = tk;
                 uint32_t *tv = sv->vals; sv->vals = vals_alt; vals_alt = tv;
             }
         }
-        PS_TRY_LAUNCH(ps_launch_tile_ranges(g, sv->keys, M, sv->offsets, s));
+        { StageTimer tm(ctx, PS_STAGE_RANGES, s); PS_TRY_LAUNCH(ps_launch_tile_ranges(g, sv->keys, M, sv->offsets, s)); }
         if (npix > 0) {
             if (save) {
                 PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
@@ -219,8 +258,9 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             } else if (keep) {
                 PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             }
+            StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
             PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->vals, sv->offsets, background, rgb, alpha, n_contrib,
-                                               sv->last, sv->t_pen, s));
+                                               sv->last, sv->t_pen, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
         }
     }
 out:
@@ -260,10 +300,11 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
     int rc = 0;
     do {
         if (cudaMemsetAsync(acc, 0, VN * PS_ACC_STRIDE * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
-        int n = ps_launch_raster_bwd(g, sv->t, sv->vals, sv->offsets, background, sv->last, sv->t_pen, d_rgb, d_alpha, acc, s);
+        int n;
+        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->vals, sv->offsets, background, sv->last, sv->t_pen, d_rgb, d_alpha, acc, s); }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
-        n = ps_launch_project_bwd(g, params, view_frame, viewmats, Ks, sv->t, acc, d_params, s);
+        { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, view_frame, viewmats, Ks, sv->t, acc, d_params, s); }
         if (n < 0) { rc = fail(3, "ps_backward: project_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
     } while (0);
@@ -320,6 +361,74 @@ int ps_saved_release(ps_ctx *ctx, ps_saved *sv, void *stream)
     if (ctx) cudaSetDevice(ctx->device);
     saved_free(sv, (cudaStream_t)stream);
     delete sv;
+    return 0;
+}
+
+int ps_ctx_set_profiling(ps_ctx *ctx, int on)
+{
+    if (!ctx) return fail(1, "ps_ctx_set_profiling: NULL context");
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int ps_ctx_stage_times(ps_ctx *ctx, double *ms, int64_t *calls, int reset)
+{
+    if (!ctx) return fail(1, "ps_ctx_stage_times: NULL context");
+    PS_CUDA(cudaSetDevice(ctx->device));
+    for (auto &sp : ctx->pending) {
+        PS_CUDA(cudaEventSynchronize(sp.b));
+        float t = 0.0f;
+        PS_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ctx->stage_ms[sp.stage] += t;
+        ctx->stage_calls[sp.stage] += 1;
+        ctx->spare.push_back(sp.a);
+        ctx->spare.push_back(sp.b);
+    }
+    ctx->pending.clear();
+    for (int i = 0; i < PS_N_STAGES; ++i) {
+        if (ms) ms[i] = ctx->stage_ms[i];
+        if (calls) calls[i] = ctx->stage_calls[i];
+        if (reset) { ctx->stage_ms[i] = 0.0; ctx->stage_calls[i] = 0; }
+    }
+    return 0;
+}
+
+int ps_ctx_raster_stats(ps_ctx *ctx, uint64_t *pairs, int reset, void *stream)
+{
+    if (!ctx || !pairs) return fail(1, "ps_ctx_raster_stats: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_CUDA(cudaMemcpyAsync(pairs, ctx->d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (reset) PS_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(uint64_t), s));
+    PS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ps_fp32_peak_probe(ps_ctx *ctx, double *tflops, void *stream)
+{
+    if (!ctx || !tflops) return fail(1, "ps_fp32_peak_probe: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    float *sink = nullptr;
+    PS_CUDA(cudaMalloc((void **)&sink, sizeof(float)));
+    cudaEvent_t a, b;
+    PS_CUDA(cudaEventCreate(&a));
+    PS_CUDA(cudaEventCreate(&b));
+    const int iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) { // first reps warm the clocks
+        PS_CUDA(cudaEventRecord(a, s));
+        PS_LAUNCH(ctx, ps_launch_fp32_probe(sink, iters, s));
+        PS_CUDA(cudaEventRecord(b, s));
+        PS_CUDA(cudaEventSynchronize(b));
+        float ms = 0.0f;
+        PS_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 64.0 * iters * 256.0 * (148.0 * 8.0);
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    *tflops = best;
     return 0;
 }
 

@@ -42,9 +42,10 @@ int ps_launch_tile_ranges(const PsGeometry &g, const uint64_t *keys, int64_t M, 
 
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
                          const float *background, float *rgb, float *alpha, int32_t *n_contrib, int32_t *last,
-                         float *t_pen, cudaStream_t s);
+                         float *t_pen, unsigned long long *stats, cudaStream_t s);
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
                          const float *background, const int32_t *last, const float *t_pen, const float *d_rgb,
                          const float *d_alpha, float *acc, cudaStream_t s);
 
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);
+int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s);

@@ -75,12 +75,14 @@ __device__ __forceinline__ void stage_batch(const PsTable &t, const uint32_t *__
     }
 }
 
-template <int MODE>
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(256)
 raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                   const float *__restrict__ background, float *__restrict__ rgb, float *__restrict__ alpha,
-                  int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, float *__restrict__ t_pen)
+                  int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, float *__restrict__ t_pen,
+                  unsigned long long *__restrict__ stats)
 {
+    unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB];
     const TileCtx c = tile_ctx(g, offsets);
     const int lane = threadIdx.x & 31;
@@ -97,10 +99,12 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         const int nvalid = min(RB, c.end - first);
         stage_batch(t, vals, first, nvalid, s_r0, s_r1, s_r2, nullptr);
         __syncthreads();
+        if (STATS && threadIdx.x == 0) st_staged += nvalid;
         if (__all_sync(0xffffffffu, done)) continue;
         for (int k = 0; k * 32 < nvalid; ++k) {
             const int j = k * 32 + lane;
             uint32_t mask = __ballot_sync(0xffffffffu, j < nvalid && block_hit<MODE>(s_r0[j], c.bx, c.by));
+            if (STATS) { if (lane == 0) st_walk += __popc(mask); st_eval += done ? 0 : __popc(mask); }
             while (mask) {
                 const int e = k * 32 + __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -152,6 +156,22 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         if (n_contrib) n_contrib[p] = cnt;
         if (last) last[p] = lastpos;
         if (t_pen) t_pen[p] = Tpen;
+    }
+    if (STATS) {
+        // lanes that finish inside a group are still counted for the whole group: an upper bound
+        // within 32 pairs per (lane, termination), negligible against the totals
+        unsigned long long contributing = (unsigned long long)cnt;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            st_eval += __shfl_xor_sync(0xffffffffu, st_eval, d);
+            contributing += __shfl_xor_sync(0xffffffffu, contributing, d);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + 0, st_eval);
+            atomicAdd(stats + 1, contributing);
+            atomicAdd(stats + 2, st_walk);
+        }
+        if (threadIdx.x == 0) atomicAdd(stats + 3, st_staged);
     }
 }
 
@@ -332,14 +352,42 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
 
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
                          const float *background, float *rgb, float *alpha, int32_t *n_contrib, int32_t *last,
-                         float *t_pen, cudaStream_t s)
+                         float *t_pen, unsigned long long *stats, cudaStream_t s)
 {
     const unsigned grid = (unsigned)g.V * (unsigned)g.n_tiles;
     if (grid == 0) return 0;
-    if (g.mode == PS_MODE_3D)
-        raster_fwd_kernel<PS_MODE_3D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, rgb, alpha, n_contrib, last, t_pen);
-    else
-        raster_fwd_kernel<PS_MODE_2D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, rgb, alpha, n_contrib, last, t_pen);
+#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, rgb, alpha, n_contrib, last, t_pen, stats)
+    if (g.mode == PS_MODE_3D) { if (stats) PS_FWD(PS_MODE_3D, true); else PS_FWD(PS_MODE_3D, false); }
+    else { if (stats) PS_FWD(PS_MODE_2D, true); else PS_FWD(PS_MODE_2D, false); }
+#undef PS_FWD
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+namespace {
+// 8 independent FFMA chains per thread; 2 flops per FFMA
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float *sink, int iters)
+{
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+    const float m = 0.999f, c = 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = __fmaf_rn(a[i], m, c);
+        }
+    }
+    float r = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += a[i];
+    if (r == 123.456f) sink[0] = r;
+}
+} // namespace
+
+int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s)
+{
+    fp32_probe_kernel<<<148 * 8, 256, 0, s>>>(sink, iters);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
