@@ -274,7 +274,7 @@ def run_b200(args):
                                       _capi.FLAG_SAVE_FOR_BACKWARD)
     info = sv.info()
     M = int(info.n_isect)
-    sort_passes = int(info.sort_passes)
+    n_lists = int(info.n_lists)
     sv.release()
     fp32_peak = _capi.fp32_peak_tflops(dev)
 
@@ -302,13 +302,15 @@ def run_b200(args):
                 "peak_source": "FFMA micro-benchmark run in this process (ps_fp32_peak_probe); no tensor cores on this path",
                 "work": f"{stats['pairs_evaluated']} evaluated (pixel,Gaussian) pairs per launch x {FLOPS_PER_PAIR[dom]:.0f} FP32 ops",
                 "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / args.steps)}
-    bits = 32 + info.tile_bits + info.view_bits - (0 if mode == "3d" else 32)
-    sort_bytes = M * (12 + 8 + 24 * sort_passes + 8)  # emit write + hist reads + scatter r/w per pass + range scan
-    sort_ms = stage_ms["emit"][0] + stage_ms["sort"][0] + stage_ms["ranges"][0]
-    proj_bytes = V * cfg["n"] * ((56 if mode == "3d" else 36) + 48 + 8 + 4)
-    roof_hbm = {"bound": "hbm", "kernel": "emit+radix_sort+tile_ranges", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+    VN = V * (args.n or cfg["n"])
+    # rank: depth word + listed flag in, order + rank out; partition: rect + count + rank in, 4 B slot out per entry;
+    # list sort: slot in, order gather, 4 B value out per entry; scan: one int in/out per (view, tile)
+    sort_bytes = (VN * 16 if mode == "3d" else 0) + VN * 16 + M * 4 + M * 12 + 8 * V * info.tiles_x * info.tiles_y
+    sort_ms = stage_ms["rank"][0] + stage_ms["scan"][0] + stage_ms["partition"][0] + stage_ms["sort"][0]
+    proj_bytes = VN * ((56 if mode == "3d" else 36) + 48 + 8 + 4)
+    roof_hbm = {"bound": "hbm", "kernel": "depth_rank+scan+partition+list_sort", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "frac": (sort_bytes / (sort_ms * 1e-3) / 1e9) / hbm_peak if sort_ms else None,
-                "traffic": None, "peak_source": hbm_src, "work": f"M={M} pairs, {sort_passes} radix passes over {bits} key bits",
+                "traffic": None, "peak_source": hbm_src, "work": f"M={M} list entries in {n_lists} non-empty (view,tile) lists, {VN} (view,Gaussian) records",
                 "avg_launch_ms": sort_ms,
                 "project": {"achieved": proj_bytes / (stage_ms['project'][0] * 1e-3) / 1e9 if stage_ms['project'][0] else None,
                             "unit": "GB/s", "avg_launch_ms": stage_ms["project"][0]}}

@@ -21,28 +21,29 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 1
+#define PS_ABI_VERSION 2
 
 #define PS_MODE_2D 2 /* GaussianRenderer2D, rows of 9 floats  (src/gaussian_renderer.py:214-334) */
 #define PS_MODE_3D 3 /* GaussianRenderer3D, rows of 14 floats (src/gaussian_renderer.py:110-211) */
 
 #define PS_FLAG_SAVE_FOR_BACKWARD 1 /* keep the state ps_backward needs                        */
-#define PS_FLAG_KEEP_BINNING 2      /* also keep sort keys / unsorted pairs for the debug taps */
+#define PS_FLAG_KEEP_BINNING 2      /* also materialise the sorted int64 keys and keep last ids for the debug taps */
 #define PS_FLAG_RASTER_STATS 4      /* count (pixel, Gaussian) pairs in the forward rasterizer (bench only) */
 
 /* stages timed by ps_ctx_set_profiling (CUDA events on the launching stream) */
-#define PS_STAGE_PROJECT 0
-#define PS_STAGE_SCAN 1
-#define PS_STAGE_EMIT 2
-#define PS_STAGE_SORT 3
-#define PS_STAGE_RANGES 4
-#define PS_STAGE_RASTER_FWD 5
+#define PS_STAGE_PROJECT 0     /* activations + projection + per-(view,tile) list lengths            */
+#define PS_STAGE_RANK 1        /* 3D: per-view depth ranking                                         */
+#define PS_STAGE_SCAN 2        /* list lengths -> tile ranges, M                                     */
+#define PS_STAGE_PARTITION 3   /* Gaussians -> lists                                                 */
+#define PS_STAGE_SORT 4        /* work list + per-list sort by depth rank / row index                */
+#define PS_STAGE_RASTER_FWD 5  /* background fill of empty tiles + forward rasterizer                */
 #define PS_STAGE_RASTER_BWD 6
 #define PS_STAGE_PROJECT_BWD 7
 #define PS_N_STAGES 8
 
 /* what ps_saved_copy can read back (bit-exact parity taps) */
-#define PS_TAP_ISECT_KEYS 1    /* int64 [M]   sorted keys  view<<(32+tile_bits) | tile<<32 | low */
+#define PS_TAP_ISECT_KEYS 1    /* int64 [M]   sorted keys  view<<(32+tile_bits) | tile<<32 | low (low = depth bits in 3D, row in 2D);
+                                  implied by the lists, materialised for this tap (PS_FLAG_KEEP_BINNING)  */
 #define PS_TAP_FLATTEN_IDS 2   /* int32 [M]   sorted values view*N + gaussian                     */
 #define PS_TAP_TILE_OFFSETS 3  /* int32 [V*n_tiles + 1] first sorted index of every (view, tile)  */
 #define PS_TAP_LAST_IDS 4      /* int32 [V,H,W] 1 + index of last contributing entry              */
@@ -50,8 +51,6 @@ extern "C" {
 #define PS_TAP_REC0 6          /* float4 [V*N] 3D: x,y,rx,ry     2D: u,v,rect(lo),rect(hi)        */
 #define PS_TAP_REC1 7          /* float4 [V*N] 3D: A,B,C,opacity 2D: cos,sin,iax,iay             */
 #define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,depth   2D: r,g,b,opacity               */
-#define PS_TAP_UNSORTED_KEYS 9 /* int64 [M] emission order                                       */
-#define PS_TAP_UNSORTED_IDS 10 /* int32 [M] emission order                                       */
 
 typedef struct ps_ctx ps_ctx;     /* per-device context (stream-ordered scratch pool, pinned mailbox) */
 typedef struct ps_saved ps_saved; /* state of one forward kept for its backward / taps               */
@@ -76,7 +75,7 @@ typedef struct ps_saved_info {
     int32_t view_bits;
     int32_t tiles_x, tiles_y;
     int32_t n_views, n_gauss, n_frames, mode, width, height;
-    int32_t sort_passes; /* radix passes executed                                             */
+    int32_t n_lists;   /* non-empty (view, tile) lists                                        */
     int32_t reserved;
 } ps_saved_info;
 

@@ -11,8 +11,7 @@ import torch
 
 MODE_2D, MODE_3D = 2, 3
 FLAG_SAVE_FOR_BACKWARD, FLAG_KEEP_BINNING = 1, 2
-TAPS = dict(isect_keys=1, flatten_ids=2, tile_offsets=3, last_ids=4, tiles_touched=5, rec0=6, rec1=7, rec2=8,
-            unsorted_keys=9, unsorted_ids=10)
+TAPS = dict(isect_keys=1, flatten_ids=2, tile_offsets=3, last_ids=4, tiles_touched=5, rec0=6, rec1=7, rec2=8)
 
 LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 
@@ -20,7 +19,7 @@ EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy",
            "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
            "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe")
 
-STAGES = ("project", "scan", "emit", "sort", "ranges", "raster_fwd", "raster_bwd", "project_bwd")
+STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd")
 FLAG_RASTER_STATS = 4
 
 
@@ -35,7 +34,7 @@ class SavedInfo(ctypes.Structure):
     _fields_ = [("n_isect", ctypes.c_int64), ("tile_bits", ctypes.c_int32), ("view_bits", ctypes.c_int32),
                 ("tiles_x", ctypes.c_int32), ("tiles_y", ctypes.c_int32), ("n_views", ctypes.c_int32),
                 ("n_gauss", ctypes.c_int32), ("n_frames", ctypes.c_int32), ("mode", ctypes.c_int32),
-                ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("sort_passes", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("n_lists", ctypes.c_int32),
                 ("reserved", ctypes.c_int32)]
 
 

@@ -1,0 +1,426 @@
+// ps_bin.cu -- tile binning (SURVEY.md 2.2 K2'-K4'): builds, for every (view, tile), the list of
+// Gaussians sorted by (depth bits | row index), i.e. exactly the order gsplat's
+// isect_tiles + cub::DeviceRadixSort(int64 key = view|tile|depth) + isect_offset_encode produce --
+// without ever sorting 12-byte (key, value) pairs over M = sum(tiles touched):
+//
+//   depth_rank   (3D) one CTA per view: stable LSD radix sort of the view's N depth words in shared
+//                memory (skipping the digits above the highest differing bit) -> order[], rank[]
+//   scan_lists   exclusive scan of the per-(view,tile) counts the projection kernel histogrammed
+//                -> tile ranges (offsets), M, list size classes            [this IS isect_offsets]
+//   partition    every Gaussian drops its depth rank (3D) / row index (2D) into the lists of the
+//                tiles it touches (CTA-aggregated reservations, order inside a list arbitrary)
+//   sort_lists   per non-empty list: the ranks are unique integers < N, so a bitmap in shared
+//                memory + popcount prefix sorts them; writes vals = view*N + gaussian
+//   worklist     non-empty lists ordered longest class first (launch order of the rasterizers)
+//
+// Equal depth words keep Gaussian order (stable ranking) like the stable radix sort of the reference
+// path.  HBM traffic: 4 B written + 4 B read + 4 B written per list entry instead of 12 B x 2 x 7 passes.
+// The sorted int64 keys are implied by (list id, depth word of vals[i]); ps_launch_debug_keys
+// materialises them for the bit-exact parity taps only.
+#include "ps_contract.cuh"
+#include "ps_internal.h"
+
+namespace {
+
+constexpr int RT = PS_RANK_THREADS;
+constexpr int RW = RT / 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+// exclusive scan of s[0..255] in place, result total returned to every thread; all RT threads call
+__device__ __forceinline__ uint32_t scan256_exclusive(uint32_t *s, uint32_t *s_tmp)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t v = 0, incl = 0;
+    if (tid < 256) {
+        v = s[tid];
+        incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t n = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) s_tmp[wid] = incl;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        uint32_t pre = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) pre += (w < wid) ? s_tmp[w] : 0u;
+        s[tid] = pre + incl - v;
+    }
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) total += s_tmp[w];
+    __syncthreads();
+    return total;
+}
+
+// One CTA per view.  IdT = uint16_t with the ping-pong buffers in dynamic shared memory,
+// uint32_t with them in global scratch (N too large for shared memory).
+template <typename IdT>
+__global__ void __launch_bounds__(RT)
+depth_rank_kernel(int N, const float4 *__restrict__ rec2, const int32_t *__restrict__ touched,
+                  uint32_t *__restrict__ order, uint32_t *__restrict__ rank, uint32_t *gscratch)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ uint32_t s_hist[256], s_tot[256], s_tmp[8], s_minmax[2];
+    __shared__ uint16_t s_wcnt[RW][256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t base = (size_t)blockIdx.x * N;
+    uint32_t *k[2];
+    IdT *id[2];
+    if (gscratch) {
+        uint32_t *p = gscratch + (size_t)blockIdx.x * 4 * N;
+        k[0] = p; k[1] = p + N;
+        id[0] = reinterpret_cast<IdT *>(p + 2 * (size_t)N); id[1] = reinterpret_cast<IdT *>(p + 3 * (size_t)N);
+    } else {
+        k[0] = reinterpret_cast<uint32_t *>(dyn); k[1] = k[0] + N;
+        id[0] = reinterpret_cast<IdT *>(k[1] + N); id[1] = id[0] + N;
+    }
+    if (tid == 0) { s_minmax[0] = 0xffffffffu; s_minmax[1] = 0u; }
+    __syncthreads();
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int i = tid; i < N; i += RT) {
+        const bool listed = touched[base + i] > 0;
+        const uint32_t key = listed ? __float_as_uint(rec2[base + i].w) : 0xffffffffu;
+        k[0][i] = key;
+        id[0][i] = (IdT)i;
+        if (listed) { mn = min(mn, key); mx = max(mx, key); }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(FULL, mn, d));
+        mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+    }
+    if (lane == 0) { atomicMin(&s_minmax[0], mn); atomicMax(&s_minmax[1], mx); }
+    __syncthreads();
+    mn = s_minmax[0]; mx = s_minmax[1];
+    // digits above the highest bit in which two listed depth words differ cannot change the order
+    const uint32_t diff = (mx >= mn) ? (mn ^ mx) : 0u;
+    const int npass = diff ? (32 - __clz(diff) + 7) / 8 : 0;
+    for (int p = 0; p < npass; ++p) {
+        const int shift = 8 * p;
+        const uint32_t *kin = k[p & 1];
+        const IdT *iin = id[p & 1];
+        uint32_t *kout = k[(p + 1) & 1];
+        IdT *iout = id[(p + 1) & 1];
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < N; i += RT) atomicAdd(&s_hist[(kin[i] >> shift) & 255u], 1u);
+        __syncthreads();
+        scan256_exclusive(s_hist, s_tmp);
+        for (int c0 = 0; c0 < N; c0 += RT) {
+            const int i = c0 + tid;
+            const bool live = i < N;
+            uint32_t key = 0, digit = 0, r = 0;
+            IdT idv = 0;
+            // clear this warp's row of the per-warp digit counts (512 B = 4 words per lane)
+            uint32_t *row = reinterpret_cast<uint32_t *>(&s_wcnt[wid][0]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) row[lane + 32 * q] = 0u;
+            __syncwarp();
+            const uint32_t live_mask = __ballot_sync(FULL, live);
+            if (live) {
+                key = kin[i];
+                idv = iin[i];
+                digit = (key >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(live_mask, digit);
+                r = __popc(peers & ((1u << lane) - 1u));
+                if (r == 0) s_wcnt[wid][digit] = (uint16_t)__popc(peers);
+            }
+            __syncthreads();
+            if (tid < 256) { // exclusive prefix of this digit's counts over the 32 warps (stable: warp order)
+                uint32_t run = 0;
+#pragma unroll 8
+                for (int w = 0; w < RW; ++w) {
+                    const uint32_t c = s_wcnt[w][tid];
+                    s_wcnt[w][tid] = (uint16_t)run;
+                    run += c;
+                }
+                s_tot[tid] = run;
+            }
+            __syncthreads();
+            if (live) {
+                const uint32_t pos = s_hist[digit] + s_wcnt[wid][digit] + r;
+                kout[pos] = key;
+                iout[pos] = idv;
+            }
+            __syncthreads();
+            if (tid < 256) s_hist[tid] += s_tot[tid];
+        }
+        __syncthreads();
+    }
+    const IdT *fin = id[npass & 1];
+    for (int r = tid; r < N; r += RT) {
+        const uint32_t gid = (uint32_t)fin[r];
+        order[base + r] = gid;
+        rank[base + gid] = (uint32_t)r;
+    }
+}
+
+// one CTA: exclusive scan of T counts in place, size-class histogram of the non-empty lists
+__global__ void __launch_bounds__(1024)
+scan_lists_kernel(int32_t *__restrict__ offsets, int T, int32_t *__restrict__ cls, int64_t *__restrict__ mailbox)
+{
+    __shared__ long long s_part[1024];
+    __shared__ int s_cls[PS_N_CLASSES];
+    __shared__ int s_nz;
+    const int tid = threadIdx.x;
+    if (tid < PS_N_CLASSES) s_cls[tid] = 0;
+    if (tid == 0) s_nz = 0;
+    __syncthreads();
+    const int per = (T + 1023) / 1024;
+    const int lo = min(T, tid * per), hi = min(T, lo + per);
+    long long acc = 0;
+    int nz = 0;
+    for (int i = lo; i < hi; ++i) {
+        const int c = offsets[i];
+        acc += c;
+        if (c > 0) { ++nz; atomicAdd(&s_cls[31 - __clz(c)], 1); }
+    }
+    s_part[tid] = acc;
+    if (nz) atomicAdd(&s_nz, nz);
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const long long add = tid >= d ? s_part[tid - d] : 0;
+        __syncthreads();
+        s_part[tid] += add;
+        __syncthreads();
+    }
+    long long run = s_part[tid] - acc;
+    for (int i = lo; i < hi; ++i) {
+        const int c = offsets[i];
+        offsets[i] = (int32_t)run;
+        run += c;
+    }
+    if (tid == 1023) {
+        const long long total = s_part[1023];
+        offsets[T] = (int32_t)(total > 0x7fffffffLL ? 0x7fffffffLL : total);
+        mailbox[0] = total;
+        mailbox[1] = s_nz;
+    }
+    if (tid == 0) { // class bases, longest class first; fill counters zeroed
+        int r = 0;
+        for (int c = PS_N_CLASSES - 1; c >= 0; --c) {
+            cls[c] = r;
+            r += s_cls[c];
+            cls[PS_N_CLASSES + c] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+build_worklist_kernel(const int32_t *__restrict__ offsets, int T, int32_t *__restrict__ cls, int32_t *__restrict__ worklist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = i < T ? offsets[i + 1] - offsets[i] : 0;
+    const uint32_t mask = __ballot_sync(FULL, c > 0);
+    if (c > 0) {
+        const int kcls = 31 - __clz(c);
+        const uint32_t peers = __match_any_sync(mask, kcls);
+        const int leader = __ffs(peers) - 1;
+        int b = 0;
+        if (lane == leader) b = atomicAdd(&cls[PS_N_CLASSES + kcls], __popc(peers));
+        b = __shfl_sync(peers, b, leader);
+        worklist[cls[kcls] + b + __popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PS_PROJ_BLOCK)
+partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, int32_t *__restrict__ fill,
+                 uint32_t *__restrict__ slots, int use_smem)
+{
+    extern __shared__ int s_dyn[]; // [2 * n_tiles] when use_smem
+    const int v = blockIdx.y;
+    const int gi = blockIdx.x * PS_PROJ_BLOCK + threadIdx.x;
+    const bool live = gi < g.N;
+    const size_t idx = (size_t)v * g.N + (live ? gi : 0);
+    const int touched = live ? t.tiles_touched[idx] : 0;
+    int tx0 = 0, ty0 = 0, tx1 = 0, ty1 = 0;
+    uint32_t val = 0;
+    if (touched) {
+        const uint2 tr = t.tile_rect[idx];
+        tx0 = tr.x & 0xffff; ty0 = tr.x >> 16; tx1 = tr.y & 0xffff; ty1 = tr.y >> 16;
+        val = (MODE == PS_MODE_3D) ? t.rank[idx] : (uint32_t)gi;
+    }
+    const int32_t *off_v = offsets + (size_t)v * g.n_tiles;
+    int32_t *fill_v = fill + (size_t)v * g.n_tiles;
+    if (!use_smem) { // very large tile grids: reserve every slot with a global atomic
+        for (int ty = ty0; ty < ty1; ++ty)
+            for (int tx = tx0; tx < tx1; ++tx) {
+                const int tl = ty * g.tiles_x + tx;
+                slots[off_v[tl] + atomicAdd(&fill_v[tl], 1)] = val;
+            }
+        return;
+    }
+    int *s_cnt = s_dyn, *s_base = s_dyn + g.n_tiles;
+    for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) s_cnt[i] = 0;
+    __syncthreads();
+    for (int ty = ty0; ty < ty1; ++ty)
+        for (int tx = tx0; tx < tx1; ++tx) atomicAdd(&s_cnt[ty * g.tiles_x + tx], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) {
+        const int c = s_cnt[i];
+        if (c) {
+            s_base[i] = off_v[i] + atomicAdd(&fill_v[i], c); // one reservation per (CTA, tile)
+            s_cnt[i] = 0;
+        }
+    }
+    __syncthreads();
+    for (int ty = ty0; ty < ty1; ++ty)
+        for (int tx = tx0; tx < tx1; ++tx) {
+            const int tl = ty * g.tiles_x + tx;
+            slots[s_base[tl] + atomicAdd(&s_cnt[tl], 1)] = val;
+        }
+}
+
+__device__ __forceinline__ int block_exclusive_scan_256i(int v, int *s_warp)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int pre = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) pre += (w < wid) ? s_warp[w] : 0;
+    return pre + incl - v;
+}
+
+// One CTA per non-empty list: unique keys < N -> bitmap sort.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_t *__restrict__ offsets,
+                  const int32_t *__restrict__ worklist, const uint32_t *__restrict__ slots, uint32_t *__restrict__ vals)
+{
+    extern __shared__ uint32_t s_bm[]; // [(N + 31) / 32]
+    __shared__ int s_warp[8];
+    const int lin = worklist[blockIdx.x];
+    const int start = offsets[lin], end = offsets[lin + 1];
+    const int view = lin / g.n_tiles;
+    const int words = (g.N + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += 256) s_bm[w] = 0u;
+    __syncthreads();
+    for (int i = start + threadIdx.x; i < end; i += 256) {
+        const uint32_t r = slots[i];
+        atomicOr(&s_bm[r >> 5], 1u << (r & 31u));
+    }
+    __syncthreads();
+    const int wpt = (words + 255) / 256;
+    const int w0 = min(words, (int)threadIdx.x * wpt), w1 = min(words, w0 + wpt);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(s_bm[w]);
+    int out = start + block_exclusive_scan_256i(cnt, s_warp);
+    const uint32_t vbase = (uint32_t)view * (uint32_t)g.N;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = s_bm[w];
+        while (bits) {
+            const uint32_t r = (uint32_t)(w << 5) + (uint32_t)(__ffs(bits) - 1);
+            bits &= bits - 1;
+            const uint32_t gid = (MODE == PS_MODE_3D) ? __ldg(order + vbase + r) : r;
+            vals[out++] = vbase + gid;
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+debug_keys_kernel(PsGeometry g, const float4 *__restrict__ rec2, const int32_t *__restrict__ offsets,
+                  const int32_t *__restrict__ worklist, const uint32_t *__restrict__ vals, uint64_t *__restrict__ keys)
+{
+    const int lin = worklist[blockIdx.x];
+    const int start = offsets[lin], end = offsets[lin + 1];
+    const int view = lin / g.n_tiles, tile = lin - view * g.n_tiles;
+    const uint64_t hi = (((uint64_t)view << g.tile_bits) | (uint64_t)tile) << 32;
+    for (int i = start + threadIdx.x; i < end; i += 256) {
+        const uint32_t id = vals[i];
+        const uint32_t low = (MODE == PS_MODE_3D) ? __float_as_uint(rec2[id].w) : id - (uint32_t)view * (uint32_t)g.N;
+        keys[i] = hi | low;
+    }
+}
+
+size_t rank_smem_bytes(int N) { return (size_t)N * 12; }
+constexpr size_t RANK_STATIC_SMEM = 256 * 4 * 2 + 8 * 4 + 8 + RW * 256 * 2;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+} // namespace
+
+size_t ps_rank_scratch_elems(const PsGeometry &g)
+{
+    if (g.mode != PS_MODE_3D || g.N == 0 || g.V == 0) return 0;
+    if (g.N <= 65535 && rank_smem_bytes(g.N) + RANK_STATIC_SMEM + 1024 <= SMEM_LIMIT) return 0;
+    return (size_t)g.V * 4 * (size_t)g.N;
+}
+
+int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, cudaStream_t s)
+{
+    if (g.mode != PS_MODE_3D || g.N == 0 || g.V == 0) return 0;
+    if (ps_rank_scratch_elems(g) == 0) {
+        const size_t dyn = rank_smem_bytes(g.N);
+        if (cudaFuncSetAttribute(depth_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+            return -1;
+        depth_rank_kernel<uint16_t><<<g.V, RT, dyn, s>>>(g.N, t.rec2, t.tiles_touched, t.order, t.rank, nullptr);
+    } else {
+        if (!scratch) return -1;
+        depth_rank_kernel<uint32_t><<<g.V, RT, 0, s>>>(g.N, t.rec2, t.tiles_touched, t.order, t.rank, scratch);
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, int64_t *mailbox, cudaStream_t s)
+{
+    scan_lists_kernel<<<1, 1024, 0, s>>>(l.offsets, g.V * g.n_tiles, l.cls, mailbox);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s)
+{
+    if (g.N == 0 || g.V == 0) return 0;
+    dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
+    const int use_smem = g.n_tiles <= PS_HIST_SMEM_TILES;
+    const size_t dyn = use_smem ? (size_t)2 * g.n_tiles * sizeof(int) : 0;
+    if (g.mode == PS_MODE_3D) {
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        partition_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);
+    } else {
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        partition_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t s)
+{
+    const int T = g.V * g.n_tiles;
+    if (T == 0) return 0;
+    build_worklist_kernel<<<(T + 255) / 256, 256, 0, s>>>(l.offsets, T, l.cls, l.worklist);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
+{
+    if (n_work <= 0) return 0;
+    const size_t dyn = (size_t)((g.N + 31) / 32) * sizeof(uint32_t);
+    if (g.mode == PS_MODE_3D) {
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        sort_lists_kernel<PS_MODE_3D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals);
+    } else {
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        sort_lists_kernel<PS_MODE_2D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals);
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint64_t *keys, cudaStream_t s)
+{
+    if (n_work <= 0) return 0;
+    if (g.mode == PS_MODE_3D) debug_keys_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t.rec2, l.offsets, l.worklist, l.vals, keys);
+    else debug_keys_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t.rec2, l.offsets, l.worklist, l.vals, keys);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}

@@ -1,6 +1,7 @@
 // ps_capi.cu -- C ABI of libpsplat.so (include/psplat.h): context, stream-ordered scratch,
-// and the stage orchestration  project -> scan -> [M to host] -> emit -> radix sort ->
-// tile ranges -> rasterize  (forward)  /  rasterize-backward -> projection-backward.
+// and the stage orchestration  project(+tile histogram) -> depth rank -> scan [M to host] ->
+// partition -> per-list bitmap sort -> fill empty tiles -> rasterize  (forward)  /
+// rasterize-backward -> projection-backward.
 // No torch types, no CPU fallback: every entry point needs a CUDA device.
 #include <stdarg.h>
 #include <stdio.h>
@@ -60,7 +61,7 @@ struct PsSpan { int stage; cudaEvent_t a, b; };
 struct ps_ctx {
     int device;
     int64_t launches;
-    int64_t *h_total; // pinned mailbox for M
+    int64_t *h_total; // pinned mailbox: [0] = M, [1] = number of non-empty lists
     int64_t *d_total;
     unsigned long long *d_stats; // [4] pair counters (PS_FLAG_RASTER_STATS)
     bool profiling;
@@ -96,15 +97,12 @@ struct StageTimer {
 struct ps_saved {
     PsGeometry g;
     PsTable t;
+    PsLists l;
     int64_t M;
-    int sort_passes;
-    uint64_t *keys;     // sorted (kept only with PS_FLAG_KEEP_BINNING)
-    uint32_t *vals;     // sorted
-    uint64_t *keys_raw; // emission order (debug)
-    uint32_t *vals_raw;
-    int32_t *offsets;   // [V*n_tiles + 1]
-    int32_t *last;      // [V,H,W]
-    float *t_pen;       // [V,H,W]
+    int n_work;     // non-empty (view, tile) lists
+    uint64_t *keys; // sorted int64 keys, materialised only with PS_FLAG_KEEP_BINNING
+    int32_t *last;  // [V,H,W]
+    float *t_pen;   // [V,H,W]
 };
 
 extern "C" {
@@ -131,8 +129,8 @@ int ps_ctx_create(int device, ps_ctx **out)
     c->launches = 0;
     c->profiling = false;
     for (int i = 0; i < PS_N_STAGES; ++i) { c->stage_ms[i] = 0.0; c->stage_calls[i] = 0; }
-    PS_CUDA(cudaMallocHost((void **)&c->h_total, sizeof(int64_t)));
-    PS_CUDA(cudaMalloc((void **)&c->d_total, sizeof(int64_t)));
+    PS_CUDA(cudaMallocHost((void **)&c->h_total, 2 * sizeof(int64_t)));
+    PS_CUDA(cudaMalloc((void **)&c->d_total, 2 * sizeof(int64_t)));
     PS_CUDA(cudaMalloc((void **)&c->d_stats, 4 * sizeof(unsigned long long)));
     PS_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
     // keep freed scratch in the pool instead of returning it to the driver between calls
@@ -162,9 +160,10 @@ int64_t ps_ctx_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches : 0;
 static void saved_free(ps_saved *sv, cudaStream_t s)
 {
     dev_free(sv->t.rec0, s); dev_free(sv->t.rec1, s); dev_free(sv->t.rec2, s);
-    dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.block_sums, s);
-    dev_free(sv->keys, s); dev_free(sv->vals, s); dev_free(sv->keys_raw, s); dev_free(sv->vals_raw, s);
-    dev_free(sv->offsets, s); dev_free(sv->last, s); dev_free(sv->t_pen, s);
+    dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
+    dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
+    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s);
+    dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->t_pen, s);
 }
 
 int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
@@ -201,56 +200,59 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
     g.near_plane = d->near_plane; g.far_plane = d->far_plane; g.radius_clip = d->radius_clip; g.eps2d = d->eps2d;
 
     int rc = 0;
-    uint64_t *keys_alt = nullptr;
-    uint32_t *vals_alt = nullptr, *hist = nullptr;
+    uint32_t *rank_scratch = nullptr;
     // everything below jumps to `out` on error so scratch is always returned to the pool
-#define PS_TRY(expr) do { rc = (expr); if (rc) goto out; } while (0)
 #define PS_TRY_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); goto out; } } while (0)
 #define PS_TRY_LAUNCH(call) do { int n_ = (call); if (n_ < 0) { rc = fail(3, "kernel launch failed in %s: %s", #call, cudaGetErrorString(cudaGetLastError())); goto out; } ctx->launches += n_; } while (0)
     {
         const size_t VN = (size_t)g.V * g.N;
-        const size_t nblk = (size_t)g.V * ((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK);
+        const size_t T = (size_t)g.V * g.n_tiles;
         const size_t npix = (size_t)g.V * g.H * g.W;
+        if (T > 0x7ffffff0ULL) { rc = fail(1, "ps_forward: %zu (view, tile) lists exceed 2^31", T); goto out; }
+        if (g.N > (1 << 20)) { rc = fail(1, "ps_forward: at most 2^20 Gaussians per frame (got %d)", g.N); goto out; }
         sv->M = 0;
+        sv->n_work = 0;
+        PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1, s));
+        PS_TRY_CUDA(dev_alloc(&sv->l.cls, (size_t)2 * PS_N_CLASSES, s));
+        PS_TRY_CUDA(cudaMemsetAsync(sv->l.offsets, 0, (T + 1) * sizeof(int32_t), s));
         if (VN > 0) {
             PS_TRY_CUDA(dev_alloc(&sv->t.rec0, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.rec1, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.rec2, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
-            PS_TRY_CUDA(dev_alloc(&sv->t.block_sums, nblk + 1, s));
-            { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, s)); }
-            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_block_sums(g, sv->t, ctx->d_total, s)); }
-            PS_TRY_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the sort
-            sv->M = *ctx->h_total;
+            { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, sv->l.offsets, s)); }
+            if (g.mode == PS_MODE_3D) {
+                PS_TRY_CUDA(dev_alloc(&sv->t.order, VN, s));
+                PS_TRY_CUDA(dev_alloc(&sv->t.rank, VN, s));
+                const size_t ns = ps_rank_scratch_elems(g);
+                if (ns) PS_TRY_CUDA(dev_alloc(&rank_scratch, ns, s));
+                StageTimer tm(ctx, PS_STAGE_RANK, s);
+                PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, s));
+            }
+            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, ctx->d_total, s)); }
+            PS_TRY_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the lists
+            sv->M = ctx->h_total[0];
+            sv->n_work = (int)ctx->h_total[1];
             if (sv->M > 0x7fffffffLL) { rc = fail(1, "ps_forward: %lld tile intersections exceed 2^31", (long long)sv->M); goto out; }
         }
         const int64_t M = sv->M;
-        PS_TRY_CUDA(dev_alloc(&sv->offsets, (size_t)g.V * g.n_tiles + 1, s));
         if (M > 0) {
-            PS_TRY_CUDA(dev_alloc(&sv->keys, (size_t)M, s));
-            PS_TRY_CUDA(dev_alloc(&sv->vals, (size_t)M, s));
-            PS_TRY_CUDA(dev_alloc(&keys_alt, (size_t)M, s));
-            PS_TRY_CUDA(dev_alloc(&vals_alt, (size_t)M, s));
-            PS_TRY_CUDA(dev_alloc(&hist, ps_sort_hist_elems(M), s));
-            { StageTimer tm(ctx, PS_STAGE_EMIT, s); PS_TRY_LAUNCH(ps_launch_emit(g, sv->t, sv->keys, sv->vals, s)); }
+            PS_TRY_CUDA(dev_alloc(&sv->l.fill, T, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.worklist, (size_t)sv->n_work, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.slots, (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.vals, (size_t)M, s));
+            PS_TRY_CUDA(cudaMemsetAsync(sv->l.fill, 0, T * sizeof(int32_t), s));
+            { StageTimer tm(ctx, PS_STAGE_PARTITION, s); PS_TRY_LAUNCH(ps_launch_partition(g, sv->t, sv->l, s)); }
+            { StageTimer tm(ctx, PS_STAGE_SORT, s);
+              PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
+              PS_TRY_LAUNCH(ps_launch_sort_lists(g, sv->t, sv->l, sv->n_work, s)); }
             if (keep) {
-                PS_TRY_CUDA(dev_alloc(&sv->keys_raw, (size_t)M, s));
-                PS_TRY_CUDA(dev_alloc(&sv->vals_raw, (size_t)M, s));
-                PS_TRY_CUDA(cudaMemcpyAsync(sv->keys_raw, sv->keys, sizeof(uint64_t) * M, cudaMemcpyDeviceToDevice, s));
-                PS_TRY_CUDA(cudaMemcpyAsync(sv->vals_raw, sv->vals, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, s));
-            }
-            // 3D sorts depth bits + tile + view; 2D emits rows in order, so only tile + view bits
-            const int bit_lo = (g.mode == PS_MODE_3D) ? 0 : 32;
-            const int bit_hi = 32 + g.tile_bits + g.view_bits;
-            { StageTimer tm(ctx, PS_STAGE_SORT, s); PS_TRY_LAUNCH(ps_launch_sort(sv->keys, sv->vals, keys_alt, vals_alt, M, bit_lo, bit_hi, hist, &sv->sort_passes, s)); }
-            if (sv->sort_passes & 1) {
-                uint64_t *tk = sv->keys; sv->keys = keys_alt; keys_alt = tk;
-                uint32_t *tv = sv->vals; sv->vals = vals_alt; vals_alt = tv;
+                PS_TRY_CUDA(dev_alloc(&sv->keys, (size_t)M, s));
+                PS_TRY_LAUNCH(ps_launch_debug_keys(g, sv->t, sv->l, sv->n_work, sv->keys, s));
             }
         }
-        { StageTimer tm(ctx, PS_STAGE_RANGES, s); PS_TRY_LAUNCH(ps_launch_tile_ranges(g, sv->keys, M, sv->offsets, s)); }
         if (npix > 0) {
             if (save) {
                 PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
@@ -259,13 +261,16 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
                 PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             }
             StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
-            PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->vals, sv->offsets, background, rgb, alpha, n_contrib,
+            PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, keep ? sv->last : nullptr, s));
+            PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->n_work, background, rgb, alpha, n_contrib,
                                                sv->last, sv->t_pen, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
         }
     }
 out:
-    dev_free(keys_alt, s); dev_free(vals_alt, s); dev_free(hist, s);
-    if (rc == 0 && !keep) { dev_free(sv->keys, s); dev_free(sv->t.tile_rect, s); dev_free(sv->t.block_sums, s); }
+    dev_free(rank_scratch, s);
+    dev_free(sv->l.fill, s); dev_free(sv->l.slots, s); dev_free(sv->l.cls, s);
+    dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
+    if (rc == 0 && !keep) dev_free(sv->t.tile_rect, s);
     if (rc != 0 || !(save || keep)) {
         saved_free(sv, s);
         delete sv;
@@ -273,7 +278,6 @@ out:
     }
     if (saved) *saved = sv;
     return rc;
-#undef PS_TRY
 #undef PS_TRY_CUDA
 #undef PS_TRY_LAUNCH
 }
@@ -301,7 +305,7 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
     do {
         if (cudaMemsetAsync(acc, 0, VN * PS_ACC_STRIDE * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
         int n;
-        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->vals, sv->offsets, background, sv->last, sv->t_pen, d_rgb, d_alpha, acc, s); }
+        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->last, sv->t_pen, d_rgb, d_alpha, acc, s); }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
         { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, view_frame, viewmats, Ks, sv->t, acc, d_params, s); }
@@ -321,7 +325,7 @@ int ps_saved_info_get(const ps_saved *sv, ps_saved_info *out)
     out->tiles_x = sv->g.tiles_x; out->tiles_y = sv->g.tiles_y;
     out->n_views = sv->g.V; out->n_gauss = sv->g.N; out->n_frames = sv->g.F;
     out->mode = sv->g.mode; out->width = sv->g.W; out->height = sv->g.H;
-    out->sort_passes = sv->sort_passes;
+    out->n_lists = sv->n_work;
     return 0;
 }
 
@@ -334,15 +338,13 @@ int ps_saved_copy(ps_ctx *ctx, const ps_saved *sv, int what, void *dst, size_t b
     size_t have = 0;
     switch (what) {
         case PS_TAP_ISECT_KEYS: src = sv->keys; have = sizeof(uint64_t) * (size_t)sv->M; break;
-        case PS_TAP_FLATTEN_IDS: src = sv->vals; have = sizeof(uint32_t) * (size_t)sv->M; break;
-        case PS_TAP_TILE_OFFSETS: src = sv->offsets; have = sizeof(int32_t) * ((size_t)g.V * g.n_tiles + 1); break;
+        case PS_TAP_FLATTEN_IDS: src = sv->l.vals; have = sizeof(uint32_t) * (size_t)sv->M; break;
+        case PS_TAP_TILE_OFFSETS: src = sv->l.offsets; have = sizeof(int32_t) * ((size_t)g.V * g.n_tiles + 1); break;
         case PS_TAP_LAST_IDS: src = sv->last; have = sizeof(int32_t) * npix; break;
         case PS_TAP_TILES_TOUCHED: src = sv->t.tiles_touched; have = sizeof(int32_t) * VN; break;
         case PS_TAP_REC0: src = sv->t.rec0; have = sizeof(float4) * VN; break;
         case PS_TAP_REC1: src = sv->t.rec1; have = sizeof(float4) * VN; break;
         case PS_TAP_REC2: src = sv->t.rec2; have = sizeof(float4) * VN; break;
-        case PS_TAP_UNSORTED_KEYS: src = sv->keys_raw; have = sizeof(uint64_t) * (size_t)sv->M; break;
-        case PS_TAP_UNSORTED_IDS: src = sv->vals_raw; have = sizeof(uint32_t) * (size_t)sv->M; break;
         default: return fail(1, "ps_saved_copy: unknown tap %d", what);
     }
     if (have == 0) return 0;

@@ -6,9 +6,12 @@
 
 #include "../../include/psplat.h"
 
-#define PS_PROJ_BLOCK 256   // (view, Gaussian) pairs per projection / emission block
-#define PS_RASTER_BATCH 256 // tile-list entries staged in shared memory per round
-#define PS_ACC_STRIDE 12    // floats per (view, Gaussian) gradient accumulator row (9 used, 16-byte aligned)
+#define PS_PROJ_BLOCK 256    // (view, Gaussian) pairs per projection / partition block
+#define PS_RASTER_BATCH 256  // tile-list entries staged in shared memory per round
+#define PS_ACC_STRIDE 12     // floats per (view, Gaussian) gradient accumulator row (9 used, 16-byte aligned)
+#define PS_HIST_SMEM_TILES 8192  // per-view tile histograms live in shared memory up to this many tiles
+#define PS_RANK_THREADS 1024     // one CTA per view in the depth-ranking kernel
+#define PS_N_CLASSES 32          // tile-list size classes (floor(log2(len))) of the work list
 
 struct PsGeometry {
     int mode, W, H, F, N, V;
@@ -22,30 +25,45 @@ struct PsTable {
     float4 *rec0, *rec1, *rec2; // [V*N]
     uint2 *tile_rect;           // [V*N] packed tx0|ty0<<16, tx1|ty1<<16
     int32_t *tiles_touched;     // [V*N]
-    int32_t *block_sums;        // [ceil(V*N / PS_PROJ_BLOCK) + 1] -> exclusive offsets after the scan
+    uint32_t *order;            // [V*N] 3D: order[view*N + r] = Gaussian with depth rank r in that view (2D: unused)
+    uint32_t *rank;             // [V*N] 3D: inverse of order                                     (2D: unused)
+};
+
+// per-(view,tile) lists
+struct PsLists {
+    int32_t *offsets;   // [T+1], T = V*n_tiles: counts after projection, exclusive offsets after the scan
+    int32_t *fill;      // [T] running fill of every list during the partition pass
+    int32_t *worklist;  // [T] non-empty (view,tile) ids, longest size class first
+    int32_t *cls;       // [2*PS_N_CLASSES] size-class base / fill counters of the work list
+    uint32_t *slots;    // [M] depth ranks (3D) / row indices (2D) in list order, unsorted inside a list
+    uint32_t *vals;     // [M] view*N + Gaussian, sorted (tile, depth | row)
 };
 
 // every launcher returns the number of kernels it launched (for gpu_launches) or -1 on error
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
-                      const float *Ks, const PsTable &t, cudaStream_t s);
-int ps_launch_scan_block_sums(const PsGeometry &g, const PsTable &t, int64_t *total_out, cudaStream_t s);
-int ps_launch_emit(const PsGeometry &g, const PsTable &t, uint64_t *keys, uint32_t *vals, cudaStream_t s);
+                      const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s);
 int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
                           const float *Ks, const PsTable &t, const float *acc, float *d_params, cudaStream_t s);
 
-// stable LSD radix sort of (key, val) pairs on key bits [bit_lo, bit_hi); result ends in keys/vals
-// (alt buffers are scratch).  hist is scratch of ps_sort_hist_elems() uint32.
-size_t ps_sort_hist_elems(int64_t M);
-int ps_launch_sort(uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, int64_t M, int bit_lo,
-                   int bit_hi, uint32_t *hist, int *passes_out, cudaStream_t s);
-int ps_launch_tile_ranges(const PsGeometry &g, const uint64_t *keys, int64_t M, int32_t *offsets, cudaStream_t s);
+// binning (ps_bin.cu)
+size_t ps_rank_scratch_elems(const PsGeometry &g); // uint32 elements of global scratch the ranking needs (0 if it fits smem)
+int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, cudaStream_t s);
+// exclusive scan of the T counts in place (offsets[T] = M), size classes; mailbox[0] = M, mailbox[1] = non-empty lists
+int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, int64_t *mailbox, cudaStream_t s);
+int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s);
+int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t s);
+int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
+int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint64_t *keys, cudaStream_t s);
 
-int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
-                         const float *background, float *rgb, float *alpha, int32_t *n_contrib, int32_t *last,
-                         float *t_pen, unsigned long long *stats, cudaStream_t s);
-int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
-                         const float *background, const int32_t *last, const float *t_pen, const float *d_rgb,
-                         const float *d_alpha, float *acc, cudaStream_t s);
+// rasterizers (ps_raster.cu)
+int ps_launch_fill_empty(const PsGeometry &g, const int32_t *offsets, const float *background, float *rgb, float *alpha,
+                         int32_t *n_contrib, int32_t *last, cudaStream_t s);
+int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
+                         float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, float *t_pen,
+                         unsigned long long *stats, cudaStream_t s);
+int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
+                         const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
+                         cudaStream_t s);
 
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);
 int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s);

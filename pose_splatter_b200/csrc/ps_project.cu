@@ -1,8 +1,7 @@
 // ps_project.cu -- per-Gaussian stages of the hot path (SURVEY.md 2.2 K1', K2', K7'):
 //   project   : fused activation + EWA projection (3D) / activation + extent (2D) -> splat records,
-//               tile rectangle, tiles-touched and a per-block sum for the scan      [HBM-bound]
-//   scan      : exclusive scan of the per-block sums (one CTA)                        [latency]
-//   emit      : in-block scan + (key, value) emission, gid-major / tile row-major     [HBM-bound]
+//               tile rectangle, tiles-touched, and the per-(view,tile) list lengths
+//               (CTA histogram in shared memory, one global atomic per (CTA, tile))  [HBM-bound]
 //   project_bwd : chain rule back to the raw rows, atomics into d_params[frame]       [HBM-bound]
 // Replaces: adapter activations src/gaussian_renderer.py:183-193 / :314-323 and gsplat's
 // fully_fused_projection + isect_tiles (absent from the reference tree).
@@ -10,33 +9,6 @@
 #include "ps_internal.h"
 
 namespace {
-
-__device__ __forceinline__ int block_exclusive_scan_256(int v, int *s_warp, int *block_total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += n;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
-        int wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += n;
-        }
-        s_warp[lane] = wi - w; // exclusive warp offsets
-        if (lane == 31) s_warp[32] = wi;
-    }
-    __syncthreads();
-    if (block_total) *block_total = s_warp[32];
-    return s_warp[wid] + incl - v;
-}
 
 // Stage a block's parameter rows through shared memory with coalesced (128-bit when aligned) loads.
 template <int P>
@@ -55,22 +27,25 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ src, int n_
 template <int MODE>
 __global__ void __launch_bounds__(PS_PROJ_BLOCK)
 project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ view_frame,
-               const float *__restrict__ viewmats, const float *__restrict__ Ks, PsTable t)
+               const float *__restrict__ viewmats, const float *__restrict__ Ks, PsTable t,
+               int32_t *__restrict__ tile_counts, int use_smem)
 {
     constexpr int P = (MODE == PS_MODE_3D) ? 14 : 9;
+    extern __shared__ int s_cnt[]; // [n_tiles] when use_smem
     __shared__ __align__(16) float s_rows[PS_PROJ_BLOCK * P];
     __shared__ float s_cam[25];
-    __shared__ int s_warp[33];
     const int v = blockIdx.y;
     const int g0 = blockIdx.x * PS_PROJ_BLOCK;
     const int n_rows = min(PS_PROJ_BLOCK, g.N - g0);
     const int frame = view_frame[v];
     stage_rows<P>(params + ((size_t)frame * g.N + g0) * P, n_rows, s_rows);
+    if (use_smem)
+        for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) s_cnt[i] = 0;
     if (MODE == PS_MODE_3D && threadIdx.x < 25) {
         s_cam[threadIdx.x] = threadIdx.x < 16 ? viewmats[(size_t)v * 16 + threadIdx.x] : Ks[(size_t)v * 9 + threadIdx.x - 16];
     }
     __syncthreads();
-    int touched = 0;
+    int32_t *cnt_v = tile_counts + (size_t)v * g.n_tiles;
     if ((int)threadIdx.x < n_rows) {
         PsRecord rec;
         if (MODE == PS_MODE_3D) {
@@ -86,68 +61,18 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
         t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
         t.tile_rect[idx] = make_uint2((uint32_t)rec.tile[0] | ((uint32_t)rec.tile[1] << 16),
                                       (uint32_t)rec.tile[2] | ((uint32_t)rec.tile[3] << 16));
-        touched = (rec.tile[2] - rec.tile[0]) * (rec.tile[3] - rec.tile[1]);
-        t.tiles_touched[idx] = touched;
+        t.tiles_touched[idx] = (rec.tile[2] - rec.tile[0]) * (rec.tile[3] - rec.tile[1]);
+        for (int ty = rec.tile[1]; ty < rec.tile[3]; ++ty)
+            for (int tx = rec.tile[0]; tx < rec.tile[2]; ++tx)
+                atomicAdd(use_smem ? &s_cnt[ty * g.tiles_x + tx] : &cnt_v[ty * g.tiles_x + tx], 1);
     }
-    int total;
-    block_exclusive_scan_256(touched, s_warp, &total);
-    if (threadIdx.x == 0) t.block_sums[blockIdx.y * gridDim.x + blockIdx.x] = total;
-}
-
-// one CTA: exclusive scan of n block sums in place; sums[n] and *total receive the grand total
-__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int32_t *sums, int n, int64_t *total)
-{
-    __shared__ long long s_part[1024];
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-    long long acc = 0;
-    for (int i = lo; i < hi; ++i) acc += sums[i];
-    s_part[threadIdx.x] = acc;
-    __syncthreads();
-    // Hillis-Steele over 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
-        long long add = threadIdx.x >= (unsigned)d ? s_part[threadIdx.x - d] : 0;
+    if (use_smem) {
         __syncthreads();
-        s_part[threadIdx.x] += add;
-        __syncthreads();
-    }
-    long long run = s_part[threadIdx.x] - acc;
-    for (int i = lo; i < hi; ++i) {
-        int c = sums[i];
-        sums[i] = (int32_t)run;
-        run += c;
-    }
-    if (threadIdx.x == 1023) {
-        *total = s_part[1023];
-        sums[n] = (int32_t)s_part[1023];
-    }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(PS_PROJ_BLOCK)
-emit_kernel(PsGeometry g, PsTable t, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
-{
-    __shared__ int s_warp[33];
-    const int v = blockIdx.y;
-    const int gi = blockIdx.x * PS_PROJ_BLOCK + threadIdx.x;
-    const bool live = gi < g.N;
-    const size_t idx = (size_t)v * g.N + (live ? gi : 0);
-    const int touched = live ? t.tiles_touched[idx] : 0;
-    const int excl = block_exclusive_scan_256(touched, s_warp, nullptr);
-    if (touched == 0) return;
-    size_t out = (size_t)t.block_sums[blockIdx.y * gridDim.x + blockIdx.x] + excl;
-    const uint2 tr = t.tile_rect[idx];
-    const int tx0 = tr.x & 0xffff, ty0 = tr.x >> 16, tx1 = tr.y & 0xffff, ty1 = tr.y >> 16;
-    const uint32_t low = (MODE == PS_MODE_3D) ? __float_as_uint(t.rec2[idx].w) : (uint32_t)gi;
-    const uint64_t view_hi = (uint64_t)v << g.tile_bits;
-    const uint32_t val = (uint32_t)idx;
-    for (int ty = ty0; ty < ty1; ++ty)
-        for (int tx = tx0; tx < tx1; ++tx) {
-            const uint64_t tile = (uint64_t)(ty * g.tiles_x + tx);
-            keys[out] = ((view_hi | tile) << 32) | low;
-            vals[out] = val;
-            ++out;
+        for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) {
+            const int c = s_cnt[i];
+            if (c) atomicAdd(&cnt_v[i], c);
         }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -313,26 +238,16 @@ __global__ void math_probe_kernel(const float *x, int n, float *y)
 } // namespace
 
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
-                      const float *Ks, const PsTable &t, cudaStream_t s)
+                      const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s)
 {
+    if (g.N == 0 || g.V == 0) return 0;
     dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
-    if (g.mode == PS_MODE_3D) project_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, view_frame, viewmats, Ks, t);
-    else project_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, view_frame, viewmats, Ks, t);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-int ps_launch_scan_block_sums(const PsGeometry &g, const PsTable &t, int64_t *total_out, cudaStream_t s)
-{
-    const int nb = ((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK) * g.V;
-    scan_block_sums_kernel<<<1, 1024, 0, s>>>(t.block_sums, nb, total_out);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-int ps_launch_emit(const PsGeometry &g, const PsTable &t, uint64_t *keys, uint32_t *vals, cudaStream_t s)
-{
-    dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
-    if (g.mode == PS_MODE_3D) emit_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, t, keys, vals);
-    else emit_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, t, keys, vals);
+    const int use_smem = g.n_tiles <= PS_HIST_SMEM_TILES;
+    const size_t dyn = use_smem ? (size_t)g.n_tiles * sizeof(int) : 0;
+    if (g.mode == PS_MODE_3D)
+        project_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, params, view_frame, viewmats, Ks, t, tile_counts, use_smem);
+    else
+        project_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, params, view_frame, viewmats, Ks, t, tile_counts, use_smem);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

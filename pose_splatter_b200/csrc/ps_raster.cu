@@ -30,10 +30,10 @@ struct TileCtx {
     bool inside;
 };
 
-__device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *offsets)
+__device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist)
 {
     TileCtx c;
-    const int lin = blockIdx.x;
+    const int lin = worklist[blockIdx.x]; // non-empty (view, tile) lists, longest size class first
     c.view = lin / g.n_tiles;
     c.tile = lin - c.view * g.n_tiles;
     const int ty = c.tile / g.tiles_x, tx = c.tile - ty * g.tiles_x;
@@ -78,13 +78,13 @@ __device__ __forceinline__ void stage_batch(const PsTable &t, const uint32_t *__
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(256)
 raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
-                  const float *__restrict__ background, float *__restrict__ rgb, float *__restrict__ alpha,
+                  const int32_t *__restrict__ worklist, const float *__restrict__ background, float *__restrict__ rgb, float *__restrict__ alpha,
                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, float *__restrict__ t_pen,
                   unsigned long long *__restrict__ stats)
 {
     unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB];
-    const TileCtx c = tile_ctx(g, offsets);
+    const TileCtx c = tile_ctx(g, offsets, worklist);
     const int lane = threadIdx.x & 31;
     const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
     const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 template <int MODE>
 __global__ void __launch_bounds__(256)
 raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
-                  const float *__restrict__ background, const int32_t *__restrict__ last,
+                  const int32_t *__restrict__ worklist, const float *__restrict__ background, const int32_t *__restrict__ last,
                   const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
                   float *__restrict__ acc)
 {
@@ -227,8 +227,7 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     __shared__ float s_grad[RB * 9];
     __shared__ int s_touched[RB];
     __shared__ int s_tile_end;
-    const TileCtx c = tile_ctx(g, offsets);
-    if (c.end == c.start) return;
+    const TileCtx c = tile_ctx(g, offsets, worklist);
     const int lane = threadIdx.x & 31;
     const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
     const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
@@ -350,13 +349,13 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
 
 } // namespace
 
-int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
-                         const float *background, float *rgb, float *alpha, int32_t *n_contrib, int32_t *last,
-                         float *t_pen, unsigned long long *stats, cudaStream_t s)
+int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
+                         float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, float *t_pen,
+                         unsigned long long *stats, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)g.V * (unsigned)g.n_tiles;
-    if (grid == 0) return 0;
-#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, rgb, alpha, n_contrib, last, t_pen, stats)
+    if (n_work <= 0) return 0;
+    const unsigned grid = (unsigned)n_work;
+#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, t_pen, stats)
     if (g.mode == PS_MODE_3D) { if (stats) PS_FWD(PS_MODE_3D, true); else PS_FWD(PS_MODE_3D, false); }
     else { if (stats) PS_FWD(PS_MODE_2D, true); else PS_FWD(PS_MODE_2D, false); }
 #undef PS_FWD
@@ -391,15 +390,67 @@ int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s)
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const uint32_t *vals, const int32_t *offsets,
-                         const float *background, const int32_t *last, const float *t_pen, const float *d_rgb,
-                         const float *d_alpha, float *acc, cudaStream_t s)
+int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
+                         const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
+                         cudaStream_t s)
 {
-    const unsigned grid = (unsigned)g.V * (unsigned)g.n_tiles;
-    if (grid == 0) return 0;
+    if (n_work <= 0) return 0;
+    const unsigned grid = (unsigned)n_work;
     if (g.mode == PS_MODE_3D)
-        raster_bwd_kernel<PS_MODE_3D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, last, t_pen, d_rgb, d_alpha, acc);
+        raster_bwd_kernel<PS_MODE_3D><<<grid, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, acc);
     else
-        raster_bwd_kernel<PS_MODE_2D><<<grid, 256, 0, s>>>(g, t, vals, offsets, background, last, t_pen, d_rgb, d_alpha, acc);
+        raster_bwd_kernel<PS_MODE_2D><<<grid, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, acc);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Pixels of tiles whose list is empty: rgb = background, alpha = 0 (what the compositing loop yields for zero
+// contributors: fma(1, bg, 0) and 1 - 1).  One thread per 4 horizontally adjacent pixels (same tile).
+namespace {
+__global__ void __launch_bounds__(256)
+fill_empty_kernel(PsGeometry g, const int32_t *__restrict__ offsets, const float *__restrict__ background,
+                  float *__restrict__ rgb, float *__restrict__ alpha, int32_t *__restrict__ n_contrib,
+                  int32_t *__restrict__ last, int groups_x, long long n_groups, int vec_ok)
+{
+    const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= n_groups) return;
+    const int gx = (int)(gidx % groups_x);
+    const long long row = gidx / groups_x; // view * H + y
+    const int y = (int)(row % g.H), v = (int)(row / g.H);
+    const int x0 = gx * 4;
+    const int lin = v * g.n_tiles + (y / PS_TILE) * g.tiles_x + x0 / PS_TILE;
+    const int start = offsets[lin];
+    if (offsets[lin + 1] != start) return;
+    const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
+    const size_t p = (size_t)row * g.W + x0;
+    const int n = min(4, g.W - x0);
+    if (n == 4 && vec_ok) {
+        float4 *d = reinterpret_cast<float4 *>(rgb + 3 * p);
+        d[0] = make_float4(b0, b1, b2, b0);
+        d[1] = make_float4(b1, b2, b0, b1);
+        d[2] = make_float4(b2, b0, b1, b2);
+        *reinterpret_cast<float4 *>(alpha + p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_contrib) *reinterpret_cast<int4 *>(n_contrib + p) = make_int4(0, 0, 0, 0);
+        if (last) *reinterpret_cast<int4 *>(last + p) = make_int4(start, start, start, start);
+    } else {
+        for (int k = 0; k < n; ++k) {
+            rgb[3 * (p + k)] = b0; rgb[3 * (p + k) + 1] = b1; rgb[3 * (p + k) + 2] = b2;
+            alpha[p + k] = 0.0f;
+            if (n_contrib) n_contrib[p + k] = 0;
+            if (last) last[p + k] = start;
+        }
+    }
+}
+} // namespace
+
+int ps_launch_fill_empty(const PsGeometry &g, const int32_t *offsets, const float *background, float *rgb, float *alpha,
+                         int32_t *n_contrib, int32_t *last, cudaStream_t s)
+{
+    const int groups_x = (g.W + 3) / 4;
+    const long long n_groups = (long long)g.V * g.H * groups_x;
+    if (n_groups == 0) return 0;
+    const uintptr_t align = (uintptr_t)rgb | (uintptr_t)alpha | (uintptr_t)n_contrib | (uintptr_t)last;
+    const int vec_ok = (g.W & 3) == 0 && (align & 15u) == 0;
+    fill_empty_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(g, offsets, background, rgb, alpha, n_contrib, last,
+                                                                      groups_x, n_groups, vec_ok);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
