@@ -11,7 +11,7 @@ import torch
 
 MODE_2D, MODE_3D = 2, 3
 FLAG_SAVE_FOR_BACKWARD, FLAG_KEEP_BINNING = 1, 2
-TAPS = dict(isect_keys=1, flatten_ids=2, tile_offsets=3, last_ids=4, tiles_touched=5, rec0=6, rec1=7, rec2=8)
+TAPS = dict(isect_keys=1, flatten_ids=2, tile_offsets=3, last_ids=4, tiles_touched=5, rec0=6, rec1=7, rec2=8, depth=9)
 
 LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 

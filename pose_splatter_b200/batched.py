@@ -45,7 +45,7 @@ class SavedForward:
                       tile_offsets=((info.n_views * info.tiles_x * info.tiles_y + 1,), torch.int32),
                       last_ids=((info.n_views, info.height, info.width), torch.int32),
                       tiles_touched=((VN,), torch.int32), rec0=((VN, 4), torch.float32), rec1=((VN, 4), torch.float32),
-                      rec2=((VN, 4), torch.float32))
+                      rec2=((VN, 4), torch.float32), depth=((VN if info.mode == 3 else 0,), torch.int32))
         shape, dtype = shapes[name]
         out = torch.empty(shape, dtype=dtype, device=self.device)
         if out.numel():

@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t scan256_exclusive(uint32_t *s, uint32_t *s_t
 // uint32_t with them in global scratch (N too large for shared memory).
 template <typename IdT>
 __global__ void __launch_bounds__(RT)
-depth_rank_kernel(int N, const float4 *__restrict__ rec2, const int32_t *__restrict__ touched,
+depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__restrict__ touched,
                   uint32_t *__restrict__ order, uint32_t *__restrict__ rank, uint32_t *gscratch)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -82,7 +82,7 @@ depth_rank_kernel(int N, const float4 *__restrict__ rec2, const int32_t *__restr
     uint32_t mn = 0xffffffffu, mx = 0u;
     for (int i = tid; i < N; i += RT) {
         const bool listed = touched[base + i] > 0;
-        const uint32_t key = listed ? __float_as_uint(rec2[base + i].w) : 0xffffffffu;
+        const uint32_t key = listed ? depth[base + i] : 0xffffffffu;
         k[0][i] = key;
         id[0][i] = (IdT)i;
         if (listed) { mn = min(mn, key); mx = max(mx, key); }
@@ -331,7 +331,7 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-debug_keys_kernel(PsGeometry g, const float4 *__restrict__ rec2, const int32_t *__restrict__ offsets,
+debug_keys_kernel(PsGeometry g, const uint32_t *__restrict__ depth, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const uint32_t *__restrict__ vals, uint64_t *__restrict__ keys)
 {
     const int lin = worklist[blockIdx.x];
@@ -340,7 +340,7 @@ debug_keys_kernel(PsGeometry g, const float4 *__restrict__ rec2, const int32_t *
     const uint64_t hi = (((uint64_t)view << g.tile_bits) | (uint64_t)tile) << 32;
     for (int i = start + threadIdx.x; i < end; i += 256) {
         const uint32_t id = vals[i];
-        const uint32_t low = (MODE == PS_MODE_3D) ? __float_as_uint(rec2[id].w) : id - (uint32_t)view * (uint32_t)g.N;
+        const uint32_t low = (MODE == PS_MODE_3D) ? depth[id] : id - (uint32_t)view * (uint32_t)g.N;
         keys[i] = hi | low;
     }
 }
@@ -365,10 +365,10 @@ int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratc
         const size_t dyn = rank_smem_bytes(g.N);
         if (cudaFuncSetAttribute(depth_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
             return -1;
-        depth_rank_kernel<uint16_t><<<g.V, RT, dyn, s>>>(g.N, t.rec2, t.tiles_touched, t.order, t.rank, nullptr);
+        depth_rank_kernel<uint16_t><<<g.V, RT, dyn, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, nullptr);
     } else {
         if (!scratch) return -1;
-        depth_rank_kernel<uint32_t><<<g.V, RT, 0, s>>>(g.N, t.rec2, t.tiles_touched, t.order, t.rank, scratch);
+        depth_rank_kernel<uint32_t><<<g.V, RT, 0, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, scratch);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -420,7 +420,7 @@ int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l
 int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint64_t *keys, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    if (g.mode == PS_MODE_3D) debug_keys_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t.rec2, l.offsets, l.worklist, l.vals, keys);
-    else debug_keys_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t.rec2, l.offsets, l.worklist, l.vals, keys);
+    if (g.mode == PS_MODE_3D) debug_keys_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t.depth, l.offsets, l.worklist, l.vals, keys);
+    else debug_keys_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t.depth, l.offsets, l.worklist, l.vals, keys);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -161,6 +161,7 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
 {
     dev_free(sv->t.rec0, s); dev_free(sv->t.rec1, s); dev_free(sv->t.rec2, s);
     dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
+    dev_free(sv->t.depth, s);
     dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
     dev_free(sv->l.slots, s); dev_free(sv->l.vals, s);
     dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->t_pen, s);
@@ -221,6 +222,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             PS_TRY_CUDA(dev_alloc(&sv->t.rec2, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
+            if (g.mode == PS_MODE_3D) PS_TRY_CUDA(dev_alloc(&sv->t.depth, VN, s));
             { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, sv->l.offsets, s)); }
             if (g.mode == PS_MODE_3D) {
                 PS_TRY_CUDA(dev_alloc(&sv->t.order, VN, s));
@@ -270,7 +272,7 @@ out:
     dev_free(rank_scratch, s);
     dev_free(sv->l.fill, s); dev_free(sv->l.slots, s); dev_free(sv->l.cls, s);
     dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
-    if (rc == 0 && !keep) dev_free(sv->t.tile_rect, s);
+    if (rc == 0 && !keep) { dev_free(sv->t.tile_rect, s); dev_free(sv->t.depth, s); }
     if (rc != 0 || !(save || keep)) {
         saved_free(sv, s);
         delete sv;
@@ -345,6 +347,7 @@ int ps_saved_copy(ps_ctx *ctx, const ps_saved *sv, int what, void *dst, size_t b
         case PS_TAP_REC0: src = sv->t.rec0; have = sizeof(float4) * VN; break;
         case PS_TAP_REC1: src = sv->t.rec1; have = sizeof(float4) * VN; break;
         case PS_TAP_REC2: src = sv->t.rec2; have = sizeof(float4) * VN; break;
+        case PS_TAP_DEPTH: src = sv->t.depth; have = sv->g.mode == PS_MODE_3D ? sizeof(uint32_t) * VN : 0; break;
         default: return fail(1, "ps_saved_copy: unknown tap %d", what);
     }
     if (have == 0) return 0;

@@ -51,10 +51,9 @@ PS_HD uint32_t psm_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 PS_HD float psm_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 #endif
 
-// 2^t, t clamped to [-125, 125]: r = t - rint(t) via the 1.5*2^23 trick, degree-5 Horner.
-PS_HD float psm_exp2(float t)
+// 2^t for |t| <= 125 (the caller guarantees the range): r = t - rint(t) via the 1.5*2^23 trick, degree-5 Horner.
+PS_HD float psm_exp2_inrange(float t)
 {
-    t = fminf(fmaxf(t, -125.0f), 125.0f);
     const float magic = 12582912.0f;
     float z = psm_add(t, magic);
     float n = psm_sub(z, magic);
@@ -67,6 +66,8 @@ PS_HD float psm_exp2(float t)
     p = psm_fma(p, r, 1.0f);
     return psm_u2f(psm_f2u(p) + (psm_f2u(z) << 23));
 }
+// 2^t, t clamped to [-125, 125]
+PS_HD float psm_exp2(float t) { return psm_exp2_inrange(fminf(fmaxf(t, -125.0f), 125.0f)); }
 PS_HD float psm_exp(float x) { return psm_exp2(psm_mul(x, 0x1.715476p+0f)); }
 PS_HD float psm_sigmoid(float x) { return psm_div(1.0f, psm_add(1.0f, psm_exp(-x))); }
 
@@ -125,10 +126,12 @@ PS_HD int ps_tile_bits(int n_tiles)
 
 // ---------------------------------------------------------------------------------------
 // Splat record: what the projection stage leaves per (view, Gaussian) for binning and
-// rasterization.  Three 16-byte words so that a tile rasterizer gathers it with three
-// aligned 128-bit loads.
-//   3D  r0 = x, y, radius_x, radius_y      r1 = A, B, C, opacity     r2 = r, g, b, depth
-//   2D  r0 = u, v, bits(x0|y0<<16), bits(x1|y1<<16)   r1 = cos, sin, iax, iay   r2 = r, g, b, opacity
+// rasterization.  In HBM it is three 16-byte words so that a tile rasterizer gathers it with
+// three aligned 128-bit copies:
+//   3D  rec0 = x, y, radius_x, radius_y   rec1 = A/2, B, C/2, opacity   rec2 = r, g, b, thr
+//       (A/2, C/2: exact halvings, what the pair arithmetic uses; thr = log(255 * opacity), the
+//        largest sigma that can pass alpha >= 1/255; the depth word goes to its own array)
+//   2D  rec0 = u, v, bits(x0|y0<<16), bits(x1|y1<<16)   rec1 = cos, sin, iax, iay   rec2 = r, g, b, opacity
 // tile rect: tx0, ty0, tx1, ty1 (exclusive max); culled <=> empty.
 // ---------------------------------------------------------------------------------------
 struct PsRecord {
@@ -137,6 +140,7 @@ struct PsRecord {
     float r2[4];
     int tile[4];
     uint32_t low; // low word of the sort key: depth bits (3D) or row index (2D)
+    float thr;    // 3D: log(255 * opacity)
 };
 
 struct PsProj3dAux { // intermediates the projection backward re-uses
@@ -149,6 +153,7 @@ PS_HD void ps_record_clear(PsRecord *rec)
 {
     for (int k = 0; k < 4; ++k) { rec->r0[k] = 0.0f; rec->r1[k] = 0.0f; rec->r2[k] = 0.0f; rec->tile[k] = 0; }
     rec->low = 0;
+    rec->thr = 0.0f;
 }
 
 // Adapter activations + EWA projection of one Gaussian for one camera. Returns 1 if visible.
@@ -248,7 +253,8 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
     float cA = psm_div(c11, det), cB = psm_div(-c01, det), cC = psm_div(c00, det);
 
     if (!(o >= PS_ALPHA_MIN)) return 0;
-    float ext = fminf(3.33f, psm_sqrt(psm_mul(2.0f, psm_log(psm_mul(o, 255.0f)))));
+    float thr = psm_log(psm_mul(o, 255.0f));
+    float ext = fminf(3.33f, psm_sqrt(psm_mul(2.0f, thr)));
     float bh = psm_mul(0.5f, psm_add(c00, c11));
     float v1 = psm_add(bh, psm_sqrt(fmaxf(0.01f, psm_fma(bh, bh, -det))));
     float r1 = psm_mul(ext, psm_sqrt(v1));
@@ -265,6 +271,7 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
     rec->r1[0] = cA; rec->r1[1] = cB; rec->r1[2] = cC; rec->r1[3] = o;
     rec->r2[3] = zc;
     rec->low = psm_f2u(zc);
+    rec->thr = thr;
 
     int tw = (W + PS_TILE - 1) / PS_TILE, th = (H + PS_TILE - 1) / PS_TILE;
     float txc = psm_mul(mx, 0.0625f), tyc = psm_mul(my, 0.0625f);
@@ -318,11 +325,11 @@ PS_HD int ps_project2d(const float *row, uint32_t row_index, int W, int H, PsRec
 // ---------------------------------------------------------------------------------------
 // Per (pixel, Gaussian) pair arithmetic.
 // ---------------------------------------------------------------------------------------
-// 3D: sigma = 1/2 (A dx^2 + C dy^2) + B dx dy with d = mean2d - pixel centre (px+0.5, py+0.5)
-PS_HD float ps_sigma3d(float gx, float gy, float A, float B, float C, float px, float py, float *dx_, float *dy_)
+// 3D: sigma = 1/2 (A dx^2 + C dy^2) + B dx dy with d = mean2d - pixel centre (px+0.5, py+0.5);
+// hA = A/2 and hC = C/2 (exact) come from the record
+PS_HD float ps_sigma3d(float gx, float gy, float hA, float B, float hC, float px, float py, float *dx_, float *dy_)
 {
     float dx = psm_sub(gx, px), dy = psm_sub(gy, py);
-    float hA = psm_mul(0.5f, A), hC = psm_mul(0.5f, C);
     float uu = psm_fma(B, dy, psm_mul(hA, dx));
     float s = psm_mul(uu, dx);
     float wv = psm_mul(hC, dy);

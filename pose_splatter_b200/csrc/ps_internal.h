@@ -25,6 +25,7 @@ struct PsTable {
     float4 *rec0, *rec1, *rec2; // [V*N]
     uint2 *tile_rect;           // [V*N] packed tx0|ty0<<16, tx1|ty1<<16
     int32_t *tiles_touched;     // [V*N]
+    uint32_t *depth;            // [V*N] 3D: bits of the camera-space depth (low word of the sort key); 2D: unused
     uint32_t *order;            // [V*N] 3D: order[view*N + r] = Gaussian with depth rank r in that view (2D: unused)
     uint32_t *rank;             // [V*N] 3D: inverse of order                                     (2D: unused)
 };

@@ -57,8 +57,14 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
         }
         const size_t idx = (size_t)v * g.N + g0 + threadIdx.x;
         t.rec0[idx] = make_float4(rec.r0[0], rec.r0[1], rec.r0[2], rec.r0[3]);
-        t.rec1[idx] = make_float4(rec.r1[0], rec.r1[1], rec.r1[2], rec.r1[3]);
-        t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
+        if (MODE == PS_MODE_3D) {
+            t.rec1[idx] = make_float4(psm_mul(0.5f, rec.r1[0]), rec.r1[1], psm_mul(0.5f, rec.r1[2]), rec.r1[3]);
+            t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.thr);
+            t.depth[idx] = rec.low;
+        } else {
+            t.rec1[idx] = make_float4(rec.r1[0], rec.r1[1], rec.r1[2], rec.r1[3]);
+            t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
+        }
         t.tile_rect[idx] = make_uint2((uint32_t)rec.tile[0] | ((uint32_t)rec.tile[1] << 16),
                                       (uint32_t)rec.tile[2] | ((uint32_t)rec.tile[3] << 16));
         t.tiles_touched[idx] = (rec.tile[2] - rec.tile[0]) * (rec.tile[3] - rec.tile[1]);

@@ -1,17 +1,20 @@
 // ps_raster.cu -- per-tile rasterizers (SURVEY.md 2.2 K5', K6'), both gaussian modes.
 //
-// One CTA per (view, 16x16 tile): 8 warps, each owning an 8x4 pixel block.  The tile's sorted
-// list is staged through shared memory 256 splat records (48 B each) at a time.  Each warp
-// first culls the staged batch against its own 8x4 block (one record per lane, ballot), then
-// walks only the surviving records in list order, so the per-pixel work is proportional to the
-// splats that can touch the block, not to the tile list (the hot tiles of this workload list
-// ~all N Gaussians).  Culling never changes a result: it only removes pairs whose
-// alpha test (3D) / rectangle test (2D) is guaranteed to fail.
-//   forward : front-to-back compositing with early termination            [FP32 pipe + smem]
-//   backward: reverse replay from last_id; transmittance recovered by division starting from
-//             the saved "T before the last contributor"; per-splat gradients are reduced across
-//             the warp (multi-value butterfly), accumulated per CTA in shared memory and flushed
-//             with one vector red.global.add.v4.f32 triple per (tile, splat)  [FP32 pipe + smem]
+// One CTA per non-empty (view, 16x16 tile) list, taken from the size-ordered work list.
+//
+// forward (v2): 8 consumer warps, each owning an 8x4 pixel block, + 1 producer warp.  The producer
+//   streams the tile's sorted list through a ring of shared-memory slots (128 splat records of 48 B
+//   per slot) with cp.async gathers that complete on an mbarrier per slot; consumers never meet at a
+//   CTA barrier: each waits for the slot it needs, culls the 128 records against its own block
+//   (one record per lane: exact ellipse-vs-rectangle test in 3D -- the minimum of sigma over the block
+//   against log(255*opacity) --, rectangle-vs-rectangle in 2D), walks the survivors in list order and
+//   publishes its progress; the producer refills a slot when all eight have passed it.  A warp whose
+//   32 pixels are all terminated retires on its own.  Culling never changes a result: it only
+//   removes pairs whose alpha test (3D) / rectangle test (2D) is guaranteed to fail.
+// backward: reverse replay from last_id; transmittance recovered by division starting from the saved
+//   "T before the last contributor"; per-splat gradients are reduced across the warp (multi-value
+//   butterfly), accumulated per CTA in shared memory and flushed with one vector
+//   red.global.add.v4.f32 triple per (tile, splat).
 // Replaces gsplat rasterize_to_pixels_3dgs_fwd/bwd (absent from the reference tree) and the
 // torch element-wise loop src/gaussian_renderer.py:379-425 plus its autograd.
 #include "ps_contract.cuh"
@@ -20,8 +23,17 @@
 namespace {
 
 constexpr int RB = PS_RASTER_BATCH;
-constexpr float CULL_MARGIN = 1.0f;  // px of slack on the 3D rectangle test (exact in real arithmetic)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float CULL_MARGIN = 1.0f;  // px of slack on the 3D rectangle test of the backward (exact in real arithmetic)
 constexpr float SIGMA_SKIP = 5.6f;   // sigma above ln(255) can never pass alpha >= 1/255 (opacity <= 1)
+constexpr float THR_SLACK = 0.01f;   // slack on sigma <= log(255*opacity): covers the rounding of exp / log / sigma
+
+// ---- forward ring ----
+constexpr int FB = 128;            // records per slot
+constexpr int FS = 6;              // slots
+constexpr int FWD_THREADS = 288;   // 8 consumer warps + 1 producer warp
+constexpr int PROG_DONE = 0x7fffffff;
+constexpr unsigned SPIN_LIMIT = 1u << 26;
 
 struct TileCtx {
     int view, tile, start, end;
@@ -39,7 +51,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *
     const int ty = c.tile / g.tiles_x, tx = c.tile - ty * g.tiles_x;
     c.start = offsets[lin];
     c.end = offsets[lin + 1];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = (threadIdx.x >> 5) & 7;
     c.bx = tx * PS_TILE + (wid & 1) * 8;
     c.by = ty * PS_TILE + (wid >> 1) * 4;
     c.px = c.bx + (lane & 7);
@@ -48,18 +60,100 @@ __device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *
     return c;
 }
 
-// does staged record (r0) possibly touch this warp's 8x4 pixel block?
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > SPIN_LIMIT) __trap(); // a lost arrival must fail loudly, never hang the GPU
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// 3D: can the splat pass sigma <= thr anywhere on the pixel centres [x0, x1] x [y0, y1]?
+// sigma(u) = hA ux^2 + hC uy^2 + B ux uy (u = pixel - mean) is convex with its minimum at u = 0, so over a
+// box that does not contain 0 the minimum lies on an edge facing the mean; along such an edge it is a 1-D
+// parabola.  NaN / inf (degenerate conics) count as a hit.
+__device__ __forceinline__ bool ellipse_hits_box(float gx, float gy, float hA, float B, float hC, float thr, float x0,
+                                                 float x1, float y0, float y1)
+{
+    const float ux0 = x0 - gx, ux1 = x1 - gx;
+    const float uy0 = y0 - gy, uy1 = y1 - gy;
+    const float cx = fminf(fmaxf(0.0f, ux0), ux1), cy = fminf(fmaxf(0.0f, uy0), uy1);
+    if (cx == 0.0f && cy == 0.0f) return true;
+    float best = 3.0e38f;
+    if (cx != 0.0f) {
+        const float t = fminf(fmaxf(__fdividef(-B * cx, 2.0f * hC), uy0), uy1);
+        best = hA * cx * cx + (hC * t + B * cx) * t;
+    }
+    if (cy != 0.0f) {
+        const float t = fminf(fmaxf(__fdividef(-B * cy, 2.0f * hA), ux0), ux1);
+        const float sv = hC * cy * cy + (hA * t + B * cy) * t;
+        best = (sv < best || !(best == best)) ? sv : best;
+    }
+    return !(best > thr * 1.0001f + 2.0f * THR_SLACK);
+}
+
+// 2D: does the splat's pixel rectangle meet the pixel box [bx0, bx1] x [by0, by1]?
+__device__ __forceinline__ bool rect_hits_box(float lo_bits, float hi_bits, int bx0, int bx1, int by0, int by1)
+{
+    const uint32_t lo = __float_as_uint(lo_bits), hi = __float_as_uint(hi_bits);
+    const int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
+    return x0 <= bx1 && x1 >= bx0 && y0 <= by1 && y1 >= by0;
+}
+__device__ __forceinline__ bool rect_hits_block(float lo_bits, float hi_bits, int bx, int by)
+{
+    return rect_hits_box(lo_bits, hi_bits, bx, bx + 7, by, by + 3);
+}
+
+// bounding box (in block-local pixel coordinates) of the lanes set in `active` (lane = y * 8 + x); active != 0
+__device__ __forceinline__ void active_box(uint32_t active, int &x0, int &x1, int &y0, int &y1)
+{
+    const uint32_t cols = (active | (active >> 8) | (active >> 16) | (active >> 24)) & 0xffu;
+    x0 = __ffs(cols) - 1;
+    x1 = 31 - __clz(cols);
+    y0 = (__ffs(active) - 1) >> 3;
+    y1 = (31 - __clz(active)) >> 3;
+}
+
+// does staged record (r0) possibly touch this warp's 8x4 pixel block?  (backward, v1 test)
 template <int MODE>
 __device__ __forceinline__ bool block_hit(const float4 &r0, int bx, int by)
 {
     if (MODE == PS_MODE_3D) {
-        // pixel centres of the block span [bx+.5, bx+7.5] x [by+.5, by+3.5]
         return fabsf(r0.x - ((float)bx + 4.0f)) <= r0.z + (3.5f + CULL_MARGIN) &&
                fabsf(r0.y - ((float)by + 2.0f)) <= r0.w + (1.5f + CULL_MARGIN);
     } else {
-        const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
-        const int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
-        return x0 <= bx + 7 && x1 >= bx && y0 <= by + 3 && y1 >= by;
+        return rect_hits_block(r0.z, r0.w, bx, by);
     }
 }
 
@@ -76,76 +170,195 @@ __device__ __forceinline__ void stage_batch(const PsTable &t, const uint32_t *__
 }
 
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FWD_THREADS, 5)
 raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
-                  const int32_t *__restrict__ worklist, const float *__restrict__ background, float *__restrict__ rgb, float *__restrict__ alpha,
+                  const int32_t *__restrict__ worklist, const float *__restrict__ background,
+                  float *__restrict__ rgb, float *__restrict__ alpha,
                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, float *__restrict__ t_pen,
                   unsigned long long *__restrict__ stats)
 {
-    unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
-    __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB];
+    __shared__ float4 s_r0[FS][FB], s_r1[FS][FB], s_r2[FS][FB];
+    __shared__ __align__(8) uint64_t s_full[FS];
+    __shared__ int s_prog[8];
     const TileCtx c = tile_ctx(g, offsets, worklist);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nbatch = (c.end - c.start + FB - 1) / FB;
+    if (threadIdx.x < FS) mbar_init(&s_full[threadIdx.x], 32);
+    if (threadIdx.x < 8) s_prog[threadIdx.x] = 0;
+    __syncthreads();
+
+    if (wid == 8) {
+        // ---------------- producer warp ----------------
+        // list ids are fetched three batches ahead into three register sets (the loop is unrolled by
+        // three so that no set is ever copied), records FS - 1 batches ahead into the ring
+        uint32_t idsA[FB / 32], idsB[FB / 32], idsC[FB / 32];
+        auto load_ids = [&](uint32_t (&ids)[FB / 32], int b) {
+            const int first = c.start + b * FB;
+            const int n = min(FB, c.end - first);
+#pragma unroll
+            for (int k = 0; k < FB / 32; ++k) ids[k] = (k * 32 + lane < n) ? __ldg(vals + first + k * 32 + lane) : 0u;
+        };
+        // returns false when every consumer has retired
+        auto produce = [&](const uint32_t (&ids)[FB / 32], int b) -> bool {
+            const int slot = b % FS;
+            if (b >= FS) { // wait until all eight consumers have passed batch b - FS (or retired)
+                const int need = b - FS + 1;
+                unsigned spins = 0;
+                int mn;
+                for (;;) {
+                    const int v = ld_acquire(&s_prog[lane & 7]);
+                    mn = __reduce_min_sync(FULL, v);
+                    if (mn >= need) break;
+                    __nanosleep(32);
+                    if (++spins > SPIN_LIMIT) __trap();
+                }
+                if (mn == PROG_DONE) return false; // every pixel of the tile is terminated
+            }
+            const int nvalid = min(FB, c.end - (c.start + b * FB));
+#pragma unroll
+            for (int k = 0; k < FB / 32; ++k) {
+                const int j = k * 32 + lane;
+                if (j < nvalid) {
+                    const uint32_t id = ids[k];
+                    cp_async16(&s_r0[slot][j], t.rec0 + id);
+                    cp_async16(&s_r1[slot][j], t.rec1 + id);
+                    cp_async16(&s_r2[slot][j], t.rec2 + id);
+                }
+            }
+            cp_async_arrive(&s_full[slot]);
+            return true;
+        };
+        load_ids(idsA, 0);
+        load_ids(idsB, 1);
+        load_ids(idsC, 2);
+        for (int b = 0; b < nbatch; b += 3) {
+            if (!produce(idsA, b)) break;
+            load_ids(idsA, b + 3);
+            if (b + 1 >= nbatch || !produce(idsB, b + 1)) break;
+            load_ids(idsB, b + 4);
+            if (b + 2 >= nbatch || !produce(idsC, b + 2)) break;
+            load_ids(idsC, b + 5);
+        }
+        cp_async_wait_all();
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
     const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
     float T = 1.0f, Tpen = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
     int cnt = 0, lastpos = c.start;
     bool done = !c.inside;
-    const int nbatch = (c.end - c.start + RB - 1) / RB;
     for (int b = 0; b < nbatch; ++b) {
-        // barrier: everyone is finished with the previous batch; also the CTA-wide early exit
-        if (__syncthreads_count(done) == (int)blockDim.x) break;
-        const int first = c.start + b * RB;
-        const int nvalid = min(RB, c.end - first);
-        stage_batch(t, vals, first, nvalid, s_r0, s_r1, s_r2, nullptr);
-        __syncthreads();
+        if (__all_sync(FULL, done)) break;
+        const int slot = b % FS;
+        mbar_wait(&s_full[slot], (uint32_t)((b / FS) & 1));
+        const int first = c.start + b * FB;
+        const int nvalid = min(FB, c.end - first);
         if (STATS && threadIdx.x == 0) st_staged += nvalid;
-        if (__all_sync(0xffffffffu, done)) continue;
-        for (int k = 0; k * 32 < nvalid; ++k) {
+        const float4 *q0 = s_r0[slot], *q1 = s_r1[slot], *q2 = s_r2[slot];
+        // cull the whole slot first, against the bounding box of the pixels that are still live (terminated
+        // pixels ignore every splat): FB / 32 independent tests per lane (instruction-level parallelism)
+        int ax0, ax1, ay0, ay1;
+        active_box(__ballot_sync(FULL, !done), ax0, ax1, ay0, ay1);
+        const float fx0 = (float)(c.bx + ax0) + 0.5f, fx1 = (float)(c.bx + ax1) + 0.5f;
+        const float fy0 = (float)(c.by + ay0) + 0.5f, fy1 = (float)(c.by + ay1) + 0.5f;
+        uint32_t masks[FB / 32];
+#pragma unroll
+        for (int k = 0; k < FB / 32; ++k) {
             const int j = k * 32 + lane;
-            uint32_t mask = __ballot_sync(0xffffffffu, j < nvalid && block_hit<MODE>(s_r0[j], c.bx, c.by));
+            bool hit = false;
+            if (j < nvalid) {
+                const float4 a0 = q0[j];
+                if (MODE == PS_MODE_3D) {
+                    const float4 a1 = q1[j];
+                    hit = ellipse_hits_box(a0.x, a0.y, a1.x, a1.y, a1.z, q2[j].w, fx0, fx1, fy0, fy1);
+                } else {
+                    hit = rect_hits_box(a0.z, a0.w, c.bx + ax0, c.bx + ax1, c.by + ay0, c.by + ay1);
+                }
+            }
+            masks[k] = __ballot_sync(FULL, hit);
+        }
+#pragma unroll
+        for (int k = 0; k < FB / 32; ++k) {
+            uint32_t mask = masks[k];
             if (STATS) { if (lane == 0) st_walk += __popc(mask); st_eval += done ? 0 : __popc(mask); }
+            // survivors two at a time: the two alpha evaluations are independent chains, the compositing is ordered
             while (mask) {
-                const int e = k * 32 + __ffs(mask) - 1;
+                const int ea = k * 32 + __ffs(mask) - 1;
                 mask &= mask - 1;
-                const float4 r0 = s_r0[e], r1 = s_r1[e];
+                const bool two = mask != 0;
+                const int eb = two ? k * 32 + __ffs(mask) - 1 : ea;
+                mask &= mask - 1;
+                const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
                 if (MODE == PS_MODE_3D) {
                     float dx, dy;
-                    const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
-                    const bool cand = !done && sg >= 0.0f && sg <= SIGMA_SKIP;
-                    if (!__any_sync(0xffffffffu, cand)) continue;
-                    const float a = fminf(PS_ALPHA_MAX, psm_mul(r1.w, psm_exp(-sg)));
-                    if (cand && a >= PS_ALPHA_MIN) {
-                        const float nT = psm_mul(T, psm_sub(1.0f, a));
+                    const float thra = q2[ea].w, thrb = q2[eb].w;
+                    const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
+                    const float sgb = ps_sigma3d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, pxf, pyf, &dx, &dy);
+                    const bool canda = !done && sga >= 0.0f && sga <= thra + THR_SLACK;
+                    bool candb = two && !done && sgb >= 0.0f && sgb <= thrb + THR_SLACK;
+                    if (!__any_sync(FULL, canda || candb)) continue;
+                    // candidates have 0 <= sigma <= ~5.6: the clamp inside psm_exp2 is the identity for them
+                    const float aa = fminf(PS_ALPHA_MAX, psm_mul(r1a.w, psm_exp2_inrange(psm_mul(-sga, 0x1.715476p+0f))));
+                    const float ab = fminf(PS_ALPHA_MAX, psm_mul(r1b.w, psm_exp2_inrange(psm_mul(-sgb, 0x1.715476p+0f))));
+                    if (canda && aa >= PS_ALPHA_MIN) {
+                        const float nT = psm_mul(T, psm_sub(1.0f, aa));
                         if (nT <= PS_T_STOP_3D) {
                             done = true;
                         } else {
-                            const float4 r2 = s_r2[e];
-                            const float vis = psm_mul(a, T);
+                            const float4 r2 = q2[ea];
+                            const float vis = psm_mul(aa, T);
                             cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                            Tpen = T; T = nT; ++cnt; lastpos = first + e + 1;
+                            Tpen = T; T = nT; ++cnt; lastpos = first + ea + 1;
+                        }
+                    }
+                    if (candb && !done && ab >= PS_ALPHA_MIN) {
+                        const float nT = psm_mul(T, psm_sub(1.0f, ab));
+                        if (nT <= PS_T_STOP_3D) {
+                            done = true;
+                        } else {
+                            const float4 r2 = q2[eb];
+                            const float vis = psm_mul(ab, T);
+                            cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                            Tpen = T; T = nT; ++cnt; lastpos = first + eb + 1;
                         }
                     }
                 } else {
-                    const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
-                    const bool in = !done && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
-                                    c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
-                    if (!__any_sync(0xffffffffu, in)) continue;
+                    const uint32_t loa = __float_as_uint(r0a.z), hia = __float_as_uint(r0a.w);
+                    const uint32_t lob = __float_as_uint(r0b.z), hib = __float_as_uint(r0b.w);
+                    const bool ina = !done && c.px >= (int)(loa & 0xffff) && c.px <= (int)(hia & 0xffff) &&
+                                     c.py >= (int)(loa >> 16) && c.py <= (int)(hia >> 16);
+                    const bool inb = two && !done && c.px >= (int)(lob & 0xffff) && c.px <= (int)(hib & 0xffff) &&
+                                     c.py >= (int)(lob >> 16) && c.py <= (int)(hib >> 16);
+                    if (!__any_sync(FULL, ina || inb)) continue;
                     float dxr, dyr;
-                    const float4 r2 = s_r2[e];
-                    const float q = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
-                    const float gv = psm_mul(r2.w, psm_exp(-q));
-                    if (in) {
-                        const float contrib = psm_mul(gv, T);
-                        cr = psm_fma(contrib, r2.x, cr); cg = psm_fma(contrib, r2.y, cg); cb = psm_fma(contrib, r2.z, cb);
-                        Tpen = T; T = psm_mul(T, psm_sub(1.0f, gv)); ++cnt; lastpos = first + e + 1;
+                    const float4 r2a = q2[ea], r2b = q2[eb];
+                    const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
+                    const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
+                    const float gva = psm_mul(r2a.w, psm_exp(-qa));
+                    const float gvb = psm_mul(r2b.w, psm_exp(-qb));
+                    if (ina) {
+                        const float contrib = psm_mul(gva, T);
+                        cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
+                        Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; lastpos = first + ea + 1;
+                        if (T <= PS_T_STOP_2D) done = true;
+                    }
+                    if (inb && !done) {
+                        const float contrib = psm_mul(gvb, T);
+                        cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
+                        Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; lastpos = first + eb + 1;
                         if (T <= PS_T_STOP_2D) done = true;
                     }
                 }
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            if (__all_sync(FULL, done)) break;
         }
+        __syncwarp();
+        if (lane == 0) st_release(&s_prog[wid], b + 1); // this warp no longer reads slot b % FS
     }
+    if (lane == 0) st_release(&s_prog[wid], PROG_DONE);
     if (c.inside) {
         const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
         const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
@@ -163,8 +376,8 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         unsigned long long contributing = (unsigned long long)cnt;
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
-            st_eval += __shfl_xor_sync(0xffffffffu, st_eval, d);
-            contributing += __shfl_xor_sync(0xffffffffu, contributing, d);
+            st_eval += __shfl_xor_sync(FULL, st_eval, d);
+            contributing += __shfl_xor_sync(FULL, contributing, d);
         }
         if (lane == 0) {
             atomicAdd(stats + 0, st_eval);
@@ -299,8 +512,8 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                                 v[3] = 0.5f * v_sigma * dx * dx;
                                 v[4] = v_sigma * dx * dy;
                                 v[5] = 0.5f * v_sigma * dy * dy;
-                                v[6] = v_sigma * (r1.x * dx + r1.y * dy);
-                                v[7] = v_sigma * (r1.y * dx + r1.z * dy);
+                                v[6] = v_sigma * (2.0f * r1.x * dx + r1.y * dy);
+                                v[7] = v_sigma * (r1.y * dx + 2.0f * r1.z * dy);
                                 v8 = ex * v_alpha;
                             }
                         }
@@ -355,7 +568,7 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
 {
     if (n_work <= 0) return 0;
     const unsigned grid = (unsigned)n_work;
-#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, t_pen, stats)
+#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, FWD_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, t_pen, stats)
     if (g.mode == PS_MODE_3D) { if (stats) PS_FWD(PS_MODE_3D, true); else PS_FWD(PS_MODE_3D, false); }
     else { if (stats) PS_FWD(PS_MODE_2D, true); else PS_FWD(PS_MODE_2D, false); }
 #undef PS_FWD

@@ -53,8 +53,12 @@ def hc_project(mode, params, W, H, V=None, K=None, near=0.01, far=1e10, clip=0.0
     return r, tile, low
 
 
-def records_from_oracle(mode, tab):
-    """Oracle table -> the product's [N,12] record layout (rec0|rec1|rec2) for bit-exact comparison."""
+def records_from_oracle(mode, tab, table=False):
+    """Oracle table -> the product's [N,12] record layout (rec0|rec1|rec2) for bit-exact comparison.
+
+    table=False: the contract-level PsRecord (A, B, C | depth).  table=True: the layout the projection kernel
+    stores in HBM for the 3D rasterizer: exact halvings A/2, C/2 and thr = log(255 * opacity) in place of depth
+    (depth bits live in their own array, tap "depth")."""
     g, rgb, rect = tab["geom"], tab["rgb"], tab["rect"]
     N = g.shape[0]
     r = np.zeros((N, 12), np.float32)
@@ -65,6 +69,12 @@ def records_from_oracle(mode, tab):
         r[:, 4:8] = g[:, 2:6]
         r[:, 8:11] = rgb
         r[:, 11] = g[:, 6]
+        if table:
+            from oracle import oracle as ora
+            r[:, 4] = np.float32(0.5) * g[:, 2]
+            r[:, 6] = np.float32(0.5) * g[:, 4]
+            thr = ora.math_probe((g[:, 5] * np.float32(255.0)).astype(np.float32))["log"]
+            r[:, 11] = np.where(g[:, 6] != 0, thr, np.float32(0.0))  # set only for Gaussians that survive every cull
     else:
         r[:, 0:2] = g[:, 0:2]
         lo = (rect[:, 0].astype(np.uint32) | (rect[:, 1].astype(np.uint32) << 16))

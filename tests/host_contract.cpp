@@ -32,7 +32,7 @@ void hc_project(int mode, const float *params, int N, const float *V, const floa
 void hc_pairs3d(const float *g /*x y A B C*/, const float *px, const float *py, int n, float *sigma)
 {
     float dx, dy;
-    for (int i = 0; i < n; ++i) sigma[i] = ps_sigma3d(g[0], g[1], g[2], g[3], g[4], px[i], py[i], &dx, &dy);
+    for (int i = 0; i < n; ++i) sigma[i] = ps_sigma3d(g[0], g[1], psm_mul(0.5f, g[2]), g[3], psm_mul(0.5f, g[4]), px[i], py[i], &dx, &dy);
 }
 void hc_pairs2d(const float *g /*u v cs sn iax iay*/, const float *x, const float *y, int n, float *q)
 {

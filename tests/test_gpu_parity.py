@@ -54,9 +54,13 @@ def _compare(mode, params, view_frame, W, H, bg, viewmats=None, Ks=None, seed_w=
     rec = torch.cat([sv.tap("rec0"), sv.tap("rec1"), sv.tap("rec2")], 1).cpu().numpy().reshape(V, N, 12)
     touched = sv.tap("tiles_touched").cpu().numpy().reshape(V, N)
     for v in range(V):
-        r_want, _ = records_from_oracle(mode, want["views"][v]["tab"])
+        r_want, _ = records_from_oracle(mode, want["views"][v]["tab"], table=True)
         assert np.array_equal(touched[v], want["views"][v]["tab"]["tiles"]), f"tiles_touched differ (view {v})"
         assert np.array_equal(bits(rec[v]), bits(r_want)), f"splat records differ (view {v})"
+    if mode == "3d":
+        depth = sv.tap("depth").cpu().numpy().view(np.uint32).reshape(V, N)
+        for v in range(V):
+            assert np.array_equal(depth[v], want["views"][v]["tab"]["low"]), f"depth words differ (view {v})"
     # --- binning: bit-exact
     assert int(info.n_isect) == len(want["keys"])
     assert np.array_equal(sv.tap("isect_keys").cpu().numpy(), want["keys"]), "sorted keys differ"
