@@ -305,10 +305,12 @@ def run_b200(args):
     VN = V * (args.n or cfg["n"])
     # rank: depth word + listed flag in, order + rank out; partition: rect + count + rank in, 4 B slot out per entry;
     # list sort: slot in, order gather, 4 B value out per entry; scan: one int in/out per (view, tile)
-    sort_bytes = (VN * 16 if mode == "3d" else 0) + VN * 16 + M * 4 + M * 12 + 8 * V * info.tiles_x * info.tiles_y
-    sort_ms = stage_ms["rank"][0] + stage_ms["scan"][0] + stage_ms["partition"][0] + stage_ms["sort"][0]
+    # block lists: list id + 32 B (3D) / 16 B (2D) record gather in, ~1.8 block entries of 4 B out per list entry
+    sort_bytes = ((VN * 16 if mode == "3d" else 0) + VN * 16 + M * 4 + M * 12 + 8 * V * info.tiles_x * info.tiles_y
+                  + M * (4 + (32 if mode == "3d" else 16) + 8))
+    sort_ms = stage_ms["rank"][0] + stage_ms["scan"][0] + stage_ms["partition"][0] + stage_ms["sort"][0] + stage_ms["blocks"][0]
     proj_bytes = VN * ((56 if mode == "3d" else 36) + 48 + 8 + 4)
-    roof_hbm = {"bound": "hbm", "kernel": "depth_rank+scan+partition+list_sort", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+    roof_hbm = {"bound": "hbm", "kernel": "depth_rank+scan+partition+list_sort+block_lists", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "frac": (sort_bytes / (sort_ms * 1e-3) / 1e9) / hbm_peak if sort_ms else None,
                 "traffic": None, "peak_source": hbm_src, "work": f"M={M} list entries in {n_lists} non-empty (view,tile) lists, {VN} (view,Gaussian) records",
                 "avg_launch_ms": sort_ms,

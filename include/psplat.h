@@ -39,7 +39,8 @@ extern "C" {
 #define PS_STAGE_RASTER_FWD 5  /* background fill of empty tiles + forward rasterizer                */
 #define PS_STAGE_RASTER_BWD 6
 #define PS_STAGE_PROJECT_BWD 7
-#define PS_N_STAGES 8
+#define PS_STAGE_BLOCKS 8      /* tile lists -> lists of the eight 8x4 pixel blocks of every tile    */
+#define PS_N_STAGES 9
 
 /* what ps_saved_copy can read back (bit-exact parity taps) */
 #define PS_TAP_ISECT_KEYS 1    /* int64 [M]   sorted keys  view<<(32+tile_bits) | tile<<32 | low (low = depth bits in 3D, row in 2D);
@@ -48,9 +49,9 @@ extern "C" {
 #define PS_TAP_TILE_OFFSETS 3  /* int32 [V*n_tiles + 1] first sorted index of every (view, tile)  */
 #define PS_TAP_LAST_IDS 4      /* int32 [V,H,W] 1 + index of last contributing entry              */
 #define PS_TAP_TILES_TOUCHED 5 /* int32 [V*N]                                                    */
-#define PS_TAP_REC0 6          /* float4 [V*N] 3D: x,y,rx,ry     2D: u,v,rect(lo),rect(hi)        */
-#define PS_TAP_REC1 7          /* float4 [V*N] 3D: A/2,B,C/2,opacity  2D: cos,sin,iax,iay        */
-#define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,log(255*opacity)  2D: r,g,b,opacity     */
+#define PS_TAP_REC0 6          /* float4 [V*N] 3D: x,y,log(255*opacity),opacity  2D: u,v,rect(lo),rect(hi) */
+#define PS_TAP_REC1 7          /* float4 [V*N] 3D: A/2,B,C/2,0   2D: cos,sin,iax,iay             */
+#define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,0       2D: r,g,b,opacity               */
 #define PS_TAP_DEPTH 9         /* uint32 [V*N] 3D: bits of the camera-space depth (key low word)  */
 
 typedef struct ps_ctx ps_ctx;     /* per-device context (stream-ordered scratch pool, pinned mailbox) */

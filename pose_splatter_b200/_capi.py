@@ -19,7 +19,7 @@ EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy",
            "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
            "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe")
 
-STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd")
+STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd", "blocks")
 FLAG_RASTER_STATS = 4
 
 

@@ -101,7 +101,8 @@ struct ps_saved {
     int64_t M;
     int n_work;     // non-empty (view, tile) lists
     uint64_t *keys; // sorted int64 keys, materialised only with PS_FLAG_KEEP_BINNING
-    int32_t *last;  // [V,H,W]
+    int32_t *last;  // [V,H,W] tile-list position + 1 of the last contributor (PS_FLAG_KEEP_BINNING: tap only)
+    int32_t *blast; // [V,H,W] block-list index + 1 of the last contributor (what the backward starts from)
     float *t_pen;   // [V,H,W]
 };
 
@@ -163,8 +164,8 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
     dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
     dev_free(sv->t.depth, s);
     dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
-    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s);
-    dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->t_pen, s);
+    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bcount, s);
+    dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->blast, s); dev_free(sv->t_pen, s);
 }
 
 int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
@@ -250,6 +251,9 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             { StageTimer tm(ctx, PS_STAGE_SORT, s);
               PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
               PS_TRY_LAUNCH(ps_launch_sort_lists(g, sv->t, sv->l, sv->n_work, s)); }
+            PS_TRY_CUDA(dev_alloc(&sv->l.blist, (size_t)8 * (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.bcount, (size_t)8 * (size_t)sv->n_work, s));
+            { StageTimer tm(ctx, PS_STAGE_BLOCKS, s); PS_TRY_LAUNCH(ps_launch_block_lists(g, sv->t, sv->l, sv->n_work, s)); }
             if (keep) {
                 PS_TRY_CUDA(dev_alloc(&sv->keys, (size_t)M, s));
                 PS_TRY_LAUNCH(ps_launch_debug_keys(g, sv->t, sv->l, sv->n_work, sv->keys, s));
@@ -257,15 +261,14 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
         }
         if (npix > 0) {
             if (save) {
-                PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
+                PS_TRY_CUDA(dev_alloc(&sv->blast, npix, s));
                 PS_TRY_CUDA(dev_alloc(&sv->t_pen, npix, s));
-            } else if (keep) {
-                PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             }
+            if (keep) PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
-            PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, keep ? sv->last : nullptr, s));
+            PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, s));
             PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->n_work, background, rgb, alpha, n_contrib,
-                                               sv->last, sv->t_pen, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
+                                               sv->last, sv->blast, sv->t_pen, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
         }
     }
 out:
@@ -299,7 +302,7 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
     PS_CUDA(cudaMemsetAsync(d_params, 0, n_out * sizeof(float), s));
     const size_t VN = (size_t)g.V * g.N;
     if (VN == 0 || sv->M == 0 || (size_t)g.H * g.W == 0) return 0;
-    if (!sv->last || !sv->t_pen) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
+    if (!sv->blast || !sv->t_pen) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
     if (!d_rgb || !d_alpha || !params || !view_frame || !background) return fail(1, "ps_backward: NULL buffer");
     float *acc = nullptr;
     PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE, s));
@@ -307,7 +310,7 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
     do {
         if (cudaMemsetAsync(acc, 0, VN * PS_ACC_STRIDE * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
         int n;
-        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->last, sv->t_pen, d_rgb, d_alpha, acc, s); }
+        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc, s); }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
         { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, view_frame, viewmats, Ks, sv->t, acc, d_params, s); }

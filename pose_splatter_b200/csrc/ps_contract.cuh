@@ -128,9 +128,10 @@ PS_HD int ps_tile_bits(int n_tiles)
 // Splat record: what the projection stage leaves per (view, Gaussian) for binning and
 // rasterization.  In HBM it is three 16-byte words so that a tile rasterizer gathers it with
 // three aligned 128-bit copies:
-//   3D  rec0 = x, y, radius_x, radius_y   rec1 = A/2, B, C/2, opacity   rec2 = r, g, b, thr
+//   3D  rec0 = x, y, thr, opacity   rec1 = A/2, B, C/2, 0   rec2 = r, g, b, 0
 //       (A/2, C/2: exact halvings, what the pair arithmetic uses; thr = log(255 * opacity), the
-//        largest sigma that can pass alpha >= 1/255; the depth word goes to its own array)
+//        largest sigma that can pass alpha >= 1/255; rec0 + rec1 is all the culling needs; the radii
+//        only shape the tile rectangle and the depth word goes to its own array)
 //   2D  rec0 = u, v, bits(x0|y0<<16), bits(x1|y1<<16)   rec1 = cos, sin, iax, iay   rec2 = r, g, b, opacity
 // tile rect: tx0, ty0, tx1, ty1 (exclusive max); culled <=> empty.
 // ---------------------------------------------------------------------------------------

@@ -38,6 +38,9 @@ struct PsLists {
     int32_t *cls;       // [2*PS_N_CLASSES] size-class base / fill counters of the work list
     uint32_t *slots;    // [M] depth ranks (3D) / row indices (2D) in list order, unsorted inside a list
     uint32_t *vals;     // [M] view*N + Gaussian, sorted (tile, depth | row)
+    uint32_t *blist;    // [8*M] per-block lists: tile with range [s, s+len) owns [8s, 8s+8len), block k at +k*len;
+                        //       entries = positions relative to s, ascending
+    int32_t *bcount;    // [8*n_work] length of every block list, indexed by work-list item
 };
 
 // every launcher returns the number of kernels it launched (for gpu_launches) or -1 on error
@@ -59,8 +62,10 @@ int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l
 // rasterizers (ps_raster.cu)
 int ps_launch_fill_empty(const PsGeometry &g, const int32_t *offsets, const float *background, float *rgb, float *alpha,
                          int32_t *n_contrib, int32_t *last, cudaStream_t s);
+int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
+// last: tile-list position + 1 of the last contributor (tap); blast: the same as an index into the block list (backward)
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
-                         float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, float *t_pen,
+                         float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, int32_t *blast, float *t_pen,
                          unsigned long long *stats, cudaStream_t s);
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,

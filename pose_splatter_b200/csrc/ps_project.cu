@@ -56,12 +56,13 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
             ps_project2d(s_rows + threadIdx.x * P, (uint32_t)(g0 + threadIdx.x), g.W, g.H, &rec);
         }
         const size_t idx = (size_t)v * g.N + g0 + threadIdx.x;
-        t.rec0[idx] = make_float4(rec.r0[0], rec.r0[1], rec.r0[2], rec.r0[3]);
         if (MODE == PS_MODE_3D) {
-            t.rec1[idx] = make_float4(psm_mul(0.5f, rec.r1[0]), rec.r1[1], psm_mul(0.5f, rec.r1[2]), rec.r1[3]);
-            t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.thr);
+            t.rec0[idx] = make_float4(rec.r0[0], rec.r0[1], rec.thr, rec.r1[3]);
+            t.rec1[idx] = make_float4(psm_mul(0.5f, rec.r1[0]), rec.r1[1], psm_mul(0.5f, rec.r1[2]), 0.0f);
+            t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], 0.0f);
             t.depth[idx] = rec.low;
         } else {
+            t.rec0[idx] = make_float4(rec.r0[0], rec.r0[1], rec.r0[2], rec.r0[3]);
             t.rec1[idx] = make_float4(rec.r1[0], rec.r1[1], rec.r1[2], rec.r1[3]);
             t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
         }

@@ -1,20 +1,25 @@
-// ps_raster.cu -- per-tile rasterizers (SURVEY.md 2.2 K5', K6'), both gaussian modes.
+// ps_raster.cu -- per-tile rasterizers (SURVEY.md 2.2 K5', K6'), both gaussian modes.  (v4)
 //
-// One CTA per non-empty (view, 16x16 tile) list, taken from the size-ordered work list.
-//
-// forward (v2): 8 consumer warps, each owning an 8x4 pixel block, + 1 producer warp.  The producer
-//   streams the tile's sorted list through a ring of shared-memory slots (128 splat records of 48 B
-//   per slot) with cp.async gathers that complete on an mbarrier per slot; consumers never meet at a
-//   CTA barrier: each waits for the slot it needs, culls the 128 records against its own block
-//   (one record per lane: exact ellipse-vs-rectangle test in 3D -- the minimum of sigma over the block
-//   against log(255*opacity) --, rectangle-vs-rectangle in 2D), walks the survivors in list order and
-//   publishes its progress; the producer refills a slot when all eight have passed it.  A warp whose
-//   32 pixels are all terminated retires on its own.  Culling never changes a result: it only
-//   removes pairs whose alpha test (3D) / rectangle test (2D) is guaranteed to fail.
-// backward: reverse replay from last_id; transmittance recovered by division starting from the saved
-//   "T before the last contributor"; per-splat gradients are reduced across the warp (multi-value
-//   butterfly), accumulated per CTA in shared memory and flushed with one vector
-//   red.global.add.v4.f32 triple per (tile, splat).
+// block_lists: every non-empty (view, 16x16 tile) list is split, in list order, into the lists of its eight
+//   8x4 pixel blocks: an entry goes to a block only if the splat can contribute there (3D: exact
+//   ellipse-vs-box test, min of sigma over the block's pixel centres against log(255*opacity); 2D: the
+//   splat's pixel rectangle meets the block).  One CTA per tile, one list entry per thread, ordered
+//   multi-split with ballots.  The block lists hold positions in the tile list (4 B each).
+// forward / backward: the unit of work is one WARP = one pixel block; a CTA is two such warps that share
+//   nothing (no __syncthreads), so a block that finishes early frees its slot: this workload is dominated by
+//   a few very long lists in which, at any depth, only some blocks still have live pixels.
+//   Tasks are launched in the size order of the work list.  A warp streams its block list 32 entries at a
+//   time (one per lane): position -> Gaussian id -> cp.async of the 48-byte splat record into a warp-private
+//   3-stage ring in shared memory, two chunks ahead of use; the lane re-culls its entry against the bounding
+//   box of the pixels that are still live (forward: not terminated; backward: still have contributors at or
+//   before this chunk); survivors (ballot) are walked in list order with broadcast reads of the ring.
+//   Culling never changes a result: it only removes pairs whose alpha test (3D) / rectangle test (2D) is
+//   guaranteed to fail for every live pixel.
+//     forward : front-to-back compositing, two survivors in flight, per-warp early exit   [FP32 pipe + smem]
+//     backward: reverse replay from the block's last contributor; transmittance recovered by division from
+//               the saved "T before the last contributor"; the nine per-splat gradient sums are reduced over
+//               the warp (multi-value butterfly) and added to the (view, Gaussian) accumulator row with
+//               red.global.add                                                          [FP32 pipe + shfl]
 // Replaces gsplat rasterize_to_pixels_3dgs_fwd/bwd (absent from the reference tree) and the
 // torch element-wise loop src/gaussian_renderer.py:379-425 plus its autograd.
 #include "ps_contract.cuh"
@@ -22,38 +27,40 @@
 
 namespace {
 
-constexpr int RB = PS_RASTER_BATCH;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr float CULL_MARGIN = 1.0f;  // px of slack on the 3D rectangle test of the backward (exact in real arithmetic)
-constexpr float SIGMA_SKIP = 5.6f;   // sigma above ln(255) can never pass alpha >= 1/255 (opacity <= 1)
-constexpr float THR_SLACK = 0.01f;   // slack on sigma <= log(255*opacity): covers the rounding of exp / log / sigma
+constexpr float THR_SLACK = 0.01f;  // slack on sigma <= log(255*opacity): covers the rounding of exp / log / sigma
+constexpr int CH = 32;              // list entries per chunk (one per lane)
+constexpr int NS = 3;               // ring stages per warp
+constexpr int WPC = 2;              // warps (pixel blocks) per CTA
+constexpr int RT_THREADS = WPC * 32;
+constexpr int TASKS_PER_TILE = 8 / WPC;
 
-// ---- forward ring ----
-constexpr int FB = 128;            // records per slot
-constexpr int FS = 6;              // slots
-constexpr int FWD_THREADS = 288;   // 8 consumer warps + 1 producer warp
-constexpr int PROG_DONE = 0x7fffffff;
-constexpr unsigned SPIN_LIMIT = 1u << 26;
-
-struct TileCtx {
-    int view, tile, start, end;
-    int px, py;   // this lane's pixel
-    int bx, by;   // warp block origin
+struct BlockCtx {
+    int view, start, len;   // tile list [start, start + len)
+    int nb;                 // entries of this block's list
+    const uint32_t *bl;     // this block's list: positions relative to `start`, ascending
+    int px, py;             // this lane's pixel
+    int bx, by;             // block origin
     bool inside;
 };
 
-__device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist)
+__device__ __forceinline__ BlockCtx block_ctx(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist,
+                                              const uint32_t *blist, const int32_t *bcount)
 {
-    TileCtx c;
-    const int lin = worklist[blockIdx.x]; // non-empty (view, tile) lists, longest size class first
+    BlockCtx c;
+    const int item = blockIdx.x / TASKS_PER_TILE;
+    const int blk = (blockIdx.x % TASKS_PER_TILE) * WPC + (threadIdx.x >> 5); // 0..7: x half = blk & 1, y quarter = blk >> 1
+    const int lin = worklist[item]; // non-empty (view, tile) lists, longest size class first
     c.view = lin / g.n_tiles;
-    c.tile = lin - c.view * g.n_tiles;
-    const int ty = c.tile / g.tiles_x, tx = c.tile - ty * g.tiles_x;
+    const int tile = lin - c.view * g.n_tiles;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
     c.start = offsets[lin];
-    c.end = offsets[lin + 1];
-    const int lane = threadIdx.x & 31, wid = (threadIdx.x >> 5) & 7;
-    c.bx = tx * PS_TILE + (wid & 1) * 8;
-    c.by = ty * PS_TILE + (wid >> 1) * 4;
+    c.len = offsets[lin + 1] - c.start;
+    c.nb = bcount[item * 8 + blk];
+    c.bl = blist + 8 * (size_t)c.start + (size_t)blk * c.len;
+    const int lane = threadIdx.x & 31;
+    c.bx = tx * PS_TILE + (blk & 1) * 8;
+    c.by = ty * PS_TILE + (blk >> 1) * 4;
     c.px = c.bx + (lane & 7);
     c.py = c.by + (lane >> 3);
     c.inside = c.px < g.W && c.py < g.H;
@@ -61,43 +68,13 @@ __device__ __forceinline__ TileCtx tile_ctx(const PsGeometry &g, const int32_t *
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity))
-        if (++spins > SPIN_LIMIT) __trap(); // a lost arrival must fail loudly, never hang the GPU
-}
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
-// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
-__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void st_release(int *p, int v)
-{
-    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 3D: can the splat pass sigma <= thr anywhere on the pixel centres [x0, x1] x [y0, y1]?
 // sigma(u) = hA ux^2 + hC uy^2 + B ux uy (u = pixel - mean) is convex with its minimum at u = 0, so over a
@@ -130,10 +107,6 @@ __device__ __forceinline__ bool rect_hits_box(float lo_bits, float hi_bits, int 
     const int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
     return x0 <= bx1 && x1 >= bx0 && y0 <= by1 && y1 >= by0;
 }
-__device__ __forceinline__ bool rect_hits_block(float lo_bits, float hi_bits, int bx, int by)
-{
-    return rect_hits_box(lo_bits, hi_bits, bx, bx + 7, by, by + 3);
-}
 
 // bounding box (in block-local pixel coordinates) of the lanes set in `active` (lane = y * 8 + x); active != 0
 __device__ __forceinline__ void active_box(uint32_t active, int &x0, int &x1, int &y0, int &y1)
@@ -145,220 +118,166 @@ __device__ __forceinline__ void active_box(uint32_t active, int &x0, int &x1, in
     y1 = (31 - __clz(active)) >> 3;
 }
 
-// does staged record (r0) possibly touch this warp's 8x4 pixel block?  (backward, v1 test)
-template <int MODE>
-__device__ __forceinline__ bool block_hit(const float4 &r0, int bx, int by)
-{
-    if (MODE == PS_MODE_3D) {
-        return fabsf(r0.x - ((float)bx + 4.0f)) <= r0.z + (3.5f + CULL_MARGIN) &&
-               fabsf(r0.y - ((float)by + 2.0f)) <= r0.w + (1.5f + CULL_MARGIN);
-    } else {
-        return rect_hits_block(r0.z, r0.w, bx, by);
-    }
-}
+// The warp-private ring: stage st holds chunk data for 32 entries.
+struct Ring {
+    float4 (*a)[CH], (*b)[CH], (*c)[CH];
+    uint32_t (*pos)[CH]; // position of the entry in the tile list (relative)
+};
 
-__device__ __forceinline__ void stage_batch(const PsTable &t, const uint32_t *__restrict__ vals, int first, int count,
-                                            float4 *s_r0, float4 *s_r1, float4 *s_r2, uint32_t *id_out)
+// lane-parallel cull of the staged chunk against the live-pixel box -> ballot of surviving entries
+template <int MODE>
+__device__ __forceinline__ uint32_t cull_chunk(const Ring &q, int st, int lane, bool valid, const BlockCtx &c, uint32_t live)
 {
-    if ((int)threadIdx.x < count) {
-        const uint32_t id = __ldg(vals + first + threadIdx.x);
-        s_r0[threadIdx.x] = __ldg(t.rec0 + id);
-        s_r1[threadIdx.x] = __ldg(t.rec1 + id);
-        s_r2[threadIdx.x] = __ldg(t.rec2 + id);
-        if (id_out) *id_out = id;
+    int ax0, ax1, ay0, ay1;
+    active_box(live, ax0, ax1, ay0, ay1);
+    bool hit = false;
+    if (valid) {
+        const float4 a0 = q.a[st][lane];
+        if (MODE == PS_MODE_3D) {
+            const float4 a1 = q.b[st][lane];
+            hit = ellipse_hits_box(a0.x, a0.y, a1.x, a1.y, a1.z, a0.z, (float)(c.bx + ax0) + 0.5f,
+                                   (float)(c.bx + ax1) + 0.5f, (float)(c.by + ay0) + 0.5f, (float)(c.by + ay1) + 0.5f);
+        } else {
+            hit = rect_hits_box(a0.z, a0.w, c.bx + ax0, c.bx + ax1, c.by + ay0, c.by + ay1);
+        }
     }
+    return __ballot_sync(FULL, hit);
 }
 
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(FWD_THREADS, 5)
+__global__ void __launch_bounds__(RT_THREADS)
 raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const float *__restrict__ background,
                   float *__restrict__ rgb, float *__restrict__ alpha,
-                  int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, float *__restrict__ t_pen,
+                  int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
+                  float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount,
                   unsigned long long *__restrict__ stats)
 {
-    __shared__ float4 s_r0[FS][FB], s_r1[FS][FB], s_r2[FS][FB];
-    __shared__ __align__(8) uint64_t s_full[FS];
-    __shared__ int s_prog[8];
-    const TileCtx c = tile_ctx(g, offsets, worklist);
+    __shared__ float4 s_a[WPC][NS][CH], s_b[WPC][NS][CH], s_c[WPC][NS][CH];
+    __shared__ uint32_t s_pos[WPC][NS][CH];
+    const BlockCtx c = block_ctx(g, offsets, worklist, blist, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nbatch = (c.end - c.start + FB - 1) / FB;
-    if (threadIdx.x < FS) mbar_init(&s_full[threadIdx.x], 32);
-    if (threadIdx.x < 8) s_prog[threadIdx.x] = 0;
-    __syncthreads();
-
-    if (wid == 8) {
-        // ---------------- producer warp ----------------
-        // list ids are fetched three batches ahead into three register sets (the loop is unrolled by
-        // three so that no set is ever copied), records FS - 1 batches ahead into the ring
-        uint32_t idsA[FB / 32], idsB[FB / 32], idsC[FB / 32];
-        auto load_ids = [&](uint32_t (&ids)[FB / 32], int b) {
-            const int first = c.start + b * FB;
-            const int n = min(FB, c.end - first);
-#pragma unroll
-            for (int k = 0; k < FB / 32; ++k) ids[k] = (k * 32 + lane < n) ? __ldg(vals + first + k * 32 + lane) : 0u;
-        };
-        // returns false when every consumer has retired
-        auto produce = [&](const uint32_t (&ids)[FB / 32], int b) -> bool {
-            const int slot = b % FS;
-            if (b >= FS) { // wait until all eight consumers have passed batch b - FS (or retired)
-                const int need = b - FS + 1;
-                unsigned spins = 0;
-                int mn;
-                for (;;) {
-                    const int v = ld_acquire(&s_prog[lane & 7]);
-                    mn = __reduce_min_sync(FULL, v);
-                    if (mn >= need) break;
-                    __nanosleep(32);
-                    if (++spins > SPIN_LIMIT) __trap();
-                }
-                if (mn == PROG_DONE) return false; // every pixel of the tile is terminated
-            }
-            const int nvalid = min(FB, c.end - (c.start + b * FB));
-#pragma unroll
-            for (int k = 0; k < FB / 32; ++k) {
-                const int j = k * 32 + lane;
-                if (j < nvalid) {
-                    const uint32_t id = ids[k];
-                    cp_async16(&s_r0[slot][j], t.rec0 + id);
-                    cp_async16(&s_r1[slot][j], t.rec1 + id);
-                    cp_async16(&s_r2[slot][j], t.rec2 + id);
-                }
-            }
-            cp_async_arrive(&s_full[slot]);
-            return true;
-        };
-        load_ids(idsA, 0);
-        load_ids(idsB, 1);
-        load_ids(idsC, 2);
-        for (int b = 0; b < nbatch; b += 3) {
-            if (!produce(idsA, b)) break;
-            load_ids(idsA, b + 3);
-            if (b + 1 >= nbatch || !produce(idsB, b + 1)) break;
-            load_ids(idsB, b + 4);
-            if (b + 2 >= nbatch || !produce(idsC, b + 2)) break;
-            load_ids(idsC, b + 5);
+    bool done = !c.inside;
+    if (__all_sync(FULL, done)) return; // block entirely outside the image
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid], s_pos[wid] };
+    const int len = c.nb;
+    const int nchunks = (len + CH - 1) / CH;
+    const uint32_t *list = vals + c.start;
+    // chunk cj: list position (ld) -> Gaussian id (dependent ld) -> record copies (cp.async); the three steps of
+    // consecutive chunks are software-pipelined: positions run 4 chunks ahead, ids 3, records 2
+    auto issue = [&](int cj, uint32_t pos, uint32_t id) { // one commit group per chunk, also when it does not exist
+        if (cj * CH + lane < len) {
+            const int st = cj % NS;
+            q.pos[st][lane] = pos;
+            cp_async16(&q.a[st][lane], t.rec0 + id);
+            cp_async16(&q.b[st][lane], t.rec1 + id);
+            cp_async16(&q.c[st][lane], t.rec2 + id);
         }
-        cp_async_wait_all();
-        return;
+        cp_async_commit();
+    };
+    auto fetch_pos = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
+    uint32_t posn, posnn, idn;
+    {
+        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
+        posn = fetch_pos(2);
+        posnn = fetch_pos(3);
+        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
+        issue(0, p0, i0);
+        issue(1, p1, i1);
+        idn = __ldg(list + posn);
     }
 
-    // ---------------- consumer warps ----------------
     unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
     const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
     float T = 1.0f, Tpen = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
-    int cnt = 0, lastpos = c.start;
-    bool done = !c.inside;
-    for (int b = 0; b < nbatch; ++b) {
-        if (__all_sync(FULL, done)) break;
-        const int slot = b % FS;
-        mbar_wait(&s_full[slot], (uint32_t)((b / FS) & 1));
-        const int first = c.start + b * FB;
-        const int nvalid = min(FB, c.end - first);
-        if (STATS && threadIdx.x == 0) st_staged += nvalid;
-        const float4 *q0 = s_r0[slot], *q1 = s_r1[slot], *q2 = s_r2[slot];
-        // cull the whole slot first, against the bounding box of the pixels that are still live (terminated
-        // pixels ignore every splat): FB / 32 independent tests per lane (instruction-level parallelism)
-        int ax0, ax1, ay0, ay1;
-        active_box(__ballot_sync(FULL, !done), ax0, ax1, ay0, ay1);
-        const float fx0 = (float)(c.bx + ax0) + 0.5f, fx1 = (float)(c.bx + ax1) + 0.5f;
-        const float fy0 = (float)(c.by + ay0) + 0.5f, fy1 = (float)(c.by + ay1) + 0.5f;
-        uint32_t masks[FB / 32];
-#pragma unroll
-        for (int k = 0; k < FB / 32; ++k) {
-            const int j = k * 32 + lane;
-            bool hit = false;
-            if (j < nvalid) {
-                const float4 a0 = q0[j];
-                if (MODE == PS_MODE_3D) {
-                    const float4 a1 = q1[j];
-                    hit = ellipse_hits_box(a0.x, a0.y, a1.x, a1.y, a1.z, q2[j].w, fx0, fx1, fy0, fy1);
-                } else {
-                    hit = rect_hits_box(a0.z, a0.w, c.bx + ax0, c.bx + ax1, c.by + ay0, c.by + ay1);
-                }
-            }
-            masks[k] = __ballot_sync(FULL, hit);
-        }
-#pragma unroll
-        for (int k = 0; k < FB / 32; ++k) {
-            uint32_t mask = masks[k];
-            if (STATS) { if (lane == 0) st_walk += __popc(mask); st_eval += done ? 0 : __popc(mask); }
-            // survivors two at a time: the two alpha evaluations are independent chains, the compositing is ordered
-            while (mask) {
-                const int ea = k * 32 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const bool two = mask != 0;
-                const int eb = two ? k * 32 + __ffs(mask) - 1 : ea;
-                mask &= mask - 1;
-                const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
-                if (MODE == PS_MODE_3D) {
-                    float dx, dy;
-                    const float thra = q2[ea].w, thrb = q2[eb].w;
-                    const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
-                    const float sgb = ps_sigma3d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, pxf, pyf, &dx, &dy);
-                    const bool canda = !done && sga >= 0.0f && sga <= thra + THR_SLACK;
-                    bool candb = two && !done && sgb >= 0.0f && sgb <= thrb + THR_SLACK;
-                    if (!__any_sync(FULL, canda || candb)) continue;
-                    // candidates have 0 <= sigma <= ~5.6: the clamp inside psm_exp2 is the identity for them
-                    const float aa = fminf(PS_ALPHA_MAX, psm_mul(r1a.w, psm_exp2_inrange(psm_mul(-sga, 0x1.715476p+0f))));
-                    const float ab = fminf(PS_ALPHA_MAX, psm_mul(r1b.w, psm_exp2_inrange(psm_mul(-sgb, 0x1.715476p+0f))));
-                    if (canda && aa >= PS_ALPHA_MIN) {
-                        const float nT = psm_mul(T, psm_sub(1.0f, aa));
-                        if (nT <= PS_T_STOP_3D) {
-                            done = true;
-                        } else {
-                            const float4 r2 = q2[ea];
-                            const float vis = psm_mul(aa, T);
-                            cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                            Tpen = T; T = nT; ++cnt; lastpos = first + ea + 1;
-                        }
-                    }
-                    if (candb && !done && ab >= PS_ALPHA_MIN) {
-                        const float nT = psm_mul(T, psm_sub(1.0f, ab));
-                        if (nT <= PS_T_STOP_3D) {
-                            done = true;
-                        } else {
-                            const float4 r2 = q2[eb];
-                            const float vis = psm_mul(ab, T);
-                            cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                            Tpen = T; T = nT; ++cnt; lastpos = first + eb + 1;
-                        }
-                    }
-                } else {
-                    const uint32_t loa = __float_as_uint(r0a.z), hia = __float_as_uint(r0a.w);
-                    const uint32_t lob = __float_as_uint(r0b.z), hib = __float_as_uint(r0b.w);
-                    const bool ina = !done && c.px >= (int)(loa & 0xffff) && c.px <= (int)(hia & 0xffff) &&
-                                     c.py >= (int)(loa >> 16) && c.py <= (int)(hia >> 16);
-                    const bool inb = two && !done && c.px >= (int)(lob & 0xffff) && c.px <= (int)(hib & 0xffff) &&
-                                     c.py >= (int)(lob >> 16) && c.py <= (int)(hib >> 16);
-                    if (!__any_sync(FULL, ina || inb)) continue;
-                    float dxr, dyr;
-                    const float4 r2a = q2[ea], r2b = q2[eb];
-                    const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
-                    const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
-                    const float gva = psm_mul(r2a.w, psm_exp(-qa));
-                    const float gvb = psm_mul(r2b.w, psm_exp(-qb));
-                    if (ina) {
-                        const float contrib = psm_mul(gva, T);
-                        cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
-                        Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; lastpos = first + ea + 1;
-                        if (T <= PS_T_STOP_2D) done = true;
-                    }
-                    if (inb && !done) {
-                        const float contrib = psm_mul(gvb, T);
-                        cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
-                        Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; lastpos = first + eb + 1;
-                        if (T <= PS_T_STOP_2D) done = true;
-                    }
-                }
-            }
-            if (__all_sync(FULL, done)) break;
-        }
+    int cnt = 0;
+    int blastpos = 0; // 1 + index (in the block list) of the last contributor
+    for (int ci = 0; ci < nchunks; ++ci) {
+        issue(ci + 2, posn, idn);
+        posn = posnn;
+        idn = __ldg(list + posn);
+        posnn = fetch_pos(ci + 4);
+        cp_async_wait_group<2>(); // chunk ci has landed (this lane's copies); the barrier makes all lanes' visible
         __syncwarp();
-        if (lane == 0) st_release(&s_prog[wid], b + 1); // this warp no longer reads slot b % FS
+        const int st = ci % NS;
+        const int first = ci * CH;
+        uint32_t mask = cull_chunk<MODE>(q, st, lane, ci * CH + lane < len, c, __ballot_sync(FULL, !done));
+        if (STATS) { st_staged += 1; if (lane == 0) st_walk += __popc(mask); st_eval += done ? 0 : __popc(mask); }
+        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        // survivors two at a time: the two alpha evaluations are independent chains, the compositing is ordered
+        while (mask) {
+            const int ea = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const bool two = mask != 0;
+            const int eb = two ? __ffs(mask) - 1 : ea;
+            mask &= mask - 1;
+            const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
+            if (MODE == PS_MODE_3D) {
+                float dx, dy;
+                const float thra = r0a.z, thrb = r0b.z;
+                const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
+                const float sgb = ps_sigma3d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, pxf, pyf, &dx, &dy);
+                const bool canda = !done && sga >= 0.0f && sga <= thra + THR_SLACK;
+                const bool candb = two && !done && sgb >= 0.0f && sgb <= thrb + THR_SLACK;
+                if (!__any_sync(FULL, canda || candb)) continue;
+                // candidates have 0 <= sigma <= ~5.6: the clamp inside psm_exp2 is the identity for them
+                const float aa = fminf(PS_ALPHA_MAX, psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-sga, 0x1.715476p+0f))));
+                const float ab = fminf(PS_ALPHA_MAX, psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-sgb, 0x1.715476p+0f))));
+                if (canda && aa >= PS_ALPHA_MIN) {
+                    const float nT = psm_mul(T, psm_sub(1.0f, aa));
+                    if (nT <= PS_T_STOP_3D) {
+                        done = true;
+                    } else {
+                        const float4 r2 = q2[ea];
+                        const float vis = psm_mul(aa, T);
+                        cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1;
+                    }
+                }
+                if (candb && !done && ab >= PS_ALPHA_MIN) {
+                    const float nT = psm_mul(T, psm_sub(1.0f, ab));
+                    if (nT <= PS_T_STOP_3D) {
+                        done = true;
+                    } else {
+                        const float4 r2 = q2[eb];
+                        const float vis = psm_mul(ab, T);
+                        cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1;
+                    }
+                }
+            } else {
+                const uint32_t loa = __float_as_uint(r0a.z), hia = __float_as_uint(r0a.w);
+                const uint32_t lob = __float_as_uint(r0b.z), hib = __float_as_uint(r0b.w);
+                const bool ina = !done && c.px >= (int)(loa & 0xffff) && c.px <= (int)(hia & 0xffff) &&
+                                 c.py >= (int)(loa >> 16) && c.py <= (int)(hia >> 16);
+                const bool inb = two && !done && c.px >= (int)(lob & 0xffff) && c.px <= (int)(hib & 0xffff) &&
+                                 c.py >= (int)(lob >> 16) && c.py <= (int)(hib >> 16);
+                if (!__any_sync(FULL, ina || inb)) continue;
+                float dxr, dyr;
+                const float4 r2a = q2[ea], r2b = q2[eb];
+                const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
+                const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
+                const float gva = psm_mul(r2a.w, psm_exp(-qa));
+                const float gvb = psm_mul(r2b.w, psm_exp(-qb));
+                if (ina) {
+                    const float contrib = psm_mul(gva, T);
+                    cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1;
+                    if (T <= PS_T_STOP_2D) done = true;
+                }
+                if (inb && !done) {
+                    const float contrib = psm_mul(gvb, T);
+                    cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1;
+                    if (T <= PS_T_STOP_2D) done = true;
+                }
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+        __syncwarp(); // every lane is finished with stage st before chunk ci + 3 is copied into it
     }
-    if (lane == 0) st_release(&s_prog[wid], PROG_DONE);
+    cp_async_wait_group<0>();
     if (c.inside) {
         const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
         const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
@@ -367,11 +286,12 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         rgb[3 * p + 2] = psm_fma(T, b2, cb);
         alpha[p] = psm_sub(1.0f, T);
         if (n_contrib) n_contrib[p] = cnt;
-        if (last) last[p] = lastpos;
+        if (last) last[p] = c.start + (blastpos ? (int)__ldg(c.bl + blastpos - 1) + 1 : 0); // tile-list position
+        if (blast) blast[p] = blastpos;
         if (t_pen) t_pen[p] = Tpen;
     }
     if (STATS) {
-        // lanes that finish inside a group are still counted for the whole group: an upper bound
+        // lanes that finish inside a chunk are still counted for the whole chunk: an upper bound
         // within 32 pairs per (lane, termination), negligible against the totals
         unsigned long long contributing = (unsigned long long)cnt;
 #pragma unroll
@@ -383,24 +303,23 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
             atomicAdd(stats + 0, st_eval);
             atomicAdd(stats + 1, contributing);
             atomicAdd(stats + 2, st_walk);
+            atomicAdd(stats + 3, st_staged * CH);
         }
-        if (threadIdx.x == 0) atomicAdd(stats + 3, st_staged);
     }
 }
 
-// Sum 9 per-lane values over the warp.  v[0..7] go through a halving butterfly (16+8+4+2+2
-// instructions instead of 8 x 10); afterwards lane L holds the total of value (L >> 2) in v[0].
+// Sum 9 per-lane values over the warp.  v[0..7] go through a halving butterfly (4+2+1+1+1 shuffles
+// instead of 8 x 5); afterwards lane L holds the total of value (L >> 2) in v[0].
 // v8 is reduced with the plain 5-step butterfly (every lane gets the total).
 __device__ __forceinline__ void warp_reduce9(float (&v)[8], float &v8, int lane)
 {
-    const uint32_t full = 0xffffffffu;
     {
         const bool hi = lane & 16;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float send = hi ? v[i] : v[i + 4];
             const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(full, send, 16);
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
         }
     }
     {
@@ -409,166 +328,250 @@ __device__ __forceinline__ void warp_reduce9(float (&v)[8], float &v8, int lane)
         for (int i = 0; i < 2; ++i) {
             const float send = hi ? v[i] : v[i + 2];
             const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(full, send, 8);
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
         }
     }
     {
         const bool hi = lane & 4;
         const float send = hi ? v[0] : v[1];
         const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(full, send, 4);
+        v[0] = keep + __shfl_xor_sync(FULL, send, 4);
     }
-    v[0] += __shfl_xor_sync(full, v[0], 2);
-    v[0] += __shfl_xor_sync(full, v[0], 1);
+    v[0] += __shfl_xor_sync(FULL, v[0], 2);
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v8 += __shfl_xor_sync(full, v8, d);
-}
-
-__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+    for (int d = 16; d >= 1; d >>= 1) v8 += __shfl_xor_sync(FULL, v8, d);
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RT_THREADS)
 raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const float *__restrict__ background, const int32_t *__restrict__ last,
                   const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
-                  float *__restrict__ acc)
+                  const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount, float *__restrict__ acc)
 {
-    __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB];
-    __shared__ float s_grad[RB * 9];
-    __shared__ int s_touched[RB];
-    __shared__ int s_tile_end;
-    const TileCtx c = tile_ctx(g, offsets, worklist);
-    const int lane = threadIdx.x & 31;
-    const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
-    const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
-    int my_last = c.start;
+    __shared__ float4 s_a[WPC][NS][CH], s_b[WPC][NS][CH], s_c[WPC][NS][CH];
+    __shared__ uint32_t s_id[WPC][NS][CH];
+    const BlockCtx c = block_ctx(g, offsets, worklist, blist, bcount);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int my_last = 0; // 1 + index in the block list of this pixel's last contributor (saved by the forward)
     float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
     if (c.inside) {
         const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
         my_last = last[p];
-        Tcur = t_pen[p];
-        w0 = d_rgb[3 * p]; w1 = d_rgb[3 * p + 1]; w2 = d_rgb[3 * p + 2];
-        S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
+        if (my_last > 0) {
+            Tcur = t_pen[p];
+            w0 = d_rgb[3 * p]; w1 = d_rgb[3 * p + 1]; w2 = d_rgb[3 * p + 2];
+            S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
+        }
     }
-    if (threadIdx.x == 0) s_tile_end = c.start;
-    __syncthreads();
+    int wmax = my_last;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
+    if (wmax <= 0) return; // no pixel of this block has a contributor
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid], nullptr };
+    uint32_t (*qid)[CH] = s_id[wid];
+    const int len = wmax;
+    const int nchunks = (len + CH - 1) / CH;
+    const uint32_t *list = vals + c.start;
+    // reverse step r handles chunk nchunks - 1 - r; its ring stage is r % NS
+    auto issue = [&](int r, uint32_t id) {
+        const int cj = nchunks - 1 - r;
+        if (cj >= 0 && cj * CH + lane < len) {
+            const int st = r % NS;
+            qid[st][lane] = id;
+            cp_async16(&q.a[st][lane], t.rec0 + id);
+            cp_async16(&q.b[st][lane], t.rec1 + id);
+            cp_async16(&q.c[st][lane], t.rec2 + id);
+        }
+        cp_async_commit();
+    };
+    auto fetch_pos = [&](int r) -> uint32_t {
+        const int cj = nchunks - 1 - r;
+        return (cj >= 0 && cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u;
+    };
+    uint32_t posn, posnn, idn;
     {
-        int m = my_last;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-        if (lane == 0) atomicMax(&s_tile_end, m);
+        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
+        posn = fetch_pos(2);
+        posnn = fetch_pos(3);
+        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
+        issue(0, i0);
+        issue(1, i1);
+        idn = __ldg(list + posn);
     }
-    __syncthreads();
-    const int tile_end = s_tile_end;
-    const int nbatch = (tile_end - c.start + RB - 1) / RB;
-    for (int b = nbatch - 1; b >= 0; --b) {
-        __syncthreads(); // previous batch fully flushed
-        const int first = c.start + b * RB;
-        const int nvalid = min(RB, tile_end - first);
-        uint32_t my_id = 0;
-        stage_batch(t, vals, first, nvalid, s_r0, s_r1, s_r2, &my_id);
+    const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
+    const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
+    for (int r = 0; r < nchunks; ++r) {
+        issue(r + 2, idn);
+        posn = posnn;
+        idn = __ldg(list + posn);
+        posnn = fetch_pos(r + 4);
+        cp_async_wait_group<2>();
+        __syncwarp();
+        const int st = r % NS;
+        const int ci = nchunks - 1 - r;
+        const int first = ci * CH;
+        // lanes whose last contributor lies at or after this chunk's first entry (never empty: first < wmax)
+        const uint32_t live = __ballot_sync(FULL, my_last > first);
+        uint32_t mask = cull_chunk<MODE>(q, st, lane, ci * CH + lane < len, c, live);
+        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        while (mask) {
+            const int e = 31 - __clz(mask);
+            mask &= ~(1u << e);
+            const int pos = first + e;
+            const bool active = pos < my_last;
+            const float4 r0 = q0[e], r1 = q1[e];
+            float v[8], v8 = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) s_grad[i * RB + threadIdx.x] = 0.0f;
-        s_touched[threadIdx.x] = 0;
-        __syncthreads();
-        if (__any_sync(0xffffffffu, my_last > first)) {
-            for (int k = (nvalid - 1) / 32; k >= 0; --k) {
-                const int j = k * 32 + lane;
-                uint32_t mask = __ballot_sync(0xffffffffu, j < nvalid && block_hit<MODE>(s_r0[j], c.bx, c.by));
-                while (mask) {
-                    const int bit = 31 - __clz(mask);
-                    mask &= ~(1u << bit);
-                    const int e = k * 32 + bit;
-                    const int pos = first + e;
-                    const bool active = pos < my_last;
-                    const float4 r0 = s_r0[e], r1 = s_r1[e];
-                    float v[8], v8 = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-                    if (MODE == PS_MODE_3D) {
-                        float dx, dy;
-                        const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
-                        const bool cand = active && sg >= 0.0f && sg <= SIGMA_SKIP;
-                        if (!__any_sync(0xffffffffu, cand)) continue;
-                        const float ex = psm_exp(-sg);
-                        const float oe = psm_mul(r1.w, ex);
-                        const float a = fminf(PS_ALPHA_MAX, oe);
-                        const bool contrib = cand && a >= PS_ALPHA_MIN;
-                        if (!__any_sync(0xffffffffu, contrib)) continue;
-                        if (contrib) {
-                            const float4 r2 = s_r2[e];
-                            const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - a);
-                            Tcur = Tb;
-                            const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-                            const float v_alpha = Tb * (cw - S);
-                            const float vis = a * Tb;
-                            v[0] = vis * w0; v[1] = vis * w1; v[2] = vis * w2;
-                            S = S + a * (cw - S);
-                            if (oe <= PS_ALPHA_MAX) {
-                                const float v_sigma = -oe * v_alpha;
-                                v[3] = 0.5f * v_sigma * dx * dx;
-                                v[4] = v_sigma * dx * dy;
-                                v[5] = 0.5f * v_sigma * dy * dy;
-                                v[6] = v_sigma * (2.0f * r1.x * dx + r1.y * dy);
-                                v[7] = v_sigma * (r1.y * dx + 2.0f * r1.z * dy);
-                                v8 = ex * v_alpha;
-                            }
-                        }
-                    } else {
-                        const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
-                        const bool contrib = active && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
-                                             c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
-                        if (!__any_sync(0xffffffffu, contrib)) continue;
-                        if (contrib) {
-                            float dxr, dyr;
-                            const float4 r2 = s_r2[e];
-                            const float q = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
-                            const float gv = psm_mul(r2.w, psm_exp(-q));
-                            const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - gv);
-                            Tcur = Tb;
-                            const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-                            const float dLdg = Tb * (cw - S);
-                            const float cn = gv * Tb;
-                            v[0] = cn * w0; v[1] = cn * w1; v[2] = cn * w2;
-                            const float Gq = -gv * dLdg;
-                            const float ddxr = 2.0f * dxr * r1.z * Gq, ddyr = 2.0f * dyr * r1.w * Gq;
-                            v[3] = ddxr; v[4] = ddyr;
-                            v[5] = ddxr * dyr - ddyr * dxr;
-                            v[6] = dxr * dxr * Gq;
-                            v[7] = dyr * dyr * Gq;
-                            v8 = Gq;
-                            S = S + gv * (cw - S);
-                        }
+            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            if (MODE == PS_MODE_3D) {
+                float dx, dy;
+                const float4 r2 = q2[e];
+                const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
+                const bool cand = active && sg >= 0.0f && sg <= r0.z + THR_SLACK;
+                if (!__any_sync(FULL, cand)) continue;
+                const float ex = psm_exp2_inrange(psm_mul(-sg, 0x1.715476p+0f));
+                const float oe = psm_mul(r0.w, ex);
+                const float a = fminf(PS_ALPHA_MAX, oe);
+                const bool contrib = cand && a >= PS_ALPHA_MIN;
+                if (!__any_sync(FULL, contrib)) continue;
+                if (contrib) {
+                    const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - a);
+                    Tcur = Tb;
+                    const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+                    const float v_alpha = Tb * (cw - S);
+                    const float vis = a * Tb;
+                    v[0] = vis * w0; v[1] = vis * w1; v[2] = vis * w2;
+                    S = S + a * (cw - S);
+                    if (oe <= PS_ALPHA_MAX) {
+                        const float v_sigma = -oe * v_alpha;
+                        v[3] = 0.5f * v_sigma * dx * dx;
+                        v[4] = v_sigma * dx * dy;
+                        v[5] = 0.5f * v_sigma * dy * dy;
+                        v[6] = v_sigma * (2.0f * r1.x * dx + r1.y * dy);
+                        v[7] = v_sigma * (r1.y * dx + 2.0f * r1.z * dy);
+                        v8 = ex * v_alpha;
                     }
-                    warp_reduce9(v, v8, lane);
-                    if ((lane & 3) == 0) atomicAdd(&s_grad[e * 9 + (lane >> 2)], v[0]);
-                    if (lane == 1) { atomicAdd(&s_grad[e * 9 + 8], v8); s_touched[e] = 1; }
                 }
+            } else {
+                const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
+                const bool contrib = active && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
+                                     c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
+                if (!__any_sync(FULL, contrib)) continue;
+                if (contrib) {
+                    float dxr, dyr;
+                    const float4 r2 = q2[e];
+                    const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
+                    const float gv = psm_mul(r2.w, psm_exp(-qv));
+                    const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - gv);
+                    Tcur = Tb;
+                    const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+                    const float dLdg = Tb * (cw - S);
+                    const float cn = gv * Tb;
+                    v[0] = cn * w0; v[1] = cn * w1; v[2] = cn * w2;
+                    const float Gq = -gv * dLdg;
+                    const float ddxr = 2.0f * dxr * r1.z * Gq, ddyr = 2.0f * dyr * r1.w * Gq;
+                    v[3] = ddxr; v[4] = ddyr;
+                    v[5] = ddxr * dyr - ddyr * dxr;
+                    v[6] = dxr * dxr * Gq;
+                    v[7] = dyr * dyr * Gq;
+                    v8 = Gq;
+                    S = S + gv * (cw - S);
+                }
+            }
+            warp_reduce9(v, v8, lane);
+            float *row = acc + (size_t)qid[st][e] * PS_ACC_STRIDE;
+            if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), v[0]);
+            if (lane == 1) atomicAdd(row + 8, v8);
+        }
+        __syncwarp(); // every lane is finished with stage st before step r + 3 is copied into it
+    }
+    cp_async_wait_group<0>();
+}
+
+// Split every non-empty tile list, in order, into the lists of its eight 8x4 pixel blocks.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
+                   const int32_t *__restrict__ worklist, uint32_t *__restrict__ blist, int32_t *__restrict__ bcount)
+{
+    __shared__ int s_cnt[8][8]; // [warp][block]
+    __shared__ int s_run[8];
+    const int item = blockIdx.x;
+    const int lin = worklist[item];
+    const int view = lin / g.n_tiles, tile = lin - view * g.n_tiles;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int start = offsets[lin], len = offsets[lin + 1] - start;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *out = blist + 8 * (size_t)start;
+    if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
+    __syncthreads();
+    for (int first = 0; first < len; first += 256) {
+        const int j = first + threadIdx.x;
+        uint32_t m8 = 0;
+        if (j < len) {
+            const uint32_t id = __ldg(vals + start + j);
+            const float4 r0 = __ldg(t.rec0 + id);
+            float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == PS_MODE_3D) r1 = __ldg(t.rec1 + id);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int bx = tx * PS_TILE + (k & 1) * 8, by = ty * PS_TILE + (k >> 1) * 4;
+                bool hit;
+                if (MODE == PS_MODE_3D)
+                    hit = ellipse_hits_box(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z, (float)bx + 0.5f, (float)bx + 7.5f,
+                                           (float)by + 0.5f, (float)by + 3.5f);
+                else
+                    hit = rect_hits_box(r0.z, r0.w, bx, bx + 7, by, by + 3);
+                if (hit && bx < g.W && by < g.H) m8 |= 1u << k;
+            }
+        }
+        uint32_t bal[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bal[k] = __ballot_sync(FULL, (m8 >> k) & 1u);
+            if (lane == 0) s_cnt[wid][k] = __popc(bal[k]);
+        }
+        __syncthreads();
+        int tot = 0; // all reads of s_cnt happen between the two barriers: the next round may overwrite it at once
+        if (threadIdx.x < 8) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_cnt[w][threadIdx.x];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((m8 >> k) & 1u) {
+                int pre = s_run[k];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) pre += (w < wid) ? s_cnt[w][k] : 0;
+                out[(size_t)k * len + pre + __popc(bal[k] & ((1u << lane) - 1u))] = (uint32_t)j;
             }
         }
         __syncthreads();
-        if ((int)threadIdx.x < nvalid && s_touched[threadIdx.x]) {
-            float *dst = acc + (size_t)my_id * PS_ACC_STRIDE;
-            const float *sg = s_grad + threadIdx.x * 9; // [entry][9]: conflict-free for the atomics and for this read
-            red_add_v4(dst, sg[0], sg[1], sg[2], sg[3]);
-            red_add_v4(dst + 4, sg[4], sg[5], sg[6], sg[7]);
-            atomicAdd(dst + 8, sg[8]);
-        }
+        if (threadIdx.x < 8) s_run[threadIdx.x] += tot;
     }
+    __syncthreads();
+    if (threadIdx.x < 8) bcount[item * 8 + threadIdx.x] = s_run[threadIdx.x];
 }
 
 } // namespace
 
+int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
+{
+    if (n_work <= 0) return 0;
+    if (g.mode == PS_MODE_3D) block_lists_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bcount);
+    else block_lists_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bcount);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
-                         float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, float *t_pen,
+                         float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, int32_t *blast, float *t_pen,
                          unsigned long long *stats, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const unsigned grid = (unsigned)n_work;
-#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, FWD_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, t_pen, stats)
+    const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
+#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, stats)
     if (g.mode == PS_MODE_3D) { if (stats) PS_FWD(PS_MODE_3D, true); else PS_FWD(PS_MODE_3D, false); }
     else { if (stats) PS_FWD(PS_MODE_2D, true); else PS_FWD(PS_MODE_2D, false); }
 #undef PS_FWD
@@ -608,11 +611,11 @@ int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l
                          cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const unsigned grid = (unsigned)n_work;
+    const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
     if (g.mode == PS_MODE_3D)
-        raster_bwd_kernel<PS_MODE_3D><<<grid, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, acc);
+        raster_bwd_kernel<PS_MODE_3D><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc);
     else
-        raster_bwd_kernel<PS_MODE_2D><<<grid, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, acc);
+        raster_bwd_kernel<PS_MODE_2D><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -56,9 +56,9 @@ def hc_project(mode, params, W, H, V=None, K=None, near=0.01, far=1e10, clip=0.0
 def records_from_oracle(mode, tab, table=False):
     """Oracle table -> the product's [N,12] record layout (rec0|rec1|rec2) for bit-exact comparison.
 
-    table=False: the contract-level PsRecord (A, B, C | depth).  table=True: the layout the projection kernel
-    stores in HBM for the 3D rasterizer: exact halvings A/2, C/2 and thr = log(255 * opacity) in place of depth
-    (depth bits live in their own array, tap "depth")."""
+    table=False: the contract-level PsRecord (x, y, rx, ry | A, B, C, o | r, g, b, depth).  table=True: the layout
+    the projection kernel stores in HBM for the 3D rasterizer: (x, y, thr, o | A/2, B, C/2, 0 | r, g, b, 0) with exact
+    halvings and thr = log(255 * opacity); radii are covered by the tile-rectangle taps, depth bits by tap "depth"."""
     g, rgb, rect = tab["geom"], tab["rgb"], tab["rect"]
     N = g.shape[0]
     r = np.zeros((N, 12), np.float32)
@@ -71,10 +71,13 @@ def records_from_oracle(mode, tab, table=False):
         r[:, 11] = g[:, 6]
         if table:
             from oracle import oracle as ora
+            thr = ora.math_probe((g[:, 5] * np.float32(255.0)).astype(np.float32))["log"]
+            r[:, 2] = np.where(g[:, 6] != 0, thr, np.float32(0.0))  # set only for Gaussians that survive every cull
+            r[:, 3] = g[:, 5]
             r[:, 4] = np.float32(0.5) * g[:, 2]
             r[:, 6] = np.float32(0.5) * g[:, 4]
-            thr = ora.math_probe((g[:, 5] * np.float32(255.0)).astype(np.float32))["log"]
-            r[:, 11] = np.where(g[:, 6] != 0, thr, np.float32(0.0))  # set only for Gaussians that survive every cull
+            r[:, 7] = 0.0
+            r[:, 11] = 0.0
     else:
         r[:, 0:2] = g[:, 0:2]
         lo = (rect[:, 0].astype(np.uint32) | (rect[:, 1].astype(np.uint32) << 16))

@@ -193,3 +193,46 @@ def test_autograd_function_matches_raw_backward():
                        w_rgb, w_a)
     rel = column_rel_err(p.grad.cpu().numpy(), got["d_params"])
     assert rel.max() < 1e-4  # same kernels; only atomic ordering differs
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json full sizes
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wl,cams", [("c2", 2), ("c3", 1), ("c1", 2)])
+def test_full_size_workload_against_oracle(wl, cams):
+    """Full N and full resolution of the benchmark configs (c2: 3D 288x256 N=16000; c3: 2D 576x512 N=16000;
+    c1: 2D 192x171 N=4096): every bit-exact stage and the tolerances, against the oracle."""
+    _, _, _, synth = _mods()
+    d = synth.make_views(wl, n_frames=1, n_cams=cams, seed=21)
+    _compare(d["mode"], d["params"], d["view_frame"], d["width"], d["height"], (1.0, 1.0, 1.0), d["viewmats"], d["Ks"])
+
+
+def test_batch_invariance_full_size_c2():
+    """Size-independent property: a view rendered inside a 24-view batch (4 frames x 6 cameras, N=16000) is
+    bit-identical to the same view rendered alone, and its gradient contribution adds up linearly."""
+    _, _capi, batched, synth = _mods()
+    d = synth.make_views("c2", n_frames=4, n_cams=6, seed=5)
+    W, H = d["width"], d["height"]
+    V = len(d["view_frame"])
+    p, vf = d["params"].to(DEV), d["view_frame"].to(DEV)
+    vm, Ks = d["viewmats"].to(DEV), d["Ks"].to(DEV)
+    bg = torch.ones(3, device=DEV)
+    w_rgb, w_a = synth.cotangents(V, H, W, seed=8)
+    w_rgb, w_a = w_rgb.to(DEV), w_a.to(DEV)
+    rgb, alpha, counts, saved = batched.forward_raw("3d", p, vf, vm, Ks, bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD, True)
+    g_all = batched.backward_raw(saved, p, vf, vm, Ks, bg, w_rgb, w_a)
+    g_sum = torch.zeros_like(g_all)
+    for v in (0, 7, 13, 23):
+        f = int(vf[v])
+        r1, a1, c1, s1 = batched.forward_raw("3d", p[f:f + 1], torch.zeros(1, dtype=torch.int32, device=DEV), vm[v:v + 1],
+                                             Ks[v:v + 1], bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD, True)
+        assert torch.equal(r1[0], rgb[v]) and torch.equal(a1[0], alpha[v]) and torch.equal(c1[0], counts[v])
+    # gradients: the batch equals the sum over single views (atomic ordering differs -> tolerance)
+    for v in range(V):
+        f = int(vf[v])
+        _, _, _, s1 = batched.forward_raw("3d", p[f:f + 1], torch.zeros(1, dtype=torch.int32, device=DEV), vm[v:v + 1],
+                                          Ks[v:v + 1], bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD)
+        g_sum[f] += batched.backward_raw(s1, p[f:f + 1], torch.zeros(1, dtype=torch.int32, device=DEV), vm[v:v + 1],
+                                         Ks[v:v + 1], bg, w_rgb[v:v + 1].contiguous(), w_a[v:v + 1].contiguous())[0]
+    rel = column_rel_err(g_all.cpu().numpy(), g_sum.cpu().numpy())
+    assert rel.max() < 1e-4, rel
