@@ -422,9 +422,9 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
             const int pos = first + e;
             const bool active = pos < my_last;
             const float4 r0 = q0[e], r1 = q1[e];
-            float v[8], v8 = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            // gradient terms are computed by every lane and gated with selects (no divergent branches);
+            // lanes that do not contribute carry zeros into the warp reduction
+            float v[8], v8;
             if (MODE == PS_MODE_3D) {
                 float dx, dy;
                 const float4 r2 = q2[e];
@@ -436,49 +436,44 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                 const float a = fminf(PS_ALPHA_MAX, oe);
                 const bool contrib = cand && a >= PS_ALPHA_MIN;
                 if (!__any_sync(FULL, contrib)) continue;
-                if (contrib) {
-                    const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - a);
-                    Tcur = Tb;
-                    const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-                    const float v_alpha = Tb * (cw - S);
-                    const float vis = a * Tb;
-                    v[0] = vis * w0; v[1] = vis * w1; v[2] = vis * w2;
-                    S = S + a * (cw - S);
-                    if (oe <= PS_ALPHA_MAX) {
-                        const float v_sigma = -oe * v_alpha;
-                        v[3] = 0.5f * v_sigma * dx * dx;
-                        v[4] = v_sigma * dx * dy;
-                        v[5] = 0.5f * v_sigma * dy * dy;
-                        v[6] = v_sigma * (2.0f * r1.x * dx + r1.y * dy);
-                        v[7] = v_sigma * (r1.y * dx + 2.0f * r1.z * dy);
-                        v8 = ex * v_alpha;
-                    }
-                }
+                const float Tb = (pos == my_last - 1) ? Tcur : __fdividef(Tcur, 1.0f - a);
+                const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+                const float v_alpha = Tb * (cw - S);
+                const float vis = contrib ? a * Tb : 0.0f;
+                const float v_sigma = (contrib && oe <= PS_ALPHA_MAX) ? -oe * v_alpha : 0.0f;
+                Tcur = contrib ? Tb : Tcur;
+                S = contrib ? S + a * (cw - S) : S;
+                v[0] = vis * w0; v[1] = vis * w1; v[2] = vis * w2;
+                const float sx = v_sigma * dx, sy = v_sigma * dy;
+                v[3] = 0.5f * sx * dx;
+                v[4] = sx * dy;
+                v[5] = 0.5f * sy * dy;
+                v[6] = 2.0f * r1.x * sx + r1.y * sy;
+                v[7] = r1.y * sx + 2.0f * r1.z * sy;
+                v8 = (contrib && oe <= PS_ALPHA_MAX) ? ex * v_alpha : 0.0f;
             } else {
                 const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
                 const bool contrib = active && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
                                      c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
                 if (!__any_sync(FULL, contrib)) continue;
-                if (contrib) {
-                    float dxr, dyr;
-                    const float4 r2 = q2[e];
-                    const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
-                    const float gv = psm_mul(r2.w, psm_exp(-qv));
-                    const float Tb = (pos == my_last - 1) ? Tcur : Tcur * __frcp_rn(1.0f - gv);
-                    Tcur = Tb;
-                    const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-                    const float dLdg = Tb * (cw - S);
-                    const float cn = gv * Tb;
-                    v[0] = cn * w0; v[1] = cn * w1; v[2] = cn * w2;
-                    const float Gq = -gv * dLdg;
-                    const float ddxr = 2.0f * dxr * r1.z * Gq, ddyr = 2.0f * dyr * r1.w * Gq;
-                    v[3] = ddxr; v[4] = ddyr;
-                    v[5] = ddxr * dyr - ddyr * dxr;
-                    v[6] = dxr * dxr * Gq;
-                    v[7] = dyr * dyr * Gq;
-                    v8 = Gq;
-                    S = S + gv * (cw - S);
-                }
+                float dxr, dyr;
+                const float4 r2 = q2[e];
+                const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
+                const float gv = psm_mul(r2.w, psm_exp(-qv));
+                const float Tb = (pos == my_last - 1) ? Tcur : __fdividef(Tcur, 1.0f - gv);
+                const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+                const float dLdg = Tb * (cw - S);
+                const float cn = contrib ? gv * Tb : 0.0f;
+                const float Gq = contrib ? -gv * dLdg : 0.0f;
+                Tcur = contrib ? Tb : Tcur;
+                S = contrib ? S + gv * (cw - S) : S;
+                v[0] = cn * w0; v[1] = cn * w1; v[2] = cn * w2;
+                const float ddxr = 2.0f * dxr * r1.z * Gq, ddyr = 2.0f * dyr * r1.w * Gq;
+                v[3] = ddxr; v[4] = ddyr;
+                v[5] = ddxr * dyr - ddyr * dxr;
+                v[6] = dxr * dxr * Gq;
+                v[7] = dyr * dyr * Gq;
+                v8 = Gq;
             }
             warp_reduce9(v, v8, lane);
             float *row = acc + (size_t)qid[st][e] * PS_ACC_STRIDE;
