@@ -4,7 +4,8 @@
 // without ever sorting 12-byte (key, value) pairs over M = sum(tiles touched):
 //
 //   depth_rank   (3D) one CTA per view: stable LSD radix sort of the view's N depth words in shared
-//                memory (skipping the digits above the highest differing bit) -> order[], rank[]
+//                memory (skipping the digits above the highest differing bit; every warp owns a contiguous
+//                segment, so a pass needs three CTA barriers) -> order[], rank[]
 //   scan_lists   exclusive scan of the per-(view,tile) counts the projection kernel histogrammed
 //                -> tile ranges (offsets), M, list size classes            [this IS isect_offsets]
 //   partition    every Gaussian drops its depth rank (3D) / row index (2D) into the lists of the
@@ -63,8 +64,8 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
                   uint32_t *__restrict__ order, uint32_t *__restrict__ rank, uint32_t *gscratch)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ uint32_t s_hist[256], s_tot[256], s_tmp[8], s_minmax[2];
-    __shared__ uint16_t s_wcnt[RW][256];
+    __shared__ uint32_t s_hist[256], s_tmp[8], s_minmax[2];
+    __shared__ IdT s_wcnt[RW][256]; // per-(warp, digit) counts, then output cursors (< N: fits IdT)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t base = (size_t)blockIdx.x * N;
     uint32_t *k[2];
@@ -98,55 +99,73 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
     // digits above the highest bit in which two listed depth words differ cannot change the order
     const uint32_t diff = (mx >= mn) ? (mn ^ mx) : 0u;
     const int npass = diff ? (32 - __clz(diff) + 7) / 8 : 0;
+    // Every warp owns one contiguous segment of the array for the whole pass, so the per-(warp, digit)
+    // counts are taken once per pass and one scan in (digit, warp) order gives each warp its private
+    // output cursor for every digit: three CTA barriers per pass, and ties keep their input order.
+    const int seg = ((N + RW - 1) / RW + 31) & ~31;
+    const int seg_lo = min(N, wid * seg), seg_hi = min(N, seg_lo + seg);
     for (int p = 0; p < npass; ++p) {
         const int shift = 8 * p;
         const uint32_t *kin = k[p & 1];
         const IdT *iin = id[p & 1];
         uint32_t *kout = k[(p + 1) & 1];
         IdT *iout = id[(p + 1) & 1];
-        if (tid < 256) s_hist[tid] = 0;
-        __syncthreads();
-        for (int i = tid; i < N; i += RT) atomicAdd(&s_hist[(kin[i] >> shift) & 255u], 1u);
-        __syncthreads();
-        scan256_exclusive(s_hist, s_tmp);
-        for (int c0 = 0; c0 < N; c0 += RT) {
-            const int i = c0 + tid;
-            const bool live = i < N;
-            uint32_t key = 0, digit = 0, r = 0;
-            IdT idv = 0;
-            // clear this warp's row of the per-warp digit counts (512 B = 4 words per lane)
-            uint32_t *row = reinterpret_cast<uint32_t *>(&s_wcnt[wid][0]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) row[lane + 32 * q] = 0u;
-            __syncwarp();
+        for (int q = 0; q < 8; ++q) s_wcnt[wid][lane + 32 * q] = (IdT)0;
+        __syncwarp();
+        for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
+            const int i = i0 + lane;
+            const bool live = i < seg_hi;
             const uint32_t live_mask = __ballot_sync(FULL, live);
             if (live) {
-                key = kin[i];
-                idv = iin[i];
-                digit = (key >> shift) & 255u;
+                const uint32_t digit = (kin[i] >> shift) & 255u;
                 const uint32_t peers = __match_any_sync(live_mask, digit);
-                r = __popc(peers & ((1u << lane) - 1u));
-                if (r == 0) s_wcnt[wid][digit] = (uint16_t)__popc(peers);
+                if ((peers & ((1u << lane) - 1u)) == 0) s_wcnt[wid][digit] += (IdT)__popc(peers);
             }
-            __syncthreads();
-            if (tid < 256) { // exclusive prefix of this digit's counts over the 32 warps (stable: warp order)
-                uint32_t run = 0;
-#pragma unroll 8
-                for (int w = 0; w < RW; ++w) {
-                    const uint32_t c = s_wcnt[w][tid];
-                    s_wcnt[w][tid] = (uint16_t)run;
-                    run += c;
-                }
-                s_tot[tid] = run;
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan of the 256 x 32 counts in (digit, warp) order: four threads per digit, eight warps
+            // each; digit totals are scanned across the CTA
+            const int d = tid >> 2, part = tid & 3;
+            uint32_t loc[8], run = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t cc = s_wcnt[part * 8 + i][d];
+                loc[i] = run;
+                run += cc;
             }
+            uint32_t incl = run;
+            uint32_t n = __shfl_up_sync(FULL, incl, 1, 4);
+            if (part >= 1) incl += n;
+            n = __shfl_up_sync(FULL, incl, 2, 4);
+            if (part >= 2) incl += n;
+            const uint32_t off = incl - run;
+            if (part == 3) s_hist[d] = incl; // digit total
             __syncthreads();
+            scan256_exclusive(s_hist, s_tmp);
+            const uint32_t dbase = s_hist[d];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_wcnt[part * 8 + i][d] = (IdT)(dbase + loc[i] + off);
+        }
+        __syncthreads();
+        for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
+            const int i = i0 + lane;
+            const bool live = i < seg_hi;
+            const uint32_t live_mask = __ballot_sync(FULL, live);
             if (live) {
-                const uint32_t pos = s_hist[digit] + s_wcnt[wid][digit] + r;
+                const uint32_t key = kin[i];
+                const IdT idv = iin[i];
+                const uint32_t digit = (key >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(live_mask, digit);
+                const uint32_t r = __popc(peers & ((1u << lane) - 1u));
+                const uint32_t pos = (uint32_t)s_wcnt[wid][digit] + r;
                 kout[pos] = key;
                 iout[pos] = idv;
+                __syncwarp(live_mask);
+                if (r == 0) s_wcnt[wid][digit] += (IdT)__popc(peers);
             }
-            __syncthreads();
-            if (tid < 256) s_hist[tid] += s_tot[tid];
+            __syncwarp();
         }
         __syncthreads();
     }
@@ -158,54 +177,119 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
     }
 }
 
-// one CTA: exclusive scan of T counts in place, size-class histogram of the non-empty lists
-__global__ void __launch_bounds__(1024)
-scan_lists_kernel(int32_t *__restrict__ offsets, int T, int32_t *__restrict__ cls, int64_t *__restrict__ mailbox)
+// Exclusive scan of the T list lengths in place + size-class histogram of the non-empty lists, three launches:
+//   scan_reduce : one CTA per 4096 lengths -> chunk total, non-empty count, class histogram (global atomics)
+//   scan_spine  : one CTA scans the chunk totals; class bases (longest class first); mailbox = {M, non-empty}
+//   scan_apply  : one CTA per chunk rescans it with its base and writes the offsets
+constexpr int SCAN_CHUNK = 4096;
+
+__device__ __forceinline__ long long block_exclusive_scan_1024(long long v, long long *s_warp, long long *total)
 {
-    __shared__ long long s_part[1024];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long n = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const long long w = s_warp[lane];
+        long long wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long n = __shfl_up_sync(FULL, wi, d);
+            if (lane >= d) wi += n;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    if (total) *total = s_warp[32];
+    return s_warp[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_reduce_kernel(const int32_t *__restrict__ counts, int T, long long *__restrict__ chunk_sum, int32_t *__restrict__ cls_count,
+                   int32_t *__restrict__ nz_total)
+{
+    __shared__ long long s_warp[33];
     __shared__ int s_cls[PS_N_CLASSES];
     __shared__ int s_nz;
     const int tid = threadIdx.x;
     if (tid < PS_N_CLASSES) s_cls[tid] = 0;
     if (tid == 0) s_nz = 0;
     __syncthreads();
-    const int per = (T + 1023) / 1024;
-    const int lo = min(T, tid * per), hi = min(T, lo + per);
+    const int base = blockIdx.x * SCAN_CHUNK;
     long long acc = 0;
     int nz = 0;
-    for (int i = lo; i < hi; ++i) {
-        const int c = offsets[i];
+#pragma unroll
+    for (int k = 0; k < SCAN_CHUNK / 1024; ++k) {
+        const int i = base + k * 1024 + tid;
+        const int c = i < T ? counts[i] : 0;
         acc += c;
         if (c > 0) { ++nz; atomicAdd(&s_cls[31 - __clz(c)], 1); }
     }
-    s_part[tid] = acc;
     if (nz) atomicAdd(&s_nz, nz);
+    long long total;
+    block_exclusive_scan_1024(acc, s_warp, &total);
+    if (tid == 0) { chunk_sum[blockIdx.x] = total; if (s_nz) atomicAdd(nz_total, s_nz); }
+    if (tid < PS_N_CLASSES && s_cls[tid]) atomicAdd(&cls_count[tid], s_cls[tid]);
+}
+
+// cls layout: [0, 32) class bases, [32, 64) fill counters (zeroed here), [64, 96) class counts, [96] non-empty total
+__global__ void __launch_bounds__(1024)
+scan_spine_kernel(long long *__restrict__ chunk_sum, int n_chunks, int32_t *__restrict__ cls, int32_t *__restrict__ offsets, int T,
+                  int64_t *__restrict__ mailbox)
+{
+    __shared__ long long s_warp[33];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const long long add = tid >= d ? s_part[tid - d] : 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += 1024) {
+        const int i = c0 + tid;
+        const long long v = i < n_chunks ? chunk_sum[i] : 0;
+        long long total;
+        const long long ex = block_exclusive_scan_1024(v, s_warp, &total);
+        if (i < n_chunks) chunk_sum[i] = s_carry + ex;
         __syncthreads();
-        s_part[tid] += add;
+        if (tid == 0) s_carry += total;
         __syncthreads();
     }
-    long long run = s_part[tid] - acc;
-    for (int i = lo; i < hi; ++i) {
-        const int c = offsets[i];
-        offsets[i] = (int32_t)run;
-        run += c;
-    }
-    if (tid == 1023) {
-        const long long total = s_part[1023];
+    if (tid == 0) {
+        const long long total = s_carry;
         offsets[T] = (int32_t)(total > 0x7fffffffLL ? 0x7fffffffLL : total);
         mailbox[0] = total;
-        mailbox[1] = s_nz;
-    }
-    if (tid == 0) { // class bases, longest class first; fill counters zeroed
+        mailbox[1] = cls[3 * PS_N_CLASSES];
         int r = 0;
         for (int c = PS_N_CLASSES - 1; c >= 0; --c) {
             cls[c] = r;
-            r += s_cls[c];
+            r += cls[2 * PS_N_CLASSES + c];
             cls[PS_N_CLASSES + c] = 0;
         }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_apply_kernel(int32_t *__restrict__ offsets, int T, const long long *__restrict__ chunk_base)
+{
+    __shared__ long long s_warp[33];
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * SCAN_CHUNK + tid * (SCAN_CHUNK / 1024);
+    int c[SCAN_CHUNK / 1024];
+    long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_CHUNK / 1024; ++k) {
+        c[k] = base + k < T ? offsets[base + k] : 0;
+        acc += c[k];
+    }
+    long long run = chunk_base[blockIdx.x] + block_exclusive_scan_1024(acc, s_warp, nullptr);
+#pragma unroll
+    for (int k = 0; k < SCAN_CHUNK / 1024; ++k) {
+        if (base + k < T) offsets[base + k] = (int32_t)run;
+        run += c[k];
     }
 }
 
@@ -373,10 +457,17 @@ int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratc
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, int64_t *mailbox, cudaStream_t s)
+size_t ps_scan_scratch_elems(const PsGeometry &g) { return (size_t)(g.V * g.n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
+
+int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, long long *chunk_scratch, int64_t *mailbox, cudaStream_t s)
 {
-    scan_lists_kernel<<<1, 1024, 0, s>>>(l.offsets, g.V * g.n_tiles, l.cls, mailbox);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    const int T = g.V * g.n_tiles;
+    const int n_chunks = (T + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (cudaMemsetAsync(l.cls, 0, sizeof(int32_t) * PS_CLS_WORDS, s) != cudaSuccess) return -1;
+    if (n_chunks > 0) scan_reduce_kernel<<<n_chunks, 1024, 0, s>>>(l.offsets, T, chunk_scratch, l.cls + 2 * PS_N_CLASSES, l.cls + 3 * PS_N_CLASSES);
+    scan_spine_kernel<<<1, 1024, 0, s>>>(chunk_scratch, n_chunks, l.cls, l.offsets, T, mailbox);
+    if (n_chunks > 0) scan_apply_kernel<<<n_chunks, 1024, 0, s>>>(l.offsets, T, chunk_scratch);
+    return cudaGetLastError() == cudaSuccess ? (n_chunks > 0 ? 3 : 1) : -1;
 }
 
 int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s)

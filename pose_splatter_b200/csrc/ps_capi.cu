@@ -160,7 +160,7 @@ int64_t ps_ctx_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 static void saved_free(ps_saved *sv, cudaStream_t s)
 {
-    dev_free(sv->t.rec0, s); dev_free(sv->t.rec1, s); dev_free(sv->t.rec2, s);
+    dev_free(sv->t.rec, s);
     dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
     dev_free(sv->t.depth, s);
     dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
@@ -203,6 +203,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
 
     int rc = 0;
     uint32_t *rank_scratch = nullptr;
+    long long *scan_scratch = nullptr;
     // everything below jumps to `out` on error so scratch is always returned to the pool
 #define PS_TRY_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); goto out; } } while (0)
 #define PS_TRY_LAUNCH(call) do { int n_ = (call); if (n_ < 0) { rc = fail(3, "kernel launch failed in %s: %s", #call, cudaGetErrorString(cudaGetLastError())); goto out; } ctx->launches += n_; } while (0)
@@ -215,12 +216,11 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
         sv->M = 0;
         sv->n_work = 0;
         PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1, s));
-        PS_TRY_CUDA(dev_alloc(&sv->l.cls, (size_t)2 * PS_N_CLASSES, s));
+        PS_TRY_CUDA(dev_alloc(&sv->l.cls, (size_t)PS_CLS_WORDS, s));
+        PS_TRY_CUDA(dev_alloc(&scan_scratch, ps_scan_scratch_elems(g), s));
         PS_TRY_CUDA(cudaMemsetAsync(sv->l.offsets, 0, (T + 1) * sizeof(int32_t), s));
         if (VN > 0) {
-            PS_TRY_CUDA(dev_alloc(&sv->t.rec0, VN, s));
-            PS_TRY_CUDA(dev_alloc(&sv->t.rec1, VN, s));
-            PS_TRY_CUDA(dev_alloc(&sv->t.rec2, VN, s));
+            PS_TRY_CUDA(dev_alloc(&sv->t.rec, 4 * VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
             if (g.mode == PS_MODE_3D) PS_TRY_CUDA(dev_alloc(&sv->t.depth, VN, s));
@@ -233,7 +233,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
                 StageTimer tm(ctx, PS_STAGE_RANK, s);
                 PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, s));
             }
-            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, ctx->d_total, s)); }
+            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, ctx->d_total, s)); }
             PS_TRY_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the lists
             sv->M = ctx->h_total[0];
@@ -273,6 +273,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
     }
 out:
     dev_free(rank_scratch, s);
+    dev_free(scan_scratch, s);
     dev_free(sv->l.fill, s); dev_free(sv->l.slots, s); dev_free(sv->l.cls, s);
     dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
     if (rc == 0 && !keep) { dev_free(sv->t.tile_rect, s); dev_free(sv->t.depth, s); }
@@ -347,9 +348,17 @@ int ps_saved_copy(ps_ctx *ctx, const ps_saved *sv, int what, void *dst, size_t b
         case PS_TAP_TILE_OFFSETS: src = sv->l.offsets; have = sizeof(int32_t) * ((size_t)g.V * g.n_tiles + 1); break;
         case PS_TAP_LAST_IDS: src = sv->last; have = sizeof(int32_t) * npix; break;
         case PS_TAP_TILES_TOUCHED: src = sv->t.tiles_touched; have = sizeof(int32_t) * VN; break;
-        case PS_TAP_REC0: src = sv->t.rec0; have = sizeof(float4) * VN; break;
-        case PS_TAP_REC1: src = sv->t.rec1; have = sizeof(float4) * VN; break;
-        case PS_TAP_REC2: src = sv->t.rec2; have = sizeof(float4) * VN; break;
+        case PS_TAP_REC0: case PS_TAP_REC1: case PS_TAP_REC2: { // one 16-byte word out of every 64-byte record
+            if (VN == 0) return 0;
+            if (!sv->t.rec) return fail(1, "ps_saved_copy: records were not kept");
+            if (bytes < sizeof(float4) * VN) return fail(1, "ps_saved_copy: destination holds %zu bytes, tap %d needs %zu", bytes, what, sizeof(float4) * VN);
+            cudaStream_t s2 = (cudaStream_t)stream;
+            PS_CUDA(cudaSetDevice(ctx->device));
+            PS_CUDA(cudaMemcpy2DAsync(dst, sizeof(float4), sv->t.rec + (what - PS_TAP_REC0), 4 * sizeof(float4), sizeof(float4), VN,
+                                      cudaMemcpyDefault, s2));
+            PS_CUDA(cudaStreamSynchronize(s2));
+            return 0;
+        }
         case PS_TAP_DEPTH: src = sv->t.depth; have = sv->g.mode == PS_MODE_3D ? sizeof(uint32_t) * VN : 0; break;
         default: return fail(1, "ps_saved_copy: unknown tap %d", what);
     }

@@ -12,6 +12,7 @@
 #define PS_HIST_SMEM_TILES 8192  // per-view tile histograms live in shared memory up to this many tiles
 #define PS_RANK_THREADS 1024     // one CTA per view in the depth-ranking kernel
 #define PS_N_CLASSES 32          // tile-list size classes (floor(log2(len))) of the work list
+#define PS_CLS_WORDS (3 * PS_N_CLASSES + 1)  // class bases | fill counters | class counts | non-empty total
 
 struct PsGeometry {
     int mode, W, H, F, N, V;
@@ -22,7 +23,7 @@ struct PsGeometry {
 
 // per-(view,Gaussian) table produced by the projection stage
 struct PsTable {
-    float4 *rec0, *rec1, *rec2; // [V*N]
+    float4 *rec;                // [V*N][4] splat records, 64 B each (one DRAM burst per gather): rec0 | rec1 | rec2 | spare
     uint2 *tile_rect;           // [V*N] packed tx0|ty0<<16, tx1|ty1<<16
     int32_t *tiles_touched;     // [V*N]
     uint32_t *depth;            // [V*N] 3D: bits of the camera-space depth (low word of the sort key); 2D: unused
@@ -30,12 +31,14 @@ struct PsTable {
     uint32_t *rank;             // [V*N] 3D: inverse of order                                     (2D: unused)
 };
 
+#define PS_REC(t, idx, k) ((t).rec + 4 * (size_t)(idx) + (k))
+
 // per-(view,tile) lists
 struct PsLists {
     int32_t *offsets;   // [T+1], T = V*n_tiles: counts after projection, exclusive offsets after the scan
     int32_t *fill;      // [T] running fill of every list during the partition pass
     int32_t *worklist;  // [T] non-empty (view,tile) ids, longest size class first
-    int32_t *cls;       // [2*PS_N_CLASSES] size-class base / fill counters of the work list
+    int32_t *cls;       // [PS_CLS_WORDS] size-class bases / fill counters / counts of the work list
     uint32_t *slots;    // [M] depth ranks (3D) / row indices (2D) in list order, unsorted inside a list
     uint32_t *vals;     // [M] view*N + Gaussian, sorted (tile, depth | row)
     uint32_t *blist;    // [8*M] per-block lists: tile with range [s, s+len) owns [8s, 8s+8len), block k at +k*len;
@@ -53,7 +56,8 @@ int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_
 size_t ps_rank_scratch_elems(const PsGeometry &g); // uint32 elements of global scratch the ranking needs (0 if it fits smem)
 int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, cudaStream_t s);
 // exclusive scan of the T counts in place (offsets[T] = M), size classes; mailbox[0] = M, mailbox[1] = non-empty lists
-int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, int64_t *mailbox, cudaStream_t s);
+size_t ps_scan_scratch_elems(const PsGeometry &g); // int64 elements of scratch the scan needs
+int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, long long *chunk_scratch, int64_t *mailbox, cudaStream_t s);
 int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s);
 int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t s);
 int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);

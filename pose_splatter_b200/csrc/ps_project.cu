@@ -57,14 +57,18 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
         }
         const size_t idx = (size_t)v * g.N + g0 + threadIdx.x;
         if (MODE == PS_MODE_3D) {
-            t.rec0[idx] = make_float4(rec.r0[0], rec.r0[1], rec.thr, rec.r1[3]);
-            t.rec1[idx] = make_float4(psm_mul(0.5f, rec.r1[0]), rec.r1[1], psm_mul(0.5f, rec.r1[2]), 0.0f);
-            t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], 0.0f);
+            float4 *dst = PS_REC(t, idx, 0);
+            dst[0] = make_float4(rec.r0[0], rec.r0[1], rec.thr, rec.r1[3]);
+            dst[1] = make_float4(psm_mul(0.5f, rec.r1[0]), rec.r1[1], psm_mul(0.5f, rec.r1[2]), 0.0f);
+            dst[2] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], 0.0f);
+            dst[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             t.depth[idx] = rec.low;
         } else {
-            t.rec0[idx] = make_float4(rec.r0[0], rec.r0[1], rec.r0[2], rec.r0[3]);
-            t.rec1[idx] = make_float4(rec.r1[0], rec.r1[1], rec.r1[2], rec.r1[3]);
-            t.rec2[idx] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
+            float4 *dst = PS_REC(t, idx, 0);
+            dst[0] = make_float4(rec.r0[0], rec.r0[1], rec.r0[2], rec.r0[3]);
+            dst[1] = make_float4(rec.r1[0], rec.r1[1], rec.r1[2], rec.r1[3]);
+            dst[2] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
+            dst[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         t.tile_rect[idx] = make_uint2((uint32_t)rec.tile[0] | ((uint32_t)rec.tile[1] << 16),
                                       (uint32_t)rec.tile[2] | ((uint32_t)rec.tile[3] << 16));
@@ -105,6 +109,12 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
     const float4 *a4 = reinterpret_cast<const float4 *>(acc + idx * PS_ACC_STRIDE);
     const float4 q0 = a4[0], q1 = a4[1], q2 = a4[2];
     const float a[9] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x };
+    {   // listed but never a contributor (hidden behind saturated pixels): every gradient is exactly zero
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) any = any || (a[k] != 0.0f);
+        if (!any) return;
+    }
     const int frame = view_frame[v];
     const float *row = params + ((size_t)frame * g.N + gi) * P;
     float *d = d_params + ((size_t)frame * g.N + gi) * P;
@@ -116,9 +126,9 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
     for (int k = 0; k < P; ++k) out[k] = 0.0f;
 
     if (MODE == PS_MODE_2D) {
-        const float4 r1 = t.rec1[idx];
+        const float4 r1 = *PS_REC(t, idx, 1);
         const float cs = r1.x, sn = r1.y, iax = r1.z, iay = r1.w;
-        const float o = t.rec2[idx].w;
+        const float o = PS_REC(t, idx, 2)->w;
         const float sx = psm_exp(r[2]), sy = psm_exp(r[3]);
         out[0] = -(cs * a[3] - sn * a[4]);
         out[1] = -(sn * a[3] + cs * a[4]);

@@ -169,9 +169,10 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         if (cj * CH + lane < len) {
             const int st = cj % NS;
             q.pos[st][lane] = pos;
-            cp_async16(&q.a[st][lane], t.rec0 + id);
-            cp_async16(&q.b[st][lane], t.rec1 + id);
-            cp_async16(&q.c[st][lane], t.rec2 + id);
+            const float4 *src = PS_REC(t, id, 0);
+            cp_async16(&q.a[st][lane], src);
+            cp_async16(&q.b[st][lane], src + 1);
+            cp_async16(&q.c[st][lane], src + 2);
         }
         cp_async_commit();
     };
@@ -380,9 +381,10 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         if (cj >= 0 && cj * CH + lane < len) {
             const int st = r % NS;
             qid[st][lane] = id;
-            cp_async16(&q.a[st][lane], t.rec0 + id);
-            cp_async16(&q.b[st][lane], t.rec1 + id);
-            cp_async16(&q.c[st][lane], t.rec2 + id);
+            const float4 *src = PS_REC(t, id, 0);
+            cp_async16(&q.a[st][lane], src);
+            cp_async16(&q.b[st][lane], src + 1);
+            cp_async16(&q.c[st][lane], src + 2);
         }
         cp_async_commit();
     };
@@ -485,6 +487,50 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     cp_async_wait_group<0>();
 }
 
+// 3D: which of the eight 8x4 blocks of tile (tx, ty) can the splat contribute to?  Same test as
+// ellipse_hits_box for every block, with the per-column / per-row terms shared: the blocks' pixel-centre
+// boxes are bounded by 4 vertical and 8 horizontal lines.
+__device__ __forceinline__ uint32_t block_mask8_3d(const float4 &r0, const float4 &r1, int tx, int ty)
+{
+    const float hA = r1.x, B = r1.y, hC = r1.z;
+    const float lim = r0.z * 1.0001f + 2.0f * THR_SLACK;
+    const float kx = __fdividef(-B, 2.0f * hC), ky = __fdividef(-B, 2.0f * hA);
+    const float X0 = (float)(tx * PS_TILE) - r0.x, Y0 = (float)(ty * PS_TILE) - r0.y;
+    float ux0[2], ux1[2], cx[2], tx_[2], ax[2], bx_[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        ux0[i] = X0 + (8.0f * i + 0.5f);
+        ux1[i] = X0 + (8.0f * i + 7.5f);
+        cx[i] = fminf(fmaxf(0.0f, ux0[i]), ux1[i]);
+        tx_[i] = kx * cx[i];          // unconstrained minimiser along the vertical line ux = cx
+        ax[i] = hA * cx[i] * cx[i];
+        bx_[i] = B * cx[i];
+    }
+    float uy0[4], uy1[4], cy[4], ty_[4], ay[4], by_[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uy0[j] = Y0 + (4.0f * j + 0.5f);
+        uy1[j] = Y0 + (4.0f * j + 3.5f);
+        cy[j] = fminf(fmaxf(0.0f, uy0[j]), uy1[j]);
+        ty_[j] = ky * cy[j];
+        ay[j] = hC * cy[j] * cy[j];
+        by_[j] = B * cy[j];
+    }
+    uint32_t m8 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = k & 1, j = k >> 1;
+        const float t1 = fminf(fmaxf(tx_[i], uy0[j]), uy1[j]);
+        const float s1 = ax[i] + (hC * t1 + bx_[i]) * t1;
+        const float t2 = fminf(fmaxf(ty_[j], ux0[i]), ux1[i]);
+        const float s2 = ay[j] + (hA * t2 + by_[j]) * t2;
+        const bool inx = cx[i] == 0.0f, iny = cy[j] == 0.0f;
+        const bool hit = (inx && iny) || (!inx && !(s1 > lim)) || (!iny && !(s2 > lim));
+        m8 |= hit ? (1u << k) : 0u;
+    }
+    return m8;
+}
+
 // Split every non-empty tile list, in order, into the lists of its eight 8x4 pixel blocks.
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -500,27 +546,40 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     const int start = offsets[lin], len = offsets[lin + 1] - start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *out = blist + 8 * (size_t)start;
+    const uint32_t *list = vals + start;
+    uint32_t inside8 = 0; // blocks that have at least one pixel inside the image
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (tx * PS_TILE + (k & 1) * 8 < g.W && ty * PS_TILE + (k >> 1) * 4 < g.H) inside8 |= 1u << k;
     if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
+    // software pipeline: ids two rounds ahead, records one round ahead
+    const int tid = threadIdx.x;
+    uint32_t id_n = (tid < len) ? __ldg(list + tid) : 0u;
+    uint32_t id_nn = (256 + tid < len) ? __ldg(list + 256 + tid) : 0u;
+    float4 r0_n = __ldg(PS_REC(t, id_n, 0));
+    float4 r1_n = (MODE == PS_MODE_3D) ? __ldg(PS_REC(t, id_n, 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int first = 0; first < len; first += 256) {
-        const int j = first + threadIdx.x;
+        const int j = first + tid;
+        const float4 r0 = r0_n, r1 = r1_n;
+        {
+            const uint32_t id_next = id_nn;
+            id_nn = (first + 512 + tid < len) ? __ldg(list + first + 512 + tid) : 0u;
+            r0_n = __ldg(PS_REC(t, id_next, 0));
+            if (MODE == PS_MODE_3D) r1_n = __ldg(PS_REC(t, id_next, 1));
+        }
         uint32_t m8 = 0;
         if (j < len) {
-            const uint32_t id = __ldg(vals + start + j);
-            const float4 r0 = __ldg(t.rec0 + id);
-            float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == PS_MODE_3D) r1 = __ldg(t.rec1 + id);
+            if (MODE == PS_MODE_3D) {
+                m8 = block_mask8_3d(r0, r1, tx, ty);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int bx = tx * PS_TILE + (k & 1) * 8, by = ty * PS_TILE + (k >> 1) * 4;
-                bool hit;
-                if (MODE == PS_MODE_3D)
-                    hit = ellipse_hits_box(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z, (float)bx + 0.5f, (float)bx + 7.5f,
-                                           (float)by + 0.5f, (float)by + 3.5f);
-                else
-                    hit = rect_hits_box(r0.z, r0.w, bx, bx + 7, by, by + 3);
-                if (hit && bx < g.W && by < g.H) m8 |= 1u << k;
+                for (int k = 0; k < 8; ++k) {
+                    const int bx = tx * PS_TILE + (k & 1) * 8, by = ty * PS_TILE + (k >> 1) * 4;
+                    if (rect_hits_box(r0.z, r0.w, bx, bx + 7, by, by + 3)) m8 |= 1u << k;
+                }
             }
+            m8 &= inside8;
         }
         uint32_t bal[8];
 #pragma unroll

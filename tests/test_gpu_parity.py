@@ -236,3 +236,30 @@ def test_batch_invariance_full_size_c2():
                                          Ks[v:v + 1], bg, w_rgb[v:v + 1].contiguous(), w_a[v:v + 1].contiguous())[0]
     rel = column_rel_err(g_all.cpu().numpy(), g_sum.cpu().numpy())
     assert rel.max() < 1e-4, rel
+
+
+def test_3d_many_gaussians_global_rank_path():
+    """N above the shared-memory capacity of the per-view depth ranking (17.8k) takes the global-scratch variant."""
+    _, _, _, synth = _mods()
+    vm, Ks = synth.ring_cameras(6, ds=12.0)
+    p = synth.gaussians_3d(20000, 31)[None]
+    _compare("3d", p, torch.zeros(1, dtype=torch.int32), 96, 80, (1.0, 1.0, 1.0), vm[4:5], Ks[4:5])
+
+
+@pytest.mark.parametrize("mode", ["3d", "2d"])
+def test_large_image_global_histogram_path(mode):
+    """More than 8192 tiles per view: the per-tile histograms of projection / partition use global atomics."""
+    _, _, _, synth = _mods()
+    W, H = 2064, 1040  # 129 x 65 = 8385 tiles
+    if mode == "3d":
+        vm, Ks = synth.ring_cameras(6, ds=1152.0 / W)
+        p = synth.gaussians_3d(300, 41)
+        p[:, 3:6] += 1.5
+        _compare("3d", p[None], torch.zeros(1, dtype=torch.int32), W, H, (0.1, 0.2, 0.3), vm[:1], Ks[:1], check_grad=True)
+    else:
+        g = torch.Generator().manual_seed(3)
+        N = 200
+        p = torch.cat([torch.rand(N, 1, generator=g) * W, torch.rand(N, 1, generator=g) * H,
+                       torch.log(torch.rand(N, 2, generator=g) * 6 + 0.5), torch.rand(N, 1, generator=g) * 6.28,
+                       torch.rand(N, 3, generator=g), torch.randn(N, 1, generator=g)], 1)
+        _compare("2d", p[None], torch.zeros(1, dtype=torch.int32), W, H, (1.0, 1.0, 1.0))
