@@ -49,9 +49,9 @@ extern "C" {
 #define PS_TAP_TILE_OFFSETS 3  /* int32 [V*n_tiles + 1] first sorted index of every (view, tile)  */
 #define PS_TAP_LAST_IDS 4      /* int32 [V,H,W] 1 + index of last contributing entry              */
 #define PS_TAP_TILES_TOUCHED 5 /* int32 [V*N]                                                    */
-#define PS_TAP_REC0 6          /* float4 [V*N] 3D: x,y,log(255*opacity),opacity  2D: u,v,rect(lo),rect(hi) */
+#define PS_TAP_REC0 6          /* float4 [V*N] 3D: x,y,log(255*opacity),opacity  2D: u,v,log(opacity/tau),opacity */
 #define PS_TAP_REC1 7          /* float4 [V*N] 3D: A/2,B,C/2,0   2D: cos,sin,iax,iay             */
-#define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,0       2D: r,g,b,opacity               */
+#define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,0       2D: r,g,b,0                     */
 #define PS_TAP_DEPTH 9         /* uint32 [V*N] 3D: bits of the camera-space depth (key low word)  */
 
 typedef struct ps_ctx ps_ctx;     /* per-device context (stream-ordered scratch pool, pinned mailbox) */

@@ -341,14 +341,19 @@ void ora2d_project(const float *params, int N, int W, int H,
         if (!(o > ORA_TAU_2D)) continue;
         float chk = ((((u + v) + iax) + iay) + sn) + cs;
         if (!(chk - chk == 0.0f)) continue; /* non-finite -> culled */
-        /* g < tau outside |d| > sqrt(ln(o/tau) * max(ax, ay)) */
+        /* g >= tau  <=>  q <= L = ln(o/tau): an ellipse.  Listed on the tiles met by its bounding box,
+         * half-widths sqrt(L * (M^-1)_xx), sqrt(L * (M^-1)_yy) with M^-1 = R^T diag(ax, ay) R, plus one pixel
+         * of slack so that no pixel passing the fp32 test q <= L can fall outside the listed tiles */
         float L = d_log(o * ORA_TAU_INV_2D);
-        float h = ceilf(sqrtf(L * fmaxf(ax, ay)));
-        if (!(h == h)) continue;
-        h = fminf(h, ORA_RADIUS_MAX);
-        float x0 = fmaxf(ceilf(u - h), 0.0f), x1 = fminf(floorf(u + h), (float)(W - 1));
-        float y0 = fmaxf(ceilf(v - h), 0.0f), y1 = fminf(floorf(v + h), (float)(H - 1));
+        float cc = cs * cs, ss = sn * sn;
+        float mxx = fmaf(ay, ss, ax * cc), myy = fmaf(ay, cc, ax * ss);
+        float hx = ceilf(sqrtf(L * mxx)) + 1.0f, hy = ceilf(sqrtf(L * myy)) + 1.0f;
+        if (!(hx == hx) || !(hy == hy)) continue;
+        hx = fminf(hx, ORA_RADIUS_MAX); hy = fminf(hy, ORA_RADIUS_MAX);
+        float x0 = fmaxf(ceilf(u - hx), 0.0f), x1 = fminf(floorf(u + hx), (float)(W - 1));
+        float y0 = fmaxf(ceilf(v - hy), 0.0f), y1 = fminf(floorf(v + hy), (float)(H - 1));
         if (!(x0 <= x1) || !(y0 <= y1)) continue;
+        g[7] = L;
         g[0] = u; g[1] = v; g[2] = cs; g[3] = sn; g[4] = iax; g[5] = iay;
         rc[0] = (int)x0; rc[1] = (int)y0; rc[2] = (int)x1; rc[3] = (int)y1;
         tr[0] = rc[0] / ORA_TILE; tr[1] = rc[1] / ORA_TILE;
@@ -550,14 +555,17 @@ void ora3d_raster_bwd(int W, int H, const float *geom, const float *rgbtab, cons
  * <= 3e-6 apart in fp32 over 16000 layers) so that the backward can replay T by
  * division.  Stop once T <= 2^-20 (what is left can add at most 9.6e-7).
  */
-static inline float g2d(const float *g, float x, float y, float *dxr_, float *dyr_)
+/* returns 0 if the pixel is outside the Gaussian's footprint q <= L, else 1 and g = o * exp(-q) */
+static inline int g2d(const float *g, float x, float y, float *dxr_, float *dyr_, float *gv)
 {
     float dx = x - g[0], dy = y - g[1];
     float dxr = fmaf(g[3], dy, g[2] * dx);
     float dyr = fmaf(g[2], dy, (-g[3]) * dx);
     float q = fmaf(dyr * dyr, g[5], (dxr * dxr) * g[4]);
     *dxr_ = dxr; *dyr_ = dyr;
-    return g[6] * d_exp(-q);
+    if (!(q <= g[7])) return 0;
+    *gv = g[6] * d_exp(-q);
+    return 1;
 }
 
 void ora2d_raster_fwd(int W, int H, const float *geom, const float *rgbtab, const int *rect,
@@ -574,10 +582,8 @@ void ora2d_raster_fwd(int W, int H, const float *geom, const float *rgbtab, cons
                     int cnt = 0, lst = s;
                     for (int k = s; k < e; ++k) {
                         int gid = vals[k] - id_base;
-                        const int *rc = rect + 4 * (size_t)gid;
-                        if (j < rc[0] || j > rc[2] || i < rc[1] || i > rc[3]) continue;
-                        float dxr, dyr;
-                        float gv = g2d(geom + 8 * (size_t)gid, (float)j, (float)i, &dxr, &dyr);
+                        float dxr, dyr, gv;
+                        if (!g2d(geom + 8 * (size_t)gid, (float)j, (float)i, &dxr, &dyr, &gv)) continue;
                         float contrib = gv * T;
                         const float *c = rgbtab + 3 * (size_t)gid;
                         r = fmaf(contrib, c[0], r); gc = fmaf(contrib, c[1], gc); b = fmaf(contrib, c[2], b);
@@ -617,10 +623,8 @@ void ora2d_raster_bwd(int W, int H, const float *geom, const float *rgbtab, cons
                     int n = 0;
                     for (int k = s; k < e; ++k) {
                         int gid = vals[k] - id_base;
-                        const int *rc = rect + 4 * (size_t)gid;
-                        if (j < rc[0] || j > rc[2] || i < rc[1] || i > rc[3]) continue;
-                        float dxr, dyr;
-                        float gv = g2d(geom + 8 * (size_t)gid, (float)j, (float)i, &dxr, &dyr);
+                        float dxr, dyr, gv;
+                        if (!g2d(geom + 8 * (size_t)gid, (float)j, (float)i, &dxr, &dyr, &gv)) continue;
                         if (n == cap) {
                             cap *= 2;
                             sT = (float *)realloc(sT, cap * 4); sG = (float *)realloc(sG, cap * 4);

@@ -132,7 +132,9 @@ PS_HD int ps_tile_bits(int n_tiles)
 //       (A/2, C/2: exact halvings, what the pair arithmetic uses; thr = log(255 * opacity), the
 //        largest sigma that can pass alpha >= 1/255; rec0 + rec1 is all the culling needs; the radii
 //        only shape the tile rectangle and the depth word goes to its own array)
-//   2D  rec0 = u, v, bits(x0|y0<<16), bits(x1|y1<<16)   rec1 = cos, sin, iax, iay   rec2 = r, g, b, opacity
+//   2D  rec0 = u, v, L, opacity   rec1 = cos, sin, iax, iay   rec2 = r, g, b, 0
+//       (L = log(opacity / tau): a pixel is in the footprint iff q <= L; the pixel rectangle of the ellipse's
+//        bounding box only shapes the tile rectangle)
 // tile rect: tx0, ty0, tx1, ty1 (exclusive max); culled <=> empty.
 // ---------------------------------------------------------------------------------------
 struct PsRecord {
@@ -141,7 +143,7 @@ struct PsRecord {
     float r2[4];
     int tile[4];
     uint32_t low; // low word of the sort key: depth bits (3D) or row index (2D)
-    float thr;    // 3D: log(255 * opacity)
+    float thr;    // 3D: log(255 * opacity)   2D: log(opacity / tau)
 };
 
 struct PsProj3dAux { // intermediates the projection backward re-uses
@@ -289,6 +291,7 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
 }
 
 // 2D activations + binning extent. Returns 1 if listed anywhere.
+// PsRecord (contract level): r0 = u, v, bits(x0|y0<<16), bits(x1|y1<<16); r1 = cos, sin, iax, iay; r2 = r, g, b, o.
 PS_HD int ps_project2d(const float *row, uint32_t row_index, int W, int H, PsRecord *rec)
 {
     ps_record_clear(rec);
@@ -306,13 +309,17 @@ PS_HD int ps_project2d(const float *row, uint32_t row_index, int W, int H, PsRec
     if (!(o > PS_TAU_2D)) return 0;
     float chk = psm_add(psm_add(psm_add(psm_add(psm_add(u, v), iax), iay), sn), cs);
     if (!psm_finite(chk)) return 0;
+    // g >= tau <=> q <= L = ln(o / tau): an ellipse, listed on the tiles met by its bounding box (+1 px of slack)
     float L = psm_log(psm_mul(o, PS_TAU_INV_2D));
-    float h = ceilf(psm_sqrt(psm_mul(L, fmaxf(ax, ay))));
-    if (!(h == h)) return 0;
-    h = fminf(h, PS_RADIUS_MAX);
-    float x0 = fmaxf(ceilf(psm_sub(u, h)), 0.0f), x1 = fminf(floorf(psm_add(u, h)), (float)(W - 1));
-    float y0 = fmaxf(ceilf(psm_sub(v, h)), 0.0f), y1 = fminf(floorf(psm_add(v, h)), (float)(H - 1));
+    float cc = psm_mul(cs, cs), ss = psm_mul(sn, sn);
+    float mxx = psm_fma(ay, ss, psm_mul(ax, cc)), myy = psm_fma(ay, cc, psm_mul(ax, ss));
+    float hx = psm_add(ceilf(psm_sqrt(psm_mul(L, mxx))), 1.0f), hy = psm_add(ceilf(psm_sqrt(psm_mul(L, myy))), 1.0f);
+    if (!(hx == hx) || !(hy == hy)) return 0;
+    hx = fminf(hx, PS_RADIUS_MAX); hy = fminf(hy, PS_RADIUS_MAX);
+    float x0 = fmaxf(ceilf(psm_sub(u, hx)), 0.0f), x1 = fminf(floorf(psm_add(u, hx)), (float)(W - 1));
+    float y0 = fmaxf(ceilf(psm_sub(v, hy)), 0.0f), y1 = fminf(floorf(psm_add(v, hy)), (float)(H - 1));
     if (!(x0 <= x1) || !(y0 <= y1)) return 0;
+    rec->thr = L;
     int ix0 = (int)x0, iy0 = (int)y0, ix1 = (int)x1, iy1 = (int)y1;
     rec->r0[0] = u; rec->r0[1] = v;
     rec->r0[2] = psm_u2f((uint32_t)ix0 | ((uint32_t)iy0 << 16));

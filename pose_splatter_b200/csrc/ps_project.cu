@@ -65,9 +65,9 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
             t.depth[idx] = rec.low;
         } else {
             float4 *dst = PS_REC(t, idx, 0);
-            dst[0] = make_float4(rec.r0[0], rec.r0[1], rec.r0[2], rec.r0[3]);
+            dst[0] = make_float4(rec.r0[0], rec.r0[1], rec.thr, rec.r2[3]);
             dst[1] = make_float4(rec.r1[0], rec.r1[1], rec.r1[2], rec.r1[3]);
-            dst[2] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], rec.r2[3]);
+            dst[2] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], 0.0f);
             dst[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         t.tile_rect[idx] = make_uint2((uint32_t)rec.tile[0] | ((uint32_t)rec.tile[1] << 16),
@@ -128,7 +128,7 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
     if (MODE == PS_MODE_2D) {
         const float4 r1 = *PS_REC(t, idx, 1);
         const float cs = r1.x, sn = r1.y, iax = r1.z, iay = r1.w;
-        const float o = PS_REC(t, idx, 2)->w;
+        const float o = PS_REC(t, idx, 0)->w;
         const float sx = psm_exp(r[2]), sy = psm_exp(r[3]);
         out[0] = -(cs * a[3] - sn * a[4]);
         out[1] = -(sn * a[3] + cs * a[4]);

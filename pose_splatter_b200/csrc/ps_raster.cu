@@ -100,12 +100,13 @@ __device__ __forceinline__ bool ellipse_hits_box(float gx, float gy, float hA, f
     return !(best > thr * 1.0001f + 2.0f * THR_SLACK);
 }
 
-// 2D: does the splat's pixel rectangle meet the pixel box [bx0, bx1] x [by0, by1]?
-__device__ __forceinline__ bool rect_hits_box(float lo_bits, float hi_bits, int bx0, int bx1, int by0, int by1)
+// 2D: q = dxr^2 iax + dyr^2 iay with (dxr, dyr) = R (dx, dy) is the quadratic form hA dx^2 + B dx dy + hC dy^2
+__device__ __forceinline__ void conic2d(const float4 &r1, float &hA, float &B, float &hC)
 {
-    const uint32_t lo = __float_as_uint(lo_bits), hi = __float_as_uint(hi_bits);
-    const int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
-    return x0 <= bx1 && x1 >= bx0 && y0 <= by1 && y1 >= by0;
+    const float cc = r1.x * r1.x, ss = r1.y * r1.y;
+    hA = cc * r1.z + ss * r1.w;
+    hC = ss * r1.z + cc * r1.w;
+    B = 2.0f * r1.x * r1.y * (r1.z - r1.w);
 }
 
 // bounding box (in block-local pixel coordinates) of the lanes set in `active` (lane = y * 8 + x); active != 0
@@ -132,14 +133,12 @@ __device__ __forceinline__ uint32_t cull_chunk(const Ring &q, int st, int lane, 
     active_box(live, ax0, ax1, ay0, ay1);
     bool hit = false;
     if (valid) {
-        const float4 a0 = q.a[st][lane];
-        if (MODE == PS_MODE_3D) {
-            const float4 a1 = q.b[st][lane];
-            hit = ellipse_hits_box(a0.x, a0.y, a1.x, a1.y, a1.z, a0.z, (float)(c.bx + ax0) + 0.5f,
-                                   (float)(c.bx + ax1) + 0.5f, (float)(c.by + ay0) + 0.5f, (float)(c.by + ay1) + 0.5f);
-        } else {
-            hit = rect_hits_box(a0.z, a0.w, c.bx + ax0, c.bx + ax1, c.by + ay0, c.by + ay1);
-        }
+        const float4 a0 = q.a[st][lane], a1 = q.b[st][lane];
+        const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f; // pixel centres: +0.5 in 3D, integers in 2D
+        float hA = a1.x, B = a1.y, hC = a1.z;
+        if (MODE == PS_MODE_2D) conic2d(a1, hA, B, hC);
+        hit = ellipse_hits_box(a0.x, a0.y, hA, B, hC, a0.z, (float)(c.bx + ax0) + half, (float)(c.bx + ax1) + half,
+                               (float)(c.by + ay0) + half, (float)(c.by + ay1) + half);
     }
     return __ballot_sync(FULL, hit);
 }
@@ -248,19 +247,16 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                     }
                 }
             } else {
-                const uint32_t loa = __float_as_uint(r0a.z), hia = __float_as_uint(r0a.w);
-                const uint32_t lob = __float_as_uint(r0b.z), hib = __float_as_uint(r0b.w);
-                const bool ina = !done && c.px >= (int)(loa & 0xffff) && c.px <= (int)(hia & 0xffff) &&
-                                 c.py >= (int)(loa >> 16) && c.py <= (int)(hia >> 16);
-                const bool inb = two && !done && c.px >= (int)(lob & 0xffff) && c.px <= (int)(hib & 0xffff) &&
-                                 c.py >= (int)(lob >> 16) && c.py <= (int)(hib >> 16);
-                if (!__any_sync(FULL, ina || inb)) continue;
                 float dxr, dyr;
-                const float4 r2a = q2[ea], r2b = q2[eb];
                 const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
                 const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
-                const float gva = psm_mul(r2a.w, psm_exp(-qa));
-                const float gvb = psm_mul(r2b.w, psm_exp(-qb));
+                const bool ina = !done && qa <= r0a.z;        // inside the footprint q <= L
+                const bool inb = two && !done && qb <= r0b.z;
+                if (!__any_sync(FULL, ina || inb)) continue;
+                const float4 r2a = q2[ea], r2b = q2[eb];
+                // 0 <= q <= L <= ~20: the clamp inside psm_exp is the identity
+                const float gva = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-qa, 0x1.715476p+0f)));
+                const float gvb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-qb, 0x1.715476p+0f)));
                 if (ina) {
                     const float contrib = psm_mul(gva, T);
                     cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
@@ -454,14 +450,12 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                 v[7] = r1.y * sx + 2.0f * r1.z * sy;
                 v8 = (contrib && oe <= PS_ALPHA_MAX) ? ex * v_alpha : 0.0f;
             } else {
-                const uint32_t lo = __float_as_uint(r0.z), hi = __float_as_uint(r0.w);
-                const bool contrib = active && c.px >= (int)(lo & 0xffff) && c.px <= (int)(hi & 0xffff) &&
-                                     c.py >= (int)(lo >> 16) && c.py <= (int)(hi >> 16);
-                if (!__any_sync(FULL, contrib)) continue;
                 float dxr, dyr;
                 const float4 r2 = q2[e];
                 const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
-                const float gv = psm_mul(r2.w, psm_exp(-qv));
+                const bool contrib = active && qv <= r0.z;
+                if (!__any_sync(FULL, contrib)) continue;
+                const float gv = psm_mul(r0.w, psm_exp2_inrange(psm_mul(-qv, 0x1.715476p+0f)));
                 const float Tb = (pos == my_last - 1) ? Tcur : __fdividef(Tcur, 1.0f - gv);
                 const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
                 const float dLdg = Tb * (cw - S);
@@ -487,20 +481,20 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     cp_async_wait_group<0>();
 }
 
-// 3D: which of the eight 8x4 blocks of tile (tx, ty) can the splat contribute to?  Same test as
+// Which of the eight 8x4 blocks of tile (tx, ty) can the splat contribute to?  `half` = 0.5 (3D pixel centres) or
+// 0 (2D: integer pixel centres).  Same test as
 // ellipse_hits_box for every block, with the per-column / per-row terms shared: the blocks' pixel-centre
 // boxes are bounded by 4 vertical and 8 horizontal lines.
-__device__ __forceinline__ uint32_t block_mask8_3d(const float4 &r0, const float4 &r1, int tx, int ty)
+__device__ __forceinline__ uint32_t block_mask8(float gx, float gy, float hA, float B, float hC, float thr, float half, int tx, int ty)
 {
-    const float hA = r1.x, B = r1.y, hC = r1.z;
-    const float lim = r0.z * 1.0001f + 2.0f * THR_SLACK;
+    const float lim = thr * 1.0001f + 2.0f * THR_SLACK;
     const float kx = __fdividef(-B, 2.0f * hC), ky = __fdividef(-B, 2.0f * hA);
-    const float X0 = (float)(tx * PS_TILE) - r0.x, Y0 = (float)(ty * PS_TILE) - r0.y;
+    const float X0 = ((float)(tx * PS_TILE) + half) - gx, Y0 = ((float)(ty * PS_TILE) + half) - gy;
     float ux0[2], ux1[2], cx[2], tx_[2], ax[2], bx_[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        ux0[i] = X0 + (8.0f * i + 0.5f);
-        ux1[i] = X0 + (8.0f * i + 7.5f);
+        ux0[i] = X0 + 8.0f * i;
+        ux1[i] = X0 + (8.0f * i + 7.0f);
         cx[i] = fminf(fmaxf(0.0f, ux0[i]), ux1[i]);
         tx_[i] = kx * cx[i];          // unconstrained minimiser along the vertical line ux = cx
         ax[i] = hA * cx[i] * cx[i];
@@ -509,8 +503,8 @@ __device__ __forceinline__ uint32_t block_mask8_3d(const float4 &r0, const float
     float uy0[4], uy1[4], cy[4], ty_[4], ay[4], by_[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uy0[j] = Y0 + (4.0f * j + 0.5f);
-        uy1[j] = Y0 + (4.0f * j + 3.5f);
+        uy0[j] = Y0 + 4.0f * j;
+        uy1[j] = Y0 + (4.0f * j + 3.0f);
         cy[j] = fminf(fmaxf(0.0f, uy0[j]), uy1[j]);
         ty_[j] = ky * cy[j];
         ay[j] = hC * cy[j] * cy[j];
@@ -557,7 +551,7 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     uint32_t id_n = (tid < len) ? __ldg(list + tid) : 0u;
     uint32_t id_nn = (256 + tid < len) ? __ldg(list + 256 + tid) : 0u;
     float4 r0_n = __ldg(PS_REC(t, id_n, 0));
-    float4 r1_n = (MODE == PS_MODE_3D) ? __ldg(PS_REC(t, id_n, 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r1_n = __ldg(PS_REC(t, id_n, 1));
     __syncthreads();
     for (int first = 0; first < len; first += 256) {
         const int j = first + tid;
@@ -566,19 +560,13 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             const uint32_t id_next = id_nn;
             id_nn = (first + 512 + tid < len) ? __ldg(list + first + 512 + tid) : 0u;
             r0_n = __ldg(PS_REC(t, id_next, 0));
-            if (MODE == PS_MODE_3D) r1_n = __ldg(PS_REC(t, id_next, 1));
+            r1_n = __ldg(PS_REC(t, id_next, 1));
         }
         uint32_t m8 = 0;
         if (j < len) {
-            if (MODE == PS_MODE_3D) {
-                m8 = block_mask8_3d(r0, r1, tx, ty);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int bx = tx * PS_TILE + (k & 1) * 8, by = ty * PS_TILE + (k >> 1) * 4;
-                    if (rect_hits_box(r0.z, r0.w, bx, bx + 7, by, by + 3)) m8 |= 1u << k;
-                }
-            }
+            float hA = r1.x, B = r1.y, hC = r1.z;
+            if (MODE == PS_MODE_2D) conic2d(r1, hA, B, hC);
+            m8 = block_mask8(r0.x, r0.y, hA, B, hC, r0.z, (MODE == PS_MODE_3D) ? 0.5f : 0.0f, tx, ty);
             m8 &= inside8;
         }
         uint32_t bal[8];

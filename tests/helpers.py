@@ -80,13 +80,18 @@ def records_from_oracle(mode, tab, table=False):
             r[:, 11] = 0.0
     else:
         r[:, 0:2] = g[:, 0:2]
-        lo = (rect[:, 0].astype(np.uint32) | (rect[:, 1].astype(np.uint32) << 16))
-        hi = (rect[:, 2].astype(np.uint32) | (rect[:, 3].astype(np.uint32) << 16))
-        r[:, 2] = lo.view(np.float32)
-        r[:, 3] = hi.view(np.float32)
         r[:, 4:8] = g[:, 2:6]
         r[:, 8:11] = rgb
-        r[:, 11] = g[:, 6]
+        if table:   # (u, v, L, o | cos, sin, iax, iay | r, g, b, 0)
+            r[:, 2] = g[:, 7]
+            r[:, 3] = g[:, 6]
+            r[:, 11] = 0.0
+        else:       # contract-level PsRecord: pixel rectangle bits in r0, opacity in r2
+            lo = (rect[:, 0].astype(np.uint32) | (rect[:, 1].astype(np.uint32) << 16))
+            hi = (rect[:, 2].astype(np.uint32) | (rect[:, 3].astype(np.uint32) << 16))
+            r[:, 2] = lo.view(np.float32)
+            r[:, 3] = hi.view(np.float32)
+            r[:, 11] = g[:, 6]
     return r, listed
 
 
