@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (x6 cameras = views); 0 = workload default")
     ap.add_argument("--split-frames", action="store_true", help="shard views (not frames): NCCL all-reduce of d_params")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short c3 (2D) measurement that rides along with c2")
     ap.add_argument("--n", type=int, default=0, help="override Gaussians per frame (debug only; invalidates the metric)")
     return ap.parse_args()
 
@@ -159,8 +160,6 @@ def workload_name(wl):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from pose_splatter_b200 import _capi, batched, synth
-    from pose_splatter_b200 import dist as psd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -170,11 +169,39 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
-    wl = args.workload
+    out = measure(args, args.workload, args.steps, world, rank, local, dev, primary=True)
+    if args.workload == "c2" and not args.no_secondary and not args.n and not args.split_frames:
+        # the metric names two configurations; the 2D one (BASELINE.json configs[2]) rides along, briefly
+        other = measure(args, "c3", max(2, min(3, args.steps)), world, rank, local, dev, primary=False)
+        if rank == 0:
+            out["also"] = {"c3": {k: other[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline",
+                                                        "stage_ms_per_step", "pairs")}}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ncu_traffic(wl, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload, or None."""
+    try:
+        return json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())[wl][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def measure(args, wl, steps, world, rank, local, dev, primary):
+    import torch
+    import torch.distributed as dist
+    from pose_splatter_b200 import _capi, batched, synth
+    from pose_splatter_b200 import dist as psd
+
     cfg = synth.WORKLOADS[wl]
     mode, W, H = cfg["mode"], cfg["width"], cfg["height"]
-    F = args.frames or FRAMES_DEFAULT[wl]
+    F = (args.frames if primary else 0) or FRAMES_DEFAULT[wl]
     n_cams = 6
     n_sets = 4  # rotate distinct input batches so no step finds its inputs in L2
 
@@ -212,30 +239,59 @@ def run_b200(args):
             psd.reduce_frame_grads(d_params)
         return d_params
 
-    out_host = torch.empty_like(host[0]["params"]).pin_memory()
-    loss_host = torch.empty(1).pin_memory()
+    # --- end to end through the public API (render_views + autograd) from pinned host buffers.  Copies run on two
+    # side streams so that step k+1's host->device copy and step k-1's device->host copy overlap step k's kernels
+    # (every copy of every timed step is inside the timed region; the region ends when all three streams are idle).
+    out_host = [torch.empty_like(host[0]["params"]).pin_memory() for _ in range(2)]
+    loss_host = torch.empty(2).pin_memory()
+    h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    staged = {}
 
-    def step_e2e(k):
-        h = host[k % n_sets]
-        p = h["params"].to(dev, non_blocking=True).requires_grad_(True)
-        vf = h["view_frame"].to(dev, non_blocking=True)
-        vm = h["viewmats"].to(dev, non_blocking=True)
-        Kd = h["Ks"].to(dev, non_blocking=True)
-        rgb, alpha = batched.render_views(mode, p, vf, W, H, bg, vm, Kd)
+    def stage_inputs(k):
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(h2d_stream):
+            t = {name: v.to(dev, non_blocking=True) for name, v in host[k % n_sets].items()}
+            ev = torch.cuda.Event()
+            ev.record(h2d_stream)
+        for v in t.values():
+            v.record_stream(main)
+        staged[k] = (t, ev)
+
+    def step_e2e(k, last=False):
+        main = torch.cuda.current_stream(dev)
+        if k not in staged:
+            stage_inputs(k)
+        t, ev = staged.pop(k)
+        if not last:
+            stage_inputs(k + 1)
+        main.wait_event(ev)
+        p = t["params"].requires_grad_(True)
+        rgb, alpha = batched.render_views(mode, p, t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
         loss = (rgb * w_rgb).sum() + (alpha * w_a).sum()
         loss.backward()
         g = p.grad
         if need_reduce:
             psd.reduce_frame_grads(g)
-        out_host.copy_(g, non_blocking=True)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        lossd = loss.detach().reshape(1)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
+            out_host[k % 2].copy_(g, non_blocking=True)
+            loss_host[k % 2:k % 2 + 1].copy_(lossd, non_blocking=True)
+        g.record_stream(d2h_stream)
+        lossd.record_stream(d2h_stream)
+
+    def drain_e2e():
+        torch.cuda.current_stream(dev).wait_stream(d2h_stream)
+        torch.cuda.current_stream(dev).wait_stream(h2d_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False):
+    def timed(fn, steps, profile=False, e2e=False):
         barrier()
         if profile:
             _capi.set_profiling(dev, True)
@@ -244,7 +300,12 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(steps):
-            fn(k)
+            if e2e:
+                fn(k, last=(k == steps - 1))
+            else:
+                fn(k)
+        if e2e:
+            drain_e2e()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -259,11 +320,12 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches, stages = timed(step_resident, args.steps, profile=True)
+    ms_total, launches, stages = timed(step_resident, steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     for k in range(max(3, args.warmup)):
-        step_e2e(k)
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+        step_e2e(k, last=True)
+    drain_e2e()
+    ms_e2e, _, _ = timed(step_e2e, steps, e2e=True)
 
     # pair counts of one step (untimed) for the FP32 roofline of the rasterizers
     s0 = devs[0]
@@ -279,10 +341,8 @@ def run_b200(args):
     fp32_peak = _capi.fp32_peak_tflops(dev)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    views_total = V * world * args.steps
+        return None
+    views_total = V * world * steps
     value = views_total / (ms_total * 1e-3)
     e2e_value = views_total / (ms_e2e * 1e-3)
     peaks = {}
@@ -293,15 +353,16 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     stage_ms = {k: (v[0] / max(1, v[1]), v[1]) for k, v in stages.items()}  # average per launch
-    per_step = {k: v[0] / args.steps for k, v in stages.items()}
+    per_step = {k: v[0] / steps for k, v in stages.items()}
     dom = max(("raster_fwd", "raster_bwd"), key=lambda k: per_step[k])
     dom_ms = stage_ms[dom][0]
     achieved_tf = stats["pairs_evaluated"] * FLOPS_PER_PAIR[dom] / (dom_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
-                "peak_source": "FFMA micro-benchmark run in this process (ps_fp32_peak_probe); no tensor cores on this path",
+                "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(wl, dom),
+                "peak_source": "FFMA micro-benchmark run in this process (ps_fp32_peak_probe), 2 flops per FMA; "
+                               "MEASURED_PEAKS.json has no FP32 figure; no tensor cores on this path",
                 "work": f"{stats['pairs_evaluated']} evaluated (pixel,Gaussian) pairs per launch x {FLOPS_PER_PAIR[dom]:.0f} FP32 ops",
-                "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / args.steps)}
+                "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / steps)}
     VN = V * (args.n or cfg["n"])
     # rank: depth word + listed flag in, order + rank out; partition: rect + count + rank in, 4 B slot out per entry;
     # list sort: slot in, order gather, 4 B value out per entry; scan: one int in/out per (view, tile)
@@ -316,27 +377,27 @@ def run_b200(args):
                 "avg_launch_ms": sort_ms,
                 "project": {"achieved": proj_bytes / (stage_ms['project'][0] * 1e-3) / 1e9 if stage_ms['project'][0] else None,
                             "unit": "GB/s", "avg_launch_ms": stage_ms["project"][0]}}
-    out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+           "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": workload_name(wl), "mode": mode, "views_per_step_per_gpu": V, "frames_per_step_per_gpu": F,
                       "cameras": n_cams, "gaussians_per_frame": args.n or cfg["n"], "isect_per_step": M,
                       "parallelism": f"views sharded over {world} GPU(s), " + ("views split, NCCL all-reduce of d_params" if need_reduce else "whole frames per rank, no collective"),
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
-           "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / args.steps,
+           "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0].values())),
-                   "d2h_bytes_per_step": int(out_host.numel() * 4 + 4)},
+                   "d2h_bytes_per_step": int(out_host[0].numel() * 4 + 4),
+                   "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm,
            "stage_ms_per_step": per_step, "pairs": stats, "fp32_peak_tflops": fp32_peak}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and primary and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample_views = cores * (4 if wl in ("c1", "c2") else 1)
+        probe_vps, _ = cpu_views_per_second(wl, cores, cores, args.n)           # short probe sizes the sample
+        sample_views = int(min(4096, max(cores, round(probe_vps * 12.0 / cores) * cores)))  # ~12 s of CPU work
         vps, dt = cpu_views_per_second(wl, sample_views, cores, args.n)
         out["cpu_baseline"] = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
                                "sample": f"{sample_views} views of the same workload (full N, full resolution, fwd+bwd), {dt:.1f} s on {cores} threads"}
-    print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":
