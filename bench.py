@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--workload", default="c2", help="BASELINE.json config: c2 = 3D 288x256 (default), c3 = 2D 576x512")
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (x6 cameras = views); 0 = workload default")
     ap.add_argument("--split-frames", action="store_true", help="shard views (not frames): NCCL all-reduce of d_params")
+    ap.add_argument("--fused-reduce", action="store_true",
+                    help="with --split-frames: projection backward adds rows straight into the owner rank's d_params over NVLink")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short c3 (2D) measurement that rides along with c2")
     ap.add_argument("--n", type=int, default=0, help="override Gaussians per frame (debug only; invalidates the metric)")
@@ -227,12 +229,20 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     w_rgb, w_a = synth.cotangents(V, H, W, seed=7)
     w_rgb, w_a = w_rgb.to(dev), w_a.to(dev)
     need_reduce = args.split_frames and world > 1 and mode == "3d"
+    fused = need_reduce and args.fused_reduce
+    peer = psd.PeerGradBuffers(tuple(sets[0]["params"].shape), dev) if fused else None
     input_mb = sum(sum(t.numel() * t.element_size() for t in h.values()) for h in host) / 2**20
 
     def step_resident(k):
         s = devs[k % n_sets]
         rgb, alpha, _, saved = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H,
                                                    _capi.FLAG_SAVE_FOR_BACKWARD)
+        if fused:
+            peer.begin()
+            batched.backward_peer_raw(saved, s["params"], s["viewmats"], s["Ks"], bg, w_rgb, w_a, peer.rank_ptrs, peer.frame_owner)
+            peer.end()
+            saved.release()
+            return peer.buf
         d_params = batched.backward_raw(saved, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, w_rgb, w_a)
         saved.release()
         if need_reduce:
@@ -382,7 +392,9 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": workload_name(wl), "mode": mode, "views_per_step_per_gpu": V, "frames_per_step_per_gpu": F,
                       "cameras": n_cams, "gaussians_per_frame": args.n or cfg["n"], "isect_per_step": M,
-                      "parallelism": f"views sharded over {world} GPU(s), " + ("views split, NCCL all-reduce of d_params" if need_reduce else "whole frames per rank, no collective"),
+                      "parallelism": f"views sharded over {world} GPU(s), " + ("views split, gradient rows added into the owner rank's buffer over NVLink inside the projection-backward kernel" if fused
+                                                                                 else "views split, NCCL all-reduce of d_params" if need_reduce
+                                                                                 else "whole frames per rank, no collective"),
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
            "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0].values())),

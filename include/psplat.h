@@ -115,6 +115,21 @@ int ps_backward(ps_ctx *ctx, ps_saved *saved, const float *params, const int32_t
                 const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
                 void *stream);
 
+/*
+ * Backward with the cross-GPU gradient sum fused in (no reference counterpart: the reference is
+ * single-GPU).  For use when the cameras of one frame are rendered by different ranks: instead of writing its
+ * partial d_params and all-reducing it, the projection-backward kernel adds every finished row
+ * (red.global.add.v2.f32) straight into the d_params buffer of the rank that owns the frame.
+ *   d_params_ranks  DEVICE array [world] of device pointers: rank r's d_params buffer [F,N,P], each mapped into
+ *                   this process (peer memory over NVLink, e.g. torch symmetric memory); entry [own rank] is local
+ *   frame_owner     DEVICE int32 [F]: the rank that owns each frame
+ * Protocol (host side): every rank zeroes its own buffer, all ranks meet at a barrier, every rank calls this,
+ * all ranks meet at a barrier again; then rank r holds the complete gradient of the frames it owns.
+ */
+int ps_backward_peer(ps_ctx *ctx, ps_saved *saved, const float *params, const float *viewmats, const float *Ks,
+                     const float *background, const float *d_rgb, const float *d_alpha, float *const *d_params_ranks,
+                     const int32_t *frame_owner, void *stream);
+
 int ps_saved_info_get(const ps_saved *saved, ps_saved_info *out);
 /* Copy one tap (PS_TAP_*) into dst (device or host pointer), at most `bytes`; waits on the stream. */
 int ps_saved_copy(ps_ctx *ctx, const ps_saved *saved, int what, void *dst, size_t bytes, void *stream);

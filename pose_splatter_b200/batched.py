@@ -111,6 +111,16 @@ def _prep(t, dtype, dev):
     return t.detach().to(device=dev, dtype=dtype).contiguous()
 
 
+def backward_peer_raw(saved: SavedForward, params, viewmats, Ks, background, d_rgb, d_alpha, rank_ptrs, frame_owner):
+    """ps_backward_peer: rows are added into the d_params buffer of each frame's owner rank (peer memory).
+    rank_ptrs: int64 device tensor [world] of buffer addresses; frame_owner: int32 device tensor [F]."""
+    dev = params.device
+    _capi.check(_capi.load().ps_backward_peer(_capi.context(dev), saved.handle, _capi.ptr(params), _capi.ptr(viewmats),
+                                              _capi.ptr(Ks), _capi.ptr(background), _capi.ptr(d_rgb), _capi.ptr(d_alpha),
+                                              _capi.ptr(rank_ptrs), _capi.ptr(frame_owner), _capi.stream_ptr(dev)),
+                "ps_backward_peer")
+
+
 class _RenderViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, params, view_frame, viewmats, Ks, background, mode, width, height, opts):

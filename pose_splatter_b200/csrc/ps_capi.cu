@@ -1,4 +1,4 @@
-// ps_capi.cu -- C ABI of libpsplat.so (include/psplat.h): context, stream-ordered scratch,
+// ps_capi.cu -- C ABI of libpsplat.so (include/psplat.h): context, cached device scratch arena,
 // and the stage orchestration  project(+tile histogram) -> depth rank -> scan [M to host] ->
 // partition -> per-list bitmap sort -> fill empty tiles -> rasterize  (forward)  /
 // rasterize-backward -> projection-backward.
@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "ps_contract.cuh"
@@ -39,18 +41,100 @@ int fail(int code, const char *fmt, ...)
         (ctx)->launches += n_;                                                 \
     } while (0)
 
+// Device scratch arena: a per-device cache of cudaMalloc'ed blocks in geometric size classes (8 per octave), so the
+// steady state of a render loop allocates nothing (the list sizes change a little from step to step; the
+// driver's stream-ordered pool turned out to re-map memory on many calls, costing milliseconds of host time).
+// A cached block is handed out again only for work on the stream it was last used on (stream order makes the
+// reuse safe); a block last used on another stream is reused after synchronising that stream.
+struct ArenaBlock { void *p; size_t cap; cudaStream_t stream; };
+struct Arena {
+    std::mutex mu;
+    std::vector<ArenaBlock> free_blocks;
+    std::unordered_map<void *, size_t> live; // pointer -> capacity
+    size_t cached_bytes = 0;
+};
+constexpr int PS_MAX_DEVICES = 64;
+Arena g_arena[PS_MAX_DEVICES];
+constexpr size_t ARENA_CACHE_LIMIT = (size_t)48 << 30; // beyond this many cached bytes everything cached is released
+
+size_t arena_class(size_t bytes)
+{
+    if (bytes < 4096) return 4096;
+    int hb = 63 - __builtin_clzll((unsigned long long)bytes);
+    const size_t step = (size_t)1 << (hb - 3); // 8 classes per octave: at most 12.5 % slack
+    return (bytes + step - 1) & ~(step - 1);
+}
+
+void arena_release_cached(Arena &a)
+{
+    for (auto &b : a.free_blocks) { cudaStreamSynchronize(b.stream); cudaFree(b.p); }
+    a.free_blocks.clear();
+    a.cached_bytes = 0;
+}
+
+cudaError_t arena_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    *p = nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= PS_MAX_DEVICES) return cudaErrorInvalidDevice;
+    Arena &a = g_arena[dev];
+    const size_t cap = arena_class(bytes);
+    std::lock_guard<std::mutex> lock(a.mu);
+    int pick = -1;
+    for (int i = (int)a.free_blocks.size() - 1; i >= 0; --i) {
+        if (a.free_blocks[i].cap != cap) continue;
+        if (a.free_blocks[i].stream == s) { pick = i; break; }
+        if (pick < 0) pick = i;
+    }
+    if (pick >= 0) {
+        ArenaBlock b = a.free_blocks[pick];
+        a.free_blocks.erase(a.free_blocks.begin() + pick);
+        a.cached_bytes -= b.cap;
+        if (b.stream != s) cudaStreamSynchronize(b.stream);
+        a.live[b.p] = b.cap;
+        *p = b.p;
+        return cudaSuccess;
+    }
+    e = cudaMalloc(p, cap);
+    if (e != cudaSuccess) { // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        arena_release_cached(a);
+        e = cudaMalloc(p, cap);
+        if (e != cudaSuccess) return e;
+    }
+    a.live[*p] = cap;
+    return cudaSuccess;
+}
+
+void arena_free(void *p, cudaStream_t s)
+{
+    if (!p) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PS_MAX_DEVICES) return;
+    Arena &a = g_arena[dev];
+    std::lock_guard<std::mutex> lock(a.mu);
+    auto it = a.live.find(p);
+    if (it == a.live.end()) return;
+    const size_t cap = it->second;
+    a.live.erase(it);
+    a.free_blocks.push_back({ p, cap, s });
+    a.cached_bytes += cap;
+    if (a.cached_bytes > ARENA_CACHE_LIMIT) arena_release_cached(a);
+}
+
 template <typename T>
 cudaError_t dev_alloc(T **p, size_t count, cudaStream_t s)
 {
-    *p = nullptr;
     if (count == 0) count = 1;
-    return cudaMallocAsync((void **)p, count * sizeof(T), s);
+    return arena_alloc((void **)p, count * sizeof(T), s);
 }
 
 template <typename T>
 void dev_free(T *&p, cudaStream_t s)
 {
-    if (p) cudaFreeAsync((void *)p, s);
+    arena_free((void *)p, s);
     p = nullptr;
 }
 
@@ -103,6 +187,7 @@ struct ps_saved {
     uint64_t *keys; // sorted int64 keys, materialised only with PS_FLAG_KEEP_BINNING
     int32_t *last;  // [V,H,W] tile-list position + 1 of the last contributor (PS_FLAG_KEEP_BINNING: tap only)
     int32_t *blast; // [V,H,W] block-list index + 1 of the last contributor (what the backward starts from)
+    int32_t *frame_off, *frame_views; // CSR: the views of every frame (projection backward sums them per row)
     float *t_pen;   // [V,H,W]
 };
 
@@ -134,11 +219,6 @@ int ps_ctx_create(int device, ps_ctx **out)
     PS_CUDA(cudaMalloc((void **)&c->d_total, 2 * sizeof(int64_t)));
     PS_CUDA(cudaMalloc((void **)&c->d_stats, 4 * sizeof(unsigned long long)));
     PS_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
-    // keep freed scratch in the pool instead of returning it to the driver between calls
-    cudaMemPool_t pool;
-    PS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX;
-    PS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     *out = c;
     return 0;
 }
@@ -152,6 +232,10 @@ int ps_ctx_destroy(ps_ctx *ctx)
     cudaFree(ctx->d_stats);
     for (auto &sp : ctx->pending) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->spare) cudaEventDestroy(e);
+    if (ctx->device >= 0 && ctx->device < PS_MAX_DEVICES) {
+        std::lock_guard<std::mutex> lock(g_arena[ctx->device].mu);
+        arena_release_cached(g_arena[ctx->device]);
+    }
     delete ctx;
     return 0;
 }
@@ -166,6 +250,7 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
     dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
     dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bcount, s);
     dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->blast, s); dev_free(sv->t_pen, s);
+    sv->frame_off = sv->frame_views = nullptr; // live inside the offsets allocation
 }
 
 int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
@@ -204,6 +289,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
     int rc = 0;
     uint32_t *rank_scratch = nullptr;
     long long *scan_scratch = nullptr;
+    int32_t *csr_cursor = nullptr;
     // everything below jumps to `out` on error so scratch is always returned to the pool
 #define PS_TRY_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); goto out; } } while (0)
 #define PS_TRY_LAUNCH(call) do { int n_ = (call); if (n_ < 0) { rc = fail(3, "kernel launch failed in %s: %s", #call, cudaGetErrorString(cudaGetLastError())); goto out; } ctx->launches += n_; } while (0)
@@ -215,7 +301,12 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
         if (g.N > (1 << 20)) { rc = fail(1, "ps_forward: at most 2^20 Gaussians per frame (got %d)", g.N); goto out; }
         sv->M = 0;
         sv->n_work = 0;
-        PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1, s));
+        // offsets [T+1] | frame_off [F+1] | frame_views [V] | csr cursor [F] share one allocation: tiny pool
+        // allocations split the large free blocks the next call wants to reuse
+        PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1 + (size_t)g.F + 1 + (size_t)g.V + (size_t)g.F, s));
+        sv->frame_off = sv->l.offsets + T + 1;
+        sv->frame_views = sv->frame_off + g.F + 1;
+        csr_cursor = sv->frame_views + g.V;
         PS_TRY_CUDA(dev_alloc(&sv->l.cls, (size_t)PS_CLS_WORDS, s));
         PS_TRY_CUDA(dev_alloc(&scan_scratch, ps_scan_scratch_elems(g), s));
         PS_TRY_CUDA(cudaMemsetAsync(sv->l.offsets, 0, (T + 1) * sizeof(int32_t), s));
@@ -259,6 +350,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
                 PS_TRY_LAUNCH(ps_launch_debug_keys(g, sv->t, sv->l, sv->n_work, sv->keys, s));
             }
         }
+        if (save) PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, s));
         if (npix > 0) {
             if (save) {
                 PS_TRY_CUDA(dev_alloc(&sv->blast, npix, s));
@@ -288,9 +380,9 @@ out:
 #undef PS_TRY_LAUNCH
 }
 
-int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *view_frame, const float *viewmats,
-                const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
-                void *stream)
+static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const float *viewmats, const float *Ks,
+                         const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
+                         float *const *peers, const int32_t *owner, void *stream)
 {
     if (!ctx || !sv) return fail(1, "ps_backward: NULL context or saved state");
     const PsGeometry &g = sv->g;
@@ -299,12 +391,15 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
     const int P = g.mode == PS_MODE_3D ? 14 : 9;
     const size_t n_out = (size_t)g.F * g.N * P;
     if (n_out == 0) return 0;
-    if (!d_params) return fail(1, "ps_backward: NULL d_params");
-    PS_CUDA(cudaMemsetAsync(d_params, 0, n_out * sizeof(float), s));
+    if (!peers && !d_params) return fail(1, "ps_backward: NULL d_params");
     const size_t VN = (size_t)g.V * g.N;
-    if (VN == 0 || sv->M == 0 || (size_t)g.H * g.W == 0) return 0;
-    if (!sv->blast || !sv->t_pen) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
-    if (!d_rgb || !d_alpha || !params || !view_frame || !background) return fail(1, "ps_backward: NULL buffer");
+    if (VN == 0 || sv->M == 0 || (size_t)g.H * g.W == 0) { // nothing was rendered: the gradient is zero
+        if (!peers) PS_CUDA(cudaMemsetAsync(d_params, 0, n_out * sizeof(float), s));
+        return 0;
+    }
+    if (!sv->blast || !sv->t_pen || !sv->frame_off) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
+    if (!d_rgb || !d_alpha || !params || !background) return fail(1, "ps_backward: NULL buffer");
+    if (peers && !owner) return fail(1, "ps_backward_peer: NULL frame_owner");
     float *acc = nullptr;
     PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE, s));
     int rc = 0;
@@ -314,12 +409,28 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
         { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc, s); }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
-        { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, view_frame, viewmats, Ks, sv->t, acc, d_params, s); }
+        { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, sv->frame_off, sv->frame_views, viewmats, Ks, sv->t, acc, d_params, peers, owner, s); }
         if (n < 0) { rc = fail(3, "ps_backward: project_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
     } while (0);
     dev_free(acc, s);
     return rc;
+}
+
+int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *view_frame, const float *viewmats,
+                const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
+                void *stream)
+{
+    (void)view_frame; // the forward saved the views of every frame
+    return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, d_params, nullptr, nullptr, stream);
+}
+
+int ps_backward_peer(ps_ctx *ctx, ps_saved *sv, const float *params, const float *viewmats, const float *Ks,
+                     const float *background, const float *d_rgb, const float *d_alpha, float *const *d_params_ranks,
+                     const int32_t *frame_owner, void *stream)
+{
+    if (!d_params_ranks) return fail(1, "ps_backward_peer: NULL d_params_ranks");
+    return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, nullptr, d_params_ranks, frame_owner, stream);
 }
 
 int ps_saved_info_get(const ps_saved *sv, ps_saved_info *out)

@@ -49,8 +49,13 @@ struct PsLists {
 // every launcher returns the number of kernels it launched (for gpu_launches) or -1 on error
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
                       const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s);
-int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
-                          const float *Ks, const PsTable &t, const float *acc, float *d_params, cudaStream_t s);
+// view_frame [V] -> CSR (frame_off [F+1], frame_views [V]); cursor [F] is scratch
+int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t *frame_off, int32_t *cursor,
+                        int32_t *frame_views, cudaStream_t s);
+// peers == nullptr: rows stored into d_params; else rows added into peers[owner[frame]] (device array of base pointers)
+int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *frame_off, const int32_t *frame_views,
+                          const float *viewmats, const float *Ks, const PsTable &t, const float *acc, float *d_params,
+                          float *const *peers, const int32_t *owner, cudaStream_t s);
 
 // binning (ps_bin.cu)
 size_t ps_rank_scratch_elems(const PsGeometry &g); // uint32 elements of global scratch the ranking needs (0 if it fits smem)

@@ -2,7 +2,9 @@
 //   project   : fused activation + EWA projection (3D) / activation + extent (2D) -> splat records,
 //               tile rectangle, tiles-touched, and the per-(view,tile) list lengths
 //               (CTA histogram in shared memory, one global atomic per (CTA, tile))  [HBM-bound]
-//   project_bwd : chain rule back to the raw rows, atomics into d_params[frame]       [HBM-bound]
+//   project_bwd : chain rule back to the raw rows; one thread per (frame, Gaussian) sums the frame's views in
+//                 registers and writes the row once -- into d_params, or (K8') with red.global.add into the
+//                 owner rank's d_params over NVLink when a frame's cameras are split across GPUs [HBM-bound]
 // Replaces: adapter activations src/gaussian_renderer.py:183-193 / :314-323 and gsplat's
 // fully_fused_projection + isect_tiles (absent from the reference tree).
 #include "ps_contract.cuh"
@@ -90,64 +92,40 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
 // Backward of the projection / activations. acc row = 9 sums from the rasterizer backward:
 //   3D: v_rgb(3), v_A, v_B, v_C, v_x, v_y, v_opacity        2D: v_rgb(3), sum d_dxr, sum d_dyr, d_theta, d_iax, d_iay, sum G_q
 // ------------------------------------------------------------------------------------------
+// Gradient of one (view, Gaussian) pair w.r.t. its raw parameter row, added into out[P].
+//   r   the raw row, cam  viewmat[16] | K[9] of the view (3D), a  the nine sums of the rasterizer backward
 template <int MODE>
-__global__ void __launch_bounds__(PS_PROJ_BLOCK)
-project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ view_frame,
-                   const float *__restrict__ viewmats, const float *__restrict__ Ks, PsTable t,
-                   const float *__restrict__ acc, float *__restrict__ d_params)
+__device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTable &t, size_t idx, const float *r,
+                                                const float *cam, const float (&a)[9],
+                                                float (&out)[(MODE == PS_MODE_3D) ? 14 : 9])
 {
     constexpr int P = (MODE == PS_MODE_3D) ? 14 : 9;
-    __shared__ float s_cam[25];
-    const int v = blockIdx.y;
-    if (MODE == PS_MODE_3D && threadIdx.x < 25)
-        s_cam[threadIdx.x] = threadIdx.x < 16 ? viewmats[(size_t)v * 16 + threadIdx.x] : Ks[(size_t)v * 9 + threadIdx.x - 16];
-    __syncthreads();
-    const int gi = blockIdx.x * PS_PROJ_BLOCK + threadIdx.x;
-    if (gi >= g.N) return;
-    const size_t idx = (size_t)v * g.N + gi;
-    if (t.tiles_touched[idx] == 0) return; // never listed -> no contribution -> zero gradient
-    const float4 *a4 = reinterpret_cast<const float4 *>(acc + idx * PS_ACC_STRIDE);
-    const float4 q0 = a4[0], q1 = a4[1], q2 = a4[2];
-    const float a[9] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x };
-    {   // listed but never a contributor (hidden behind saturated pixels): every gradient is exactly zero
-        bool any = false;
+    float o[P];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) any = any || (a[k] != 0.0f);
-        if (!any) return;
-    }
-    const int frame = view_frame[v];
-    const float *row = params + ((size_t)frame * g.N + gi) * P;
-    float *d = d_params + ((size_t)frame * g.N + gi) * P;
-    float r[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) r[k] = __ldg(row + k);
-    float out[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) out[k] = 0.0f;
-
+    for (int k = 0; k < P; ++k) o[k] = 0.0f;
     if (MODE == PS_MODE_2D) {
         const float4 r1 = *PS_REC(t, idx, 1);
         const float cs = r1.x, sn = r1.y, iax = r1.z, iay = r1.w;
-        const float o = PS_REC(t, idx, 0)->w;
+        const float op = PS_REC(t, idx, 0)->w;
         const float sx = psm_exp(r[2]), sy = psm_exp(r[3]);
-        out[0] = -(cs * a[3] - sn * a[4]);
-        out[1] = -(sn * a[3] + cs * a[4]);
-        out[2] = a[6] * (-(iax * iax) * 4.0f * sx * sx);
-        out[3] = a[7] * (-(iay * iay) * 4.0f * sy * sy);
-        out[4] = a[5];
+        o[0] = -(cs * a[3] - sn * a[4]);
+        o[1] = -(sn * a[3] + cs * a[4]);
+        o[2] = a[6] * (-(iax * iax) * 4.0f * sx * sx);
+        o[3] = a[7] * (-(iay * iay) * 4.0f * sy * sy);
+        o[4] = a[5];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) out[5 + k] = (r[5 + k] >= 0.0f && r[5 + k] <= 1.0f) ? a[k] : 0.0f;
-        out[8] = -a[8] * (1.0f - o);
+        for (int k = 0; k < 3; ++k) o[5 + k] = (r[5 + k] >= 0.0f && r[5 + k] <= 1.0f) ? a[k] : 0.0f;
+        o[8] = -a[8] * (1.0f - op);
     } else {
         PsRecord rec;
         PsProj3dAux x;
-        const int ok = ps_project3d(r, s_cam, s_cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x);
+        const int ok = ps_project3d(r, cam, cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) out[10 + k] = (r[10 + k] >= 0.0f && r[10 + k] <= 1.0f) ? a[k] : 0.0f;
-        const float o = rec.r1[3];
-        out[13] = a[8] * o * (1.0f - o);
+        for (int k = 0; k < 3; ++k) o[10 + k] = (r[10 + k] >= 0.0f && r[10 + k] <= 1.0f) ? a[k] : 0.0f;
+        const float op = rec.r1[3];
+        o[13] = a[8] * op * (1.0f - op);
         if (ok) {
-            const float *V = s_cam, *K = s_cam + 16;
+            const float *V = cam, *K = cam + 16;
             const float fx = K[0], fy = K[4];
             // conic = inverse(cov2d):  G_S = -X G_X X,  G_X = [[vA, vB/2], [vB/2, vC]]
             const float XA = rec.r1[0], XB = rec.r1[1], XC = rec.r1[2];
@@ -187,7 +165,7 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
             if (!x.clampy) { vpc1 += -fy * rz2 * GJ[1][2]; vpc2 += 2.0f * fy * x.ty * rz3 * GJ[1][2]; }
             else { vpc2 += fy * x.ty * rz3 * GJ[1][2]; }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) out[c] = V[c] * vpc0 + V[4 + c] * vpc1 + V[8 + c] * vpc2;
+            for (int c = 0; c < 3; ++c) o[c] = V[c] * vpc0 + V[4 + c] * vpc1 + V[8 + c] * vpc2;
             // G_Sigma = Rwc^T GSc Rwc
             float Tm[3][3], GS[3][3];
 #pragma unroll
@@ -212,7 +190,7 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
                 float vs = 0.0f;
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr) { GR[rr][c] = GM[rr][c] * x.s[c]; vs += x.R[3 * rr + c] * GM[rr][c]; }
-                out[3 + c] = vs * x.s[c];
+                o[3 + c] = vs * x.s[c];
             }
             const float w = x.qh[0], qx = x.qh[1], qy = x.qh[2], qz = x.qh[3];
             float vq[4];
@@ -230,13 +208,147 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
             for (int k = 0; k < 4; ++k) {
                 float g0 = va[k] / den;
                 if (n > 0.0f) g0 -= dq / (den * den) * (r[6 + k] / n);
-                out[6 + k] = g0;
+                o[6 + k] = g0;
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < P; ++k)
-        if (out[k] != 0.0f) atomicAdd(d + k, out[k]);
+    for (int k = 0; k < P; ++k) out[k] += o[k];
+}
+
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// One thread per (frame, Gaussian): loops over the views of the frame (CSR frame_off / frame_views built by the
+// forward), sums their gradients in registers and writes the row ONCE.
+//   peers == nullptr : plain stores into d_params (no atomics, no memset: rows without gradient get zeros)
+//   peers != nullptr : K8' fused gradient reduce -- the row is added with red.global.add.v2.f32 straight into the
+//                      d_params buffer of the rank that owns the frame (peers[owner[frame]]: local memory, or a
+//                      peer GPU's over NVLink), so the cross-GPU sum needs no separate collective or staging copy.
+//                      The owners zero their buffers and all ranks meet at a barrier before and after (host side).
+template <int MODE>
+__global__ void __launch_bounds__(PS_PROJ_BLOCK)
+project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ frame_off,
+                   const int32_t *__restrict__ frame_views, const float *__restrict__ viewmats,
+                   const float *__restrict__ Ks, PsTable t, const float *__restrict__ acc, float *__restrict__ d_params,
+                   float *const *__restrict__ peers, const int32_t *__restrict__ owner)
+{
+    constexpr int P = (MODE == PS_MODE_3D) ? 14 : 9;
+    __shared__ float s_cam[25];
+    const int frame = blockIdx.y;
+    const int gi = blockIdx.x * PS_PROJ_BLOCK + threadIdx.x;
+    const bool live = gi < g.N;
+    float r[P], out[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) { r[k] = 0.0f; out[k] = 0.0f; }
+    if (live) {
+        const float *row = params + ((size_t)frame * g.N + gi) * P;
+#pragma unroll
+        for (int k = 0; k < P; ++k) r[k] = __ldg(row + k);
+    }
+    const int j0 = frame_off[frame], j1 = frame_off[frame + 1];
+    for (int j = j0; j < j1; ++j) {
+        const int v = frame_views[j];
+        if (MODE == PS_MODE_3D) {
+            __syncthreads();
+            if (threadIdx.x < 25)
+                s_cam[threadIdx.x] = threadIdx.x < 16 ? viewmats[(size_t)v * 16 + threadIdx.x] : Ks[(size_t)v * 9 + threadIdx.x - 16];
+            __syncthreads();
+        }
+        if (!live) continue;
+        const size_t idx = (size_t)v * g.N + gi;
+        if (t.tiles_touched[idx] == 0) continue; // never listed -> no contribution -> zero gradient
+        const float4 *a4 = reinterpret_cast<const float4 *>(acc + idx * PS_ACC_STRIDE);
+        const float4 q0 = a4[0], q1 = a4[1], q2 = a4[2];
+        const float a[9] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x };
+        bool any = false; // listed but never a contributor (hidden behind saturated pixels): gradient exactly zero
+#pragma unroll
+        for (int k = 0; k < 9; ++k) any = any || (a[k] != 0.0f);
+        if (!any) continue;
+        project_bwd_row<MODE>(g, t, idx, r, s_cam, a, out);
+    }
+    if (!live) return;
+    const size_t off = ((size_t)frame * g.N + gi) * P;
+    if (peers == nullptr) {
+        float *d = d_params + off;
+        if (MODE == PS_MODE_3D) { // 56-byte rows: 8-byte aligned
+#pragma unroll
+            for (int k = 0; k < P; k += 2) *reinterpret_cast<float2 *>(d + k) = make_float2(out[k], out[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k) d[k] = out[k];
+        }
+    } else {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < P; ++k) any = any || (out[k] != 0.0f);
+        if (!any) return;
+        float *d = peers[owner[frame]] + off;
+        if (MODE == PS_MODE_3D) {
+#pragma unroll
+            for (int k = 0; k < P; k += 2) red_add_v2(d + k, out[k], out[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k) atomicAdd(d + k, out[k]);
+        }
+    }
+}
+
+// view -> frame map to CSR (views of every frame): one CTA; order inside a frame is arbitrary
+__global__ void __launch_bounds__(1024)
+frame_csr_kernel(const int32_t *__restrict__ view_frame, int V, int F, int32_t *__restrict__ frame_off,
+                 int32_t *__restrict__ cursor, int32_t *__restrict__ frame_views)
+{
+    __shared__ int s_carry;
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int f = tid; f <= F; f += 1024) frame_off[f] = 0;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int v = tid; v < V; v += 1024) {
+        const int f = view_frame[v];
+        if (f >= 0 && f < F) atomicAdd(&frame_off[f + 1], 1);
+    }
+    __syncthreads();
+    // inclusive scan of frame_off[1..F] in chunks of 1024
+    for (int c0 = 1; c0 <= F; c0 += 1024) {
+        const int i = c0 + tid;
+        const int val = i <= F ? frame_off[i] : 0;
+        int incl = val;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = s_warp[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += n;
+            }
+            s_warp[lane] = wi - w;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        if (i <= F) {
+            const int res = s_carry + s_warp[wid] + incl;
+            frame_off[i] = res;
+            cursor[i - 1] = res - val; // start of frame i-1
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += s_warp[32];
+        __syncthreads();
+    }
+    for (int v = tid; v < V; v += 1024) {
+        const int f = view_frame[v];
+        if (f >= 0 && f < F) frame_views[atomicAdd(&cursor[f], 1)] = v;
+    }
 }
 
 __global__ void math_probe_kernel(const float *x, int n, float *y)
@@ -268,14 +380,23 @@ int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *v
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
-                          const float *Ks, const PsTable &t, const float *acc, float *d_params, cudaStream_t s)
+int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t *frame_off, int32_t *cursor,
+                        int32_t *frame_views, cudaStream_t s)
 {
-    dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
+    frame_csr_kernel<<<1, 1024, 0, s>>>(view_frame, g.V, g.F, frame_off, cursor, frame_views);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *frame_off, const int32_t *frame_views,
+                          const float *viewmats, const float *Ks, const PsTable &t, const float *acc, float *d_params,
+                          float *const *peers, const int32_t *owner, cudaStream_t s)
+{
+    if (g.N == 0 || g.F == 0) return 0;
+    dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.F);
     if (g.mode == PS_MODE_3D)
-        project_bwd_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, view_frame, viewmats, Ks, t, acc, d_params);
+        project_bwd_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, owner);
     else
-        project_bwd_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, view_frame, viewmats, Ks, t, acc, d_params);
+        project_bwd_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, owner);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

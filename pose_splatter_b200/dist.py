@@ -40,6 +40,36 @@ def reduce_frame_grads(d_params: torch.Tensor, group=None) -> torch.Tensor:
     return d_params
 
 
+class PeerGradBuffers:
+    """Fused cross-GPU gradient sum (K8'): one d_params buffer [F,N,P] per rank, allocated as symmetric memory and
+    mapped into every process of the node (NVLink peer access).  With it the projection-backward kernel adds each
+    finished row straight into the buffer of the rank that owns the frame (ps_backward_peer) -- no all-reduce, no
+    staging copy.  frame f is owned by rank `f % world`.
+
+        bufs = PeerGradBuffers((F, N, P), device)
+        bufs.begin()                      # zero own buffer, barrier
+        batched.backward_peer_raw(saved, params, viewmats, Ks, bg, d_rgb, d_alpha, bufs.rank_ptrs, bufs.frame_owner)
+        bufs.end()                        # barrier: bufs.buf[f] is complete for every owned frame f
+    """
+
+    def __init__(self, shape, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buf = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.rank_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.frame_owner = (torch.arange(shape[0], device=device) % self.world).to(torch.int32)
+        self.owned = [f for f in range(shape[0]) if f % self.world == self.rank]
+
+    def begin(self):
+        self.buf.zero_()
+        self.handle.barrier()
+
+    def end(self):
+        self.handle.barrier()
+
+
 def max_over_ranks(value: float, device) -> float:
     """Timing rule: a multi-GPU number is the max over ranks."""
     t = torch.tensor([value], dtype=torch.float64, device=device)
