@@ -29,6 +29,9 @@ extern "C" {
 #define PS_FLAG_SAVE_FOR_BACKWARD 1 /* keep the state ps_backward needs                        */
 #define PS_FLAG_KEEP_BINNING 2      /* also materialise the sorted int64 keys and keep last ids for the debug taps */
 #define PS_FLAG_RASTER_STATS 4      /* count (pixel, Gaussian) pairs in the forward rasterizer (bench only) */
+#define PS_FLAG_ACTIVATED_INPUTS 8  /* 3D rows = means | scales | quats | colours | opacity as gsplat's rasterization()
+                                       takes them (src/model.py:342-361): no exp / q/(|q|+1e-8) / clamp / sigmoid, and
+                                       the gradient is w.r.t. those values                                          */
 
 /* stages timed by ps_ctx_set_profiling (CUDA events on the launching stream) */
 #define PS_STAGE_PROJECT 0     /* activations + projection + per-(view,tile) list lengths            */

@@ -20,7 +20,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB = None
 
 TILE = 16
-DEFAULTS_3D = dict(near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3)
+DEFAULTS_3D = dict(near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, activated=False)
 
 
 def build(force: bool = False) -> Path:
@@ -88,7 +88,8 @@ def project(mode, params, W, H, viewmat=None, K=None, **opts):
         lib().ora3d_project(_f(params), N, _f(V), _f(Kf), W, H,
                             ctypes.c_float(o["near_plane"]), ctypes.c_float(o["far_plane"]),
                             ctypes.c_float(o["radius_clip"]), ctypes.c_float(o["eps2d"]),
-                            _f(geom), _f(rgb), _i(rect), _i(trect), _p(low, ctypes.c_uint32), _i(tiles))
+                            _f(geom), _f(rgb), _i(rect), _i(trect), _p(low, ctypes.c_uint32), _i(tiles),
+                            ctypes.c_int(int(bool(o["activated"]))))
     else:
         lib().ora2d_project(_f(params), N, W, H, _f(geom), _f(rgb), _i(rect), _i(trect),
                             _p(low, ctypes.c_uint32), _i(tiles))
@@ -162,7 +163,7 @@ def project_bwd(mode, params, tab, acc, W, H, viewmat=None, K=None, d_params=Non
         lib().ora3d_project_bwd(_f(params), N, _f(V), _f(Kf), W, H,
                                 ctypes.c_float(o["near_plane"]), ctypes.c_float(o["far_plane"]),
                                 ctypes.c_float(o["radius_clip"]), ctypes.c_float(o["eps2d"]),
-                                acc.ctypes.data_as(dp), d_params.ctypes.data_as(dp))
+                                acc.ctypes.data_as(dp), d_params.ctypes.data_as(dp), ctypes.c_int(int(bool(o["activated"]))))
     else:
         lib().ora2d_project_bwd(_f(params), N, _f(tab["geom"]), acc.ctypes.data_as(dp), d_params.ctypes.data_as(dp))
     return d_params

@@ -172,18 +172,21 @@ typedef struct {
 static int project3d_one(const float *row, const float *V, const float *K, int W, int H,
                          float near_plane, float far_plane, float radius_clip, float eps2d,
                          float *geom, float *rgb, int *rect, int *tile_rect, uint32_t *low,
-                         ora_proj3d_tmp *t)
+                         ora_proj3d_tmp *t, int activated)
 {
-    /* adapter: src/gaussian_renderer.py:183-193 */
-    for (int k = 0; k < 3; ++k) t->s[k] = d_exp(row[3 + k]);
+    /* adapter: src/gaussian_renderer.py:183-193.  activated != 0: the row already holds scales, quaternion,
+     * colours and opacity as gsplat.rendering.rasterization receives them (src/model.py:342-361): no exp, no
+     * q/(|q|+1e-8), no clamp, no sigmoid (gsplat still normalises the quaternion itself) */
+    for (int k = 0; k < 3; ++k) t->s[k] = activated ? row[3 + k] : d_exp(row[3 + k]);
     float qw = row[6], qx = row[7], qy = row[8], qz = row[9];
     float n2 = fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, qw * qw)));
     float qn = sqrtf(n2);
     t->qn_raw = qn;
     float den = qn + 1e-8f;
-    t->qa[0] = qw / den; t->qa[1] = qx / den; t->qa[2] = qy / den; t->qa[3] = qz / den;
-    for (int k = 0; k < 3; ++k) rgb[k] = fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
-    float o = d_sigmoid(row[13]);
+    if (activated) { t->qa[0] = qw; t->qa[1] = qx; t->qa[2] = qy; t->qa[3] = qz; }
+    else { t->qa[0] = qw / den; t->qa[1] = qx / den; t->qa[2] = qy / den; t->qa[3] = qz / den; }
+    for (int k = 0; k < 3; ++k) rgb[k] = activated ? row[10 + k] : fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
+    float o = activated ? row[13] : d_sigmoid(row[13]);
 
     for (int k = 0; k < 8; ++k) geom[k] = 0.0f;
     rect[0] = rect[1] = rect[2] = rect[3] = 0;
@@ -302,13 +305,13 @@ static int project3d_one(const float *row, const float *V, const float *K, int W
 /* params [N,14] row-major; V [16]; K [9].  Outputs per Gaussian (see table comment). */
 void ora3d_project(const float *params, int N, const float *V, const float *K, int W, int H,
                    float near_plane, float far_plane, float radius_clip, float eps2d,
-                   float *geom, float *rgb, int *rect, int *tile_rect, uint32_t *low, int *tiles_touched)
+                   float *geom, float *rgb, int *rect, int *tile_rect, uint32_t *low, int *tiles_touched, int activated)
 {
     ora_proj3d_tmp t;
     for (int i = 0; i < N; ++i) {
         project3d_one(params + 14 * (size_t)i, V, K, W, H, near_plane, far_plane, radius_clip, eps2d,
                       geom + 8 * (size_t)i, rgb + 3 * (size_t)i, rect + 4 * (size_t)i,
-                      tile_rect + 4 * (size_t)i, low + i, &t);
+                      tile_rect + 4 * (size_t)i, low + i, &t, activated);
         const int *tr = tile_rect + 4 * (size_t)i;
         tiles_touched[i] = (tr[2] - tr[0]) * (tr[3] - tr[1]);
     }
@@ -684,7 +687,7 @@ void ora2d_project_bwd(const float *params, int N, const float *geom, const doub
 /* gsplat fully_fused_projection backward + adapter activations, in double from fp32 saves */
 void ora3d_project_bwd(const float *params, int N, const float *V, const float *K, int W, int H,
                        float near_plane, float far_plane, float radius_clip, float eps2d,
-                       const double *acc, double *d_params)
+                       const double *acc, double *d_params, int activated)
 {
     float geom[8], rgb[3]; int rect[4], trect[4]; uint32_t low;
     ora_proj3d_tmp t;
@@ -694,11 +697,11 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         double *d = d_params + 14 * (size_t)i;
         /* colour and opacity do not depend on visibility of the projection */
         int ok = project3d_one(row, V, K, W, H, near_plane, far_plane, radius_clip, eps2d,
-                               geom, rgb, rect, trect, &low, &t);
+                               geom, rgb, rect, trect, &low, &t, activated);
         for (int k = 0; k < 3; ++k)
-            if (row[10 + k] >= 0.0f && row[10 + k] <= 1.0f) d[10 + k] += a[k];
+            if (activated || (row[10 + k] >= 0.0f && row[10 + k] <= 1.0f)) d[10 + k] += a[k];
         double o = geom[5];
-        d[13] += a[8] * o * (1.0 - o);
+        d[13] += activated ? a[8] : a[8] * o * (1.0 - o);
         if (!ok) continue;
         double fx = K[0], fy = K[4];
         /* conic = inverse(cov2d): G_S = -X G_X X with G_X = [[vA, vB/2],[vB/2, vC]] */
@@ -769,7 +772,7 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         double GR[3][3], vs[3] = { 0, 0, 0 };
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) { GR[r][c] = GM[r][c] * t.s[c]; vs[c] += Rq[r][c] * GM[r][c]; }
-        for (int k = 0; k < 3; ++k) d[3 + k] += vs[k] * t.s[k]; /* scale = exp(log_scale) */
+        for (int k = 0; k < 3; ++k) d[3 + k] += activated ? vs[k] : vs[k] * t.s[k]; /* scale = exp(log_scale) */
         /* R(qh) */
         double w = t.qh[0], qx = t.qh[1], qy = t.qh[2], qz = t.qh[3];
         double vq[4];
@@ -782,6 +785,7 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         double va[4];
         double qhv[4] = { w, qx, qy, qz };
         for (int k = 0; k < 4; ++k) va[k] = (vq[k] - dot * qhv[k]) * t.inv2;
+        if (activated) { for (int k = 0; k < 4; ++k) d[6 + k] += va[k]; continue; }
         /* qa = q / (|q| + 1e-8) */
         double n = t.qn_raw, den = n + 1e-8;
         double dq = va[0] * row[6] + va[1] * row[7] + va[2] * row[8] + va[3] * row[9];

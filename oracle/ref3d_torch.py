@@ -22,12 +22,15 @@ def quat_to_rotmat(q):
         2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1).view(-1, 3, 3)
 
 
-def project(params, viewmat, K, width, height, near=0.01, far=1e10, eps2d=0.3, radius_clip=0.0):
+def project(params, viewmat, K, width, height, near=0.01, far=1e10, eps2d=0.3, radius_clip=0.0, activated=False):
     means, log_s, quats, cols, logit = params[:, 0:3], params[:, 3:6], params[:, 6:10], params[:, 10:13], params[:, 13]
-    scales = log_s.exp()
-    quats = quats / (quats.norm(dim=-1, keepdim=True) + 1e-8)
-    cols = cols.clamp(0.0, 1.0)
-    opac = logit.sigmoid()
+    if activated:  # values as gsplat.rendering.rasterization receives them (src/model.py:342-361)
+        scales, opac = log_s, logit
+    else:          # adapter activations, src/gaussian_renderer.py:183-193
+        scales = log_s.exp()
+        quats = quats / (quats.norm(dim=-1, keepdim=True) + 1e-8)
+        cols = cols.clamp(0.0, 1.0)
+        opac = logit.sigmoid()
     qh = quats / quats.norm(dim=-1, keepdim=True)
     R = quat_to_rotmat(qh)
     M = R * scales[:, None, :]

@@ -21,6 +21,7 @@ EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy",
 
 STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd", "blocks")
 FLAG_RASTER_STATS = 4
+FLAG_ACTIVATED_INPUTS = 8
 
 
 class RenderDesc(ctypes.Structure):

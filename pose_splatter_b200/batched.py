@@ -15,12 +15,14 @@ import torch
 
 from . import _capi
 
-DEFAULTS_3D = dict(near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3)
+DEFAULTS_3D = dict(near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, activated=False)
 
 
 def _desc(mode, width, height, n_frames, n_gauss, n_views, flags, opts):
     o = dict(DEFAULTS_3D)
     o.update(opts or {})
+    if o["activated"]:
+        flags |= _capi.FLAG_ACTIVATED_INPUTS
     return _capi.RenderDesc(_capi.MODE_3D if mode == "3d" else _capi.MODE_2D, int(width), int(height), int(n_frames),
                             int(n_gauss), int(n_views), int(flags), o["near_plane"], o["far_plane"], o["radius_clip"],
                             o["eps2d"])

@@ -285,6 +285,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
     g.view_bits = 0;
     while ((1 << g.view_bits) < g.V) ++g.view_bits;
     g.near_plane = d->near_plane; g.far_plane = d->far_plane; g.radius_clip = d->radius_clip; g.eps2d = d->eps2d;
+    g.activated = (d->flags & PS_FLAG_ACTIVATED_INPUTS) != 0 && d->mode == PS_MODE_3D;
 
     int rc = 0;
     uint32_t *rank_scratch = nullptr;

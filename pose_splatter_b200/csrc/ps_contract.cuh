@@ -160,20 +160,25 @@ PS_HD void ps_record_clear(PsRecord *rec)
 }
 
 // Adapter activations + EWA projection of one Gaussian for one camera. Returns 1 if visible.
+// activated != 0: the row already holds scales / quaternion / colours / opacity as gsplat's rasterization() takes
+// them (the legacy PoseSplatter.splat call, src/model.py:342-361): no exp, no q/(|q|+1e-8), no clamp, no sigmoid.
 PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, int H, float near_plane,
-                       float far_plane, float radius_clip, float eps2d, PsRecord *rec, PsProj3dAux *t)
+                       float far_plane, float radius_clip, float eps2d, PsRecord *rec, PsProj3dAux *t, int activated = 0)
 {
     ps_record_clear(rec);
-    for (int k = 0; k < 3; ++k) t->s[k] = psm_exp(row[3 + k]);
+    for (int k = 0; k < 3; ++k) t->s[k] = activated ? row[3 + k] : psm_exp(row[3 + k]);
     float qw = row[6], qx = row[7], qy = row[8], qz = row[9];
     float n2 = psm_fma(qz, qz, psm_fma(qy, qy, psm_fma(qx, qx, psm_mul(qw, qw))));
     float qn = psm_sqrt(n2);
     t->qn_raw = qn;
     float den = psm_add(qn, 1e-8f);
-    t->qa[0] = psm_div(qw, den); t->qa[1] = psm_div(qx, den);
-    t->qa[2] = psm_div(qy, den); t->qa[3] = psm_div(qz, den);
-    for (int k = 0; k < 3; ++k) rec->r2[k] = fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
-    float o = psm_sigmoid(row[13]);
+    if (activated) { t->qa[0] = qw; t->qa[1] = qx; t->qa[2] = qy; t->qa[3] = qz; }
+    else {
+        t->qa[0] = psm_div(qw, den); t->qa[1] = psm_div(qx, den);
+        t->qa[2] = psm_div(qy, den); t->qa[3] = psm_div(qz, den);
+    }
+    for (int k = 0; k < 3; ++k) rec->r2[k] = activated ? row[10 + k] : fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
+    float o = activated ? row[13] : psm_sigmoid(row[13]);
     rec->r1[3] = o;
 
     float a0 = t->qa[0], a1 = t->qa[1], a2 = t->qa[2], a3 = t->qa[3];

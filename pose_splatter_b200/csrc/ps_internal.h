@@ -19,6 +19,7 @@ struct PsGeometry {
     int tiles_x, tiles_y, n_tiles;
     int tile_bits, view_bits;
     float near_plane, far_plane, radius_clip, eps2d;
+    int activated; // 3D rows hold activated values (PS_FLAG_ACTIVATED_INPUTS)
 };
 
 // per-(view,Gaussian) table produced by the projection stage

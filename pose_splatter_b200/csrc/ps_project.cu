@@ -53,7 +53,7 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
         if (MODE == PS_MODE_3D) {
             PsProj3dAux aux;
             ps_project3d(s_rows + threadIdx.x * P, s_cam, s_cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip,
-                         g.eps2d, &rec, &aux);
+                         g.eps2d, &rec, &aux, g.activated);
         } else {
             ps_project2d(s_rows + threadIdx.x * P, (uint32_t)(g0 + threadIdx.x), g.W, g.H, &rec);
         }
@@ -119,11 +119,12 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
     } else {
         PsRecord rec;
         PsProj3dAux x;
-        const int ok = ps_project3d(r, cam, cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x);
+        const int ok = ps_project3d(r, cam, cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x,
+                                    g.activated);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o[10 + k] = (r[10 + k] >= 0.0f && r[10 + k] <= 1.0f) ? a[k] : 0.0f;
+        for (int k = 0; k < 3; ++k) o[10 + k] = (g.activated || (r[10 + k] >= 0.0f && r[10 + k] <= 1.0f)) ? a[k] : 0.0f;
         const float op = rec.r1[3];
-        o[13] = a[8] * op * (1.0f - op);
+        o[13] = g.activated ? a[8] : a[8] * op * (1.0f - op);
         if (ok) {
             const float *V = cam, *K = cam + 16;
             const float fx = K[0], fy = K[4];
@@ -190,7 +191,7 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
                 float vs = 0.0f;
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr) { GR[rr][c] = GM[rr][c] * x.s[c]; vs += x.R[3 * rr + c] * GM[rr][c]; }
-                o[3 + c] = vs * x.s[c];
+                o[3 + c] = g.activated ? vs : vs * x.s[c];
             }
             const float w = x.qh[0], qx = x.qh[1], qy = x.qh[2], qz = x.qh[3];
             float vq[4];
@@ -202,13 +203,18 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
             float va[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) va[k] = (vq[k] - dot * x.qh[k]) * x.inv2;
-            const float n = x.qn_raw, den = n + 1e-8f;
-            const float dq = va[0] * r[6] + va[1] * r[7] + va[2] * r[8] + va[3] * r[9];
+            if (g.activated) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float g0 = va[k] / den;
-                if (n > 0.0f) g0 -= dq / (den * den) * (r[6 + k] / n);
-                o[6 + k] = g0;
+                for (int k = 0; k < 4; ++k) o[6 + k] = va[k];
+            } else {
+                const float n = x.qn_raw, den = n + 1e-8f;
+                const float dq = va[0] * r[6] + va[1] * r[7] + va[2] * r[8] + va[3] * r[9];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float g0 = va[k] / den;
+                    if (n > 0.0f) g0 -= dq / (den * den) * (r[6 + k] / n);
+                    o[6 + k] = g0;
+                }
             }
         }
     }

@@ -37,7 +37,7 @@ def host_contract():
     return ctypes.CDLL(str(so))
 
 
-def hc_project(mode, params, W, H, V=None, K=None, near=0.01, far=1e10, clip=0.0, eps=0.3):
+def hc_project(mode, params, W, H, V=None, K=None, near=0.01, far=1e10, clip=0.0, eps=0.3, activated=False):
     L = host_contract()
     fp, ip, up = (ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32))
     params = np.ascontiguousarray(params, np.float32)
@@ -49,7 +49,7 @@ def hc_project(mode, params, W, H, V=None, K=None, near=0.01, far=1e10, clip=0.0
     K = np.zeros(9, np.float32) if K is None else np.ascontiguousarray(K, np.float32).reshape(9)
     L.hc_project(3 if mode == "3d" else 2, params.ctypes.data_as(fp), N, V.ctypes.data_as(fp), K.ctypes.data_as(fp),
                  W, H, ctypes.c_float(near), ctypes.c_float(far), ctypes.c_float(clip), ctypes.c_float(eps),
-                 r.ctypes.data_as(fp), tile.ctypes.data_as(ip), low.ctypes.data_as(up))
+                 r.ctypes.data_as(fp), tile.ctypes.data_as(ip), low.ctypes.data_as(up), int(bool(activated)))
     return r, tile, low
 
 

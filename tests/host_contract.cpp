@@ -15,12 +15,12 @@ void hc_math_probe(const float *x, int n, float *o_exp, float *o_log, float *o_s
 }
 // records out: r [N,12] floats, tile [N,4] ints, low [N]
 void hc_project(int mode, const float *params, int N, const float *V, const float *K, int W, int H, float near_plane,
-                float far_plane, float radius_clip, float eps2d, float *r, int *tile, uint32_t *low)
+                float far_plane, float radius_clip, float eps2d, float *r, int *tile, uint32_t *low, int activated)
 {
     PsRecord rec;
     PsProj3dAux aux;
     for (int i = 0; i < N; ++i) {
-        if (mode == 3) ps_project3d(params + 14 * (size_t)i, V, K, W, H, near_plane, far_plane, radius_clip, eps2d, &rec, &aux);
+        if (mode == 3) ps_project3d(params + 14 * (size_t)i, V, K, W, H, near_plane, far_plane, radius_clip, eps2d, &rec, &aux, activated);
         else ps_project2d(params + 9 * (size_t)i, (uint32_t)i, W, H, &rec);
         for (int k = 0; k < 4; ++k) {
             r[12 * (size_t)i + k] = rec.r0[k]; r[12 * (size_t)i + 4 + k] = rec.r1[k]; r[12 * (size_t)i + 8 + k] = rec.r2[k];

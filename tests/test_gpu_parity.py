@@ -263,3 +263,15 @@ def test_large_image_global_histogram_path(mode):
                        torch.log(torch.rand(N, 2, generator=g) * 6 + 0.5), torch.rand(N, 1, generator=g) * 6.28,
                        torch.rand(N, 3, generator=g), torch.randn(N, 1, generator=g)], 1)
         _compare("2d", p[None], torch.zeros(1, dtype=torch.int32), W, H, (1.0, 1.0, 1.0))
+
+
+def test_3d_activated_inputs_bit_exact():
+    """PS_FLAG_ACTIVATED_INPUTS (the gsplat.rendering shim path): every bit-exact stage and the gradients."""
+    _, _, _, synth = _mods()
+    vm, Ks = synth.ring_cameras(6, ds=8.0)
+    p = synth.gaussians_3d(900, 6)
+    p[:, 3:6] = torch.exp(p[:, 3:6] + 0.5)
+    p[:, 10:13] = p[:, 10:13] * 1.2
+    p[:, 13] = torch.sigmoid(p[:, 13])
+    _compare("3d", p[None], torch.zeros(2, dtype=torch.int32), 144, 128, (0.0, 0.0, 0.0), vm[:2], Ks[:2],
+             radius_clip=2.0, activated=True)

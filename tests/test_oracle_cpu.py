@@ -218,3 +218,42 @@ def test_gradients_are_linear_in_the_cotangents():
     g1, g2 = grad(w1[0].numpy(), a1[0].numpy()), grad(w2[0].numpy(), a2[0].numpy())
     g12 = grad((2 * w1[0] - 0.5 * w2[0]).numpy(), (2 * a1[0] - 0.5 * a2[0]).numpy())
     assert column_rel_err(g12, 2 * g1 - 0.5 * g2).max() < 1e-4
+
+
+def _activated_rows(N, seed):
+    """[N,14] rows holding ACTIVATED values (scales, raw quaternion, colours in [0,1.2], opacity) like the legacy
+    PoseSplatter.splat call hands to gsplat (src/model.py:300-317,342-361)."""
+    p = synth.gaussians_3d(N, seed)
+    p[:, 3:6] = torch.exp(p[:, 3:6] + 0.7)
+    p[:, 10:13] = p[:, 10:13] * 1.2
+    p[:, 13] = torch.sigmoid(p[:, 13])
+    return p
+
+
+def test_oracle_3d_activated_inputs_match_fp64_torch_restatement():
+    """The gsplat.rendering shim path: no adapter activations, gradients w.r.t. the activated values."""
+    W, H, cam = 64, 56, 2
+    vm, Ks = synth.ring_cameras(6, ds=1152.0 / W)
+    p = _activated_rows(280, 5)
+    bg = torch.zeros(3, dtype=torch.float64)
+    w_rgb, w_a = synth.cotangents(1, H, W, seed=6)
+    pd = p.double().requires_grad_(True)
+    rgb, alpha, ncon = ref3d_torch.render(pd, vm[cam].double(), Ks[cam].double(), W, H, bg, radius_clip=2.0, activated=True)
+    ((rgb * w_rgb[0].double()).sum() + (alpha * w_a[0].double()).sum()).backward()
+    o = ora.render("3d", p.numpy(), W, H, np.zeros(3, np.float32), vm[cam].numpy(), Ks[cam].numpy(), w_rgb[0].numpy(),
+                   w_a[0].numpy(), radius_clip=2.0, activated=True)
+    assert np.abs(o["rgb"] - rgb.detach().numpy()).max() <= RGB_TOL
+    assert np.abs(o["alpha"] - alpha.detach().numpy()).max() <= RGB_TOL
+    rel = column_rel_err(o["d_params"], pd.grad.numpy())
+    assert rel.max() <= GRAD_TOL, rel
+
+
+def test_contract_projection_3d_activated_bit_exact():
+    W, H = 144, 128
+    vm, Ks = synth.ring_cameras(6, ds=8.0)
+    p = _activated_rows(1500, 9).numpy()
+    tab = ora.project("3d", p, W, H, vm[1].numpy(), Ks[1].numpy(), radius_clip=2.0, activated=True)
+    r, tile, low = hc_project("3d", p, W, H, vm[1].numpy(), Ks[1].numpy(), clip=2.0, activated=True)
+    want, _ = records_from_oracle("3d", tab)
+    assert np.array_equal(bits(r), bits(want))
+    assert np.array_equal(tile, tab["tile_rect"]) and np.array_equal(low, tab["low"])
