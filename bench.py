@@ -42,13 +42,15 @@ def parse():
     ap.add_argument("--split-frames", action="store_true", help="shard views (not frames): NCCL all-reduce of d_params")
     ap.add_argument("--fused-reduce", action="store_true",
                     help="with --split-frames: projection backward adds rows straight into the owner rank's d_params over NVLink")
+    ap.add_argument("--forward-only", action="store_true",
+                    help="inference: time the forward render alone (SURVEY 8d-d1: forward-only views/s for c1 and c4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short c3 (2D) measurement that rides along with c2")
     ap.add_argument("--n", type=int, default=0, help="override Gaussians per frame (debug only; invalidates the metric)")
     return ap.parse_args()
 
 
-FRAMES_DEFAULT = {"c1": 64, "c2": 64, "c3": 16, "c5_3d": 8, "c5_2d": 4}
+FRAMES_DEFAULT = {"c1": 64, "c2": 256, "c3": 32, "c5_3d": 16, "c5_2d": 4}
 
 
 # ------------------------------------------------------------------------------------------
@@ -175,7 +177,7 @@ def run_b200(args):
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     out = measure(args, args.workload, args.steps, world, rank, local, dev, primary=True)
-    if args.workload == "c2" and not args.no_secondary and not args.n and not args.split_frames:
+    if args.workload == "c2" and not args.no_secondary and not args.n and not args.split_frames and not args.forward_only:
         # the metric names two configurations; the 2D one (BASELINE.json configs[2]) rides along, briefly
         other = measure(args, "c3", max(2, min(3, args.steps)), world, rank, local, dev, primary=False)
         if rank == 0:
@@ -233,8 +235,14 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     peer = psd.PeerGradBuffers(tuple(sets[0]["params"].shape), dev) if fused else None
     input_mb = sum(sum(t.numel() * t.element_size() for t in h.values()) for h in host) / 2**20
 
+    fwd_only = bool(args.forward_only)
+    img_host = None
+
     def step_resident(k):
         s = devs[k % n_sets]
+        if fwd_only:
+            rgb, alpha, _, _ = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H, 0)
+            return rgb
         rgb, alpha, _, saved = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H,
                                                    _capi.FLAG_SAVE_FOR_BACKWARD)
         if fused:
@@ -275,6 +283,22 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         if not last:
             stage_inputs(k + 1)
         main.wait_event(ev)
+        if fwd_only:  # inference: rendered images go back to the host
+            nonlocal img_host
+            with torch.no_grad():
+                rgb, alpha = batched.render_views(mode, t["params"], t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
+            if img_host is None:
+                img_host = [(torch.empty_like(rgb, device="cpu").pin_memory(), torch.empty_like(alpha, device="cpu").pin_memory())
+                            for _ in range(2)]
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                img_host[k % 2][0].copy_(rgb, non_blocking=True)
+                img_host[k % 2][1].copy_(alpha, non_blocking=True)
+            rgb.record_stream(d2h_stream)
+            alpha.record_stream(d2h_stream)
+            return
         p = t["params"].requires_grad_(True)
         rgb, alpha = batched.render_views(mode, p, t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
         loss = (rgb * w_rgb).sum() + (alpha * w_a).sum()
@@ -364,7 +388,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     stage_ms = {k: (v[0] / max(1, v[1]), v[1]) for k, v in stages.items()}  # average per launch
     per_step = {k: v[0] / steps for k, v in stages.items()}
-    dom = max(("raster_fwd", "raster_bwd"), key=lambda k: per_step[k])
+    dom = "raster_fwd" if fwd_only else max(("raster_fwd", "raster_bwd"), key=lambda k: per_step[k])
     dom_ms = stage_ms[dom][0]
     achieved_tf = stats["pairs_evaluated"] * FLOPS_PER_PAIR[dom] / (dom_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -390,7 +414,8 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(wl), "mode": mode, "views_per_step_per_gpu": V, "frames_per_step_per_gpu": F,
+           "config": {"workload": workload_name(wl) + (" -- FORWARD ONLY (inference)" if fwd_only else ""), "mode": mode,
+                      "pass": "forward only" if fwd_only else "forward + backward", "views_per_step_per_gpu": V, "frames_per_step_per_gpu": F,
                       "cameras": n_cams, "gaussians_per_frame": args.n or cfg["n"], "isect_per_step": M,
                       "parallelism": f"views sharded over {world} GPU(s), " + ("views split, gradient rows added into the owner rank's buffer over NVLink inside the projection-backward kernel" if fused
                                                                                  else "views split, NCCL all-reduce of d_params" if need_reduce
@@ -398,7 +423,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
            "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0].values())),
-                   "d2h_bytes_per_step": int(out_host[0].numel() * 4 + 4),
+                   "d2h_bytes_per_step": int(V * H * W * 16) if fwd_only else int(out_host[0].numel() * 4 + 4),
                    "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm,
            "stage_ms_per_step": per_step, "pairs": stats, "fp32_peak_tflops": fp32_peak}
