@@ -240,9 +240,8 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
 
     def step_resident(k):
         s = devs[k % n_sets]
-        if fwd_only:
-            rgb, alpha, _, _ = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H, 0)
-            return rgb
+        if fwd_only:  # inference writes uint8 RGBA like scripts/utils/evaluate_model.py:101-113
+            return batched.render_views_rgba8(mode, s["params"], s["view_frame"], W, H, bg, s["viewmats"], s["Ks"])
         rgb, alpha, _, saved = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H,
                                                    _capi.FLAG_SAVE_FOR_BACKWARD)
         if fused:
@@ -285,19 +284,15 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         main.wait_event(ev)
         if fwd_only:  # inference: rendered images go back to the host
             nonlocal img_host
-            with torch.no_grad():
-                rgb, alpha = batched.render_views(mode, t["params"], t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
+            img = batched.render_views_rgba8(mode, t["params"], t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
             if img_host is None:
-                img_host = [(torch.empty_like(rgb, device="cpu").pin_memory(), torch.empty_like(alpha, device="cpu").pin_memory())
-                            for _ in range(2)]
+                img_host = [torch.empty_like(img, device="cpu").pin_memory() for _ in range(2)]
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
-                img_host[k % 2][0].copy_(rgb, non_blocking=True)
-                img_host[k % 2][1].copy_(alpha, non_blocking=True)
-            rgb.record_stream(d2h_stream)
-            alpha.record_stream(d2h_stream)
+                img_host[k % 2].copy_(img, non_blocking=True)
+            img.record_stream(d2h_stream)
             return
         p = t["params"].requires_grad_(True)
         rgb, alpha = batched.render_views(mode, p, t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
@@ -423,7 +418,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
            "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0].values())),
-                   "d2h_bytes_per_step": int(V * H * W * 16) if fwd_only else int(out_host[0].numel() * 4 + 4),
+                   "d2h_bytes_per_step": int(V * H * W * 4) if fwd_only else int(out_host[0].numel() * 4 + 4),
                    "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm,
            "stage_ms_per_step": per_step, "pairs": stats, "fp32_peak_tflops": fp32_peak}

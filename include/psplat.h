@@ -109,6 +109,14 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *desc, const float *params, con
                int32_t *n_contrib, ps_saved **saved, void *stream);
 
 /*
+ * Inference forward that writes uint8 RGBA [V,H,W,4] directly: replaces render + torch.cat([rgb, alpha], -1) +
+ * (255 * clip(x, 0, 1)).astype(uint8) of the evaluation writer (scripts/utils/evaluate_model.py:101-113), so a
+ * pixel leaves the GPU as 4 bytes instead of 16.  Same arguments as ps_forward; no state is saved.
+ */
+int ps_forward_rgba8(ps_ctx *ctx, const ps_render_desc *desc, const float *params, const int32_t *view_frame,
+                     const float *viewmats, const float *Ks, const float *background, uint8_t *rgba8, void *stream);
+
+/*
  * Backward of ps_forward: d_params [F,N,P] = dL/d gaussian_params given d_rgb [V,H,W,3] and
  * d_alpha [V,H,W].  Replaces autograd through :183-211 / :314-427 (gsplat's
  * rasterize_to_pixels_bwd + fully_fused_projection_bwd in 3D).  The input pointers must be

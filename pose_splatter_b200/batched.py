@@ -98,6 +98,27 @@ def forward_raw(mode, params, view_frame, viewmats, Ks, background, width, heigh
     return rgb, alpha, counts, saved
 
 
+def render_views_rgba8(mode: str, params: torch.Tensor, view_frame: torch.Tensor, width: int, height: int,
+                       background: torch.Tensor, viewmats: Optional[torch.Tensor] = None, Ks: Optional[torch.Tensor] = None,
+                       **opts) -> torch.Tensor:
+    """Inference render straight to uint8 RGBA [V,H,W,4], quantised like the reference's evaluation writer
+    (scripts/utils/evaluate_model.py:110-113).  Not differentiable."""
+    mode = mode.lower()
+    _check_inputs(mode, params, view_frame, viewmats, Ks, background)
+    dev = params.device
+    p = params.detach().contiguous().float()
+    vf, vm, Kd, bg = _prep(view_frame, torch.int32, dev), _prep(viewmats, torch.float32, dev), _prep(Ks, torch.float32, dev), \
+        _prep(background, torch.float32, dev)
+    F, N, _ = p.shape
+    V = int(vf.shape[0])
+    out = torch.empty(V, height, width, 4, dtype=torch.uint8, device=dev)
+    desc = _desc(mode, width, height, F, N, V, 0, opts)
+    _capi.check(_capi.load().ps_forward_rgba8(_capi.context(dev), ctypes.byref(desc), _capi.ptr(p), _capi.ptr(vf), _capi.ptr(vm),
+                                              _capi.ptr(Kd), _capi.ptr(bg), _capi.ptr(out), _capi.stream_ptr(dev)),
+                "ps_forward_rgba8")
+    return out
+
+
 def backward_raw(saved: SavedForward, params, view_frame, viewmats, Ks, background, d_rgb, d_alpha):
     d_params = torch.empty_like(params)
     dev = params.device

@@ -253,9 +253,9 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
     sv->frame_off = sv->frame_views = nullptr; // live inside the offsets allocation
 }
 
-int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
-               const float *viewmats, const float *Ks, const float *background, float *rgb, float *alpha,
-               int32_t *n_contrib, ps_saved **saved, void *stream)
+static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
+                        const float *viewmats, const float *Ks, const float *background, float *rgb, float *alpha,
+                        uint32_t *rgba8, int32_t *n_contrib, ps_saved **saved, void *stream)
 {
     if (saved) *saved = nullptr;
     if (!ctx || !d) return fail(1, "ps_forward: NULL context or descriptor");
@@ -264,7 +264,7 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
         return fail(1, "ps_forward: image size %dx%d unsupported", d->width, d->height);
     if (d->n_views < 0 || d->n_gauss < 0 || d->n_frames < 0) return fail(1, "ps_forward: negative size");
     if (d->n_views > 65535) return fail(1, "ps_forward: at most 65535 views per call (got %d)", d->n_views);
-    if (d->n_views > 0 && (!view_frame || !background || !rgb || !alpha)) return fail(1, "ps_forward: NULL buffer");
+    if (d->n_views > 0 && (!view_frame || !background || (!rgba8 && (!rgb || !alpha)))) return fail(1, "ps_forward: NULL buffer");
     if (d->n_views > 0 && d->n_gauss > 0 && !params) return fail(1, "ps_forward: NULL params");
     if (d->mode == PS_MODE_3D && d->n_views > 0 && (!viewmats || !Ks)) return fail(1, "ps_forward: 3D needs viewmats and Ks");
     if ((int64_t)d->n_views * d->n_gauss > 0x7fffffffLL) return fail(1, "ps_forward: V*N exceeds 2^31");
@@ -359,9 +359,9 @@ int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const 
             }
             if (keep) PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
-            PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, s));
+            PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, rgba8, s));
             PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->n_work, background, rgb, alpha, n_contrib,
-                                               sv->last, sv->blast, sv->t_pen, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
+                                               sv->last, sv->blast, sv->t_pen, rgba8, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
         }
     }
 out:
@@ -379,6 +379,23 @@ out:
     return rc;
 #undef PS_TRY_CUDA
 #undef PS_TRY_LAUNCH
+}
+
+int ps_forward(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
+               const float *viewmats, const float *Ks, const float *background, float *rgb, float *alpha,
+               int32_t *n_contrib, ps_saved **saved, void *stream)
+{
+    return forward_impl(ctx, d, params, view_frame, viewmats, Ks, background, rgb, alpha, nullptr, n_contrib, saved, stream);
+}
+
+int ps_forward_rgba8(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
+                     const float *viewmats, const float *Ks, const float *background, uint8_t *rgba8, void *stream)
+{
+    if (!rgba8 && d && d->n_views > 0) return fail(1, "ps_forward_rgba8: NULL output");
+    if (((uintptr_t)rgba8 & 3u) != 0) return fail(1, "ps_forward_rgba8: output must be 4-byte aligned");
+    if (d && (d->flags & (PS_FLAG_SAVE_FOR_BACKWARD | PS_FLAG_KEEP_BINNING))) return fail(1, "ps_forward_rgba8 is inference only");
+    return forward_impl(ctx, d, params, view_frame, viewmats, Ks, background, nullptr, nullptr, reinterpret_cast<uint32_t *>(rgba8),
+                        nullptr, nullptr, stream);
 }
 
 static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const float *viewmats, const float *Ks,

@@ -70,13 +70,14 @@ int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l
 int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint64_t *keys, cudaStream_t s);
 
 // rasterizers (ps_raster.cu)
+// rgb / alpha / rgba8 may each be NULL (rgba8: uint8 RGBA, one uint32 per pixel, quantised like the reference's writer)
 int ps_launch_fill_empty(const PsGeometry &g, const int32_t *offsets, const float *background, float *rgb, float *alpha,
-                         int32_t *n_contrib, int32_t *last, cudaStream_t s);
+                         int32_t *n_contrib, int32_t *last, uint32_t *rgba8, cudaStream_t s);
 int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
 // last: tile-list position + 1 of the last contributor (tap); blast: the same as an index into the block list (backward)
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, int32_t *blast, float *t_pen,
-                         unsigned long long *stats, cudaStream_t s);
+                         uint32_t *rgba8, unsigned long long *stats, cudaStream_t s);
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
                          cudaStream_t s);

@@ -119,6 +119,17 @@ __device__ __forceinline__ void active_box(uint32_t active, int &x0, int &x1, in
     y1 = (31 - __clz(active)) >> 3;
 }
 
+// uint8 RGBA exactly as the reference's evaluation writer quantises it (scripts/utils/evaluate_model.py:110-113):
+// (255 * clip(x, 0, 1)).astype(uint8), i.e. fp32 multiply, truncation
+__device__ __forceinline__ uint32_t quantise_rgba8(float r, float g, float b, float a)
+{
+    const uint32_t qr = (uint32_t)psm_mul(255.0f, fminf(fmaxf(r, 0.0f), 1.0f));
+    const uint32_t qg = (uint32_t)psm_mul(255.0f, fminf(fmaxf(g, 0.0f), 1.0f));
+    const uint32_t qb = (uint32_t)psm_mul(255.0f, fminf(fmaxf(b, 0.0f), 1.0f));
+    const uint32_t qa = (uint32_t)psm_mul(255.0f, fminf(fmaxf(a, 0.0f), 1.0f));
+    return qr | (qg << 8) | (qb << 16) | (qa << 24);
+}
+
 // The warp-private ring: stage st holds chunk data for 32 entries.
 struct Ring {
     float4 (*a)[CH], (*b)[CH], (*c)[CH];
@@ -150,7 +161,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                   float *__restrict__ rgb, float *__restrict__ alpha,
                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount,
-                  unsigned long long *__restrict__ stats)
+                  uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats)
 {
     __shared__ float4 s_a[WPC][NS][CH], s_b[WPC][NS][CH], s_c[WPC][NS][CH];
     __shared__ uint32_t s_pos[WPC][NS][CH];
@@ -278,10 +289,10 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     if (c.inside) {
         const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
         const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
-        rgb[3 * p + 0] = psm_fma(T, b0, cr);
-        rgb[3 * p + 1] = psm_fma(T, b1, cg);
-        rgb[3 * p + 2] = psm_fma(T, b2, cb);
-        alpha[p] = psm_sub(1.0f, T);
+        const float o0 = psm_fma(T, b0, cr), o1 = psm_fma(T, b1, cg), o2 = psm_fma(T, b2, cb), oa = psm_sub(1.0f, T);
+        if (rgb) { rgb[3 * p + 0] = o0; rgb[3 * p + 1] = o1; rgb[3 * p + 2] = o2; }
+        if (alpha) alpha[p] = oa;
+        if (rgba8) rgba8[p] = quantise_rgba8(o0, o1, o2, oa);
         if (n_contrib) n_contrib[p] = cnt;
         if (last) last[p] = c.start + (blastpos ? (int)__ldg(c.bl + blastpos - 1) + 1 : 0); // tile-list position
         if (blast) blast[p] = blastpos;
@@ -609,11 +620,11 @@ int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &
 
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, int32_t *blast, float *t_pen,
-                         unsigned long long *stats, cudaStream_t s)
+                         uint32_t *rgba8, unsigned long long *stats, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
     const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
-#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, stats)
+#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, rgba8, stats)
     if (g.mode == PS_MODE_3D) { if (stats) PS_FWD(PS_MODE_3D, true); else PS_FWD(PS_MODE_3D, false); }
     else { if (stats) PS_FWD(PS_MODE_2D, true); else PS_FWD(PS_MODE_2D, false); }
 #undef PS_FWD
@@ -667,7 +678,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 fill_empty_kernel(PsGeometry g, const int32_t *__restrict__ offsets, const float *__restrict__ background,
                   float *__restrict__ rgb, float *__restrict__ alpha, int32_t *__restrict__ n_contrib,
-                  int32_t *__restrict__ last, int groups_x, long long n_groups, int vec_ok)
+                  int32_t *__restrict__ last, uint32_t *__restrict__ rgba8, int groups_x, long long n_groups, int vec_ok)
 {
     const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gidx >= n_groups) return;
@@ -681,18 +692,23 @@ fill_empty_kernel(PsGeometry g, const int32_t *__restrict__ offsets, const float
     const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
     const size_t p = (size_t)row * g.W + x0;
     const int n = min(4, g.W - x0);
+    const uint32_t q8 = quantise_rgba8(b0, b1, b2, 0.0f);
     if (n == 4 && vec_ok) {
-        float4 *d = reinterpret_cast<float4 *>(rgb + 3 * p);
-        d[0] = make_float4(b0, b1, b2, b0);
-        d[1] = make_float4(b1, b2, b0, b1);
-        d[2] = make_float4(b2, b0, b1, b2);
-        *reinterpret_cast<float4 *>(alpha + p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rgb) {
+            float4 *d = reinterpret_cast<float4 *>(rgb + 3 * p);
+            d[0] = make_float4(b0, b1, b2, b0);
+            d[1] = make_float4(b1, b2, b0, b1);
+            d[2] = make_float4(b2, b0, b1, b2);
+        }
+        if (alpha) *reinterpret_cast<float4 *>(alpha + p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rgba8) *reinterpret_cast<uint4 *>(rgba8 + p) = make_uint4(q8, q8, q8, q8);
         if (n_contrib) *reinterpret_cast<int4 *>(n_contrib + p) = make_int4(0, 0, 0, 0);
         if (last) *reinterpret_cast<int4 *>(last + p) = make_int4(start, start, start, start);
     } else {
         for (int k = 0; k < n; ++k) {
-            rgb[3 * (p + k)] = b0; rgb[3 * (p + k) + 1] = b1; rgb[3 * (p + k) + 2] = b2;
-            alpha[p + k] = 0.0f;
+            if (rgb) { rgb[3 * (p + k)] = b0; rgb[3 * (p + k) + 1] = b1; rgb[3 * (p + k) + 2] = b2; }
+            if (alpha) alpha[p + k] = 0.0f;
+            if (rgba8) rgba8[p + k] = q8;
             if (n_contrib) n_contrib[p + k] = 0;
             if (last) last[p + k] = start;
         }
@@ -701,14 +717,14 @@ fill_empty_kernel(PsGeometry g, const int32_t *__restrict__ offsets, const float
 } // namespace
 
 int ps_launch_fill_empty(const PsGeometry &g, const int32_t *offsets, const float *background, float *rgb, float *alpha,
-                         int32_t *n_contrib, int32_t *last, cudaStream_t s)
+                         int32_t *n_contrib, int32_t *last, uint32_t *rgba8, cudaStream_t s)
 {
     const int groups_x = (g.W + 3) / 4;
     const long long n_groups = (long long)g.V * g.H * groups_x;
     if (n_groups == 0) return 0;
-    const uintptr_t align = (uintptr_t)rgb | (uintptr_t)alpha | (uintptr_t)n_contrib | (uintptr_t)last;
+    const uintptr_t align = (uintptr_t)rgb | (uintptr_t)alpha | (uintptr_t)n_contrib | (uintptr_t)last | (uintptr_t)rgba8;
     const int vec_ok = (g.W & 3) == 0 && (align & 15u) == 0;
     fill_empty_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(g, offsets, background, rgb, alpha, n_contrib, last,
-                                                                      groups_x, n_groups, vec_ok);
+                                                                      rgba8, groups_x, n_groups, vec_ok);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

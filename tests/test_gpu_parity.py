@@ -275,3 +275,21 @@ def test_3d_activated_inputs_bit_exact():
     p[:, 13] = torch.sigmoid(p[:, 13])
     _compare("3d", p[None], torch.zeros(2, dtype=torch.int32), 144, 128, (0.0, 0.0, 0.0), vm[:2], Ks[:2],
              radius_clip=2.0, activated=True)
+
+
+@pytest.mark.parametrize("wl", ["c2", "c1"])
+def test_rgba8_inference_output_matches_reference_quantisation(wl):
+    """ps_forward_rgba8 == (255 * clip(cat(rgb, alpha), 0, 1)).astype(uint8) of the oracle's float image
+    (scripts/utils/evaluate_model.py:101-113), bit for bit; tiles without splats included."""
+    ora, _, batched, synth = _mods()
+    d = synth.make_views(wl, n_frames=1, n_cams=2, seed=13, n=2500)
+    W, H = d["width"], d["height"]
+    bg = np.array([1.0, 1.0, 1.0], np.float32)
+    got = batched.render_views_rgba8(d["mode"], d["params"].to(DEV), d["view_frame"].to(DEV), W, H,
+                                     torch.from_numpy(bg).to(DEV), d["viewmats"].to(DEV), d["Ks"].to(DEV)).cpu().numpy()
+    want = ora.render_views(d["mode"], d["params"].numpy(), d["view_frame"].numpy(), W, H, bg, d["viewmats"].numpy(),
+                            d["Ks"].numpy())
+    rgba = np.concatenate([want["rgb"], want["alpha"][..., None]], -1)
+    want8 = (255 * rgba.clip(0, 1)).astype(np.uint8)
+    assert got.shape == want8.shape and got.dtype == np.uint8
+    assert np.array_equal(got, want8)
