@@ -296,7 +296,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
             return
         p = t["params"].requires_grad_(True)
         rgb, alpha = batched.render_views(mode, p, t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
-        loss = (rgb * w_rgb).sum() + (alpha * w_a).sum()
+        loss = torch.dot(rgb.reshape(-1), w_rgb.reshape(-1)) + torch.dot(alpha.reshape(-1), w_a.reshape(-1))
         loss.backward()
         g = p.grad
         if need_reduce:

@@ -65,9 +65,11 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ uint32_t s_hist[256], s_tmp[8], s_minmax[2];
-    __shared__ IdT s_wcnt[RW][256]; // per-(warp, digit) counts, then output cursors (< N: fits IdT)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t base = (size_t)blockIdx.x * N;
+    // per-(warp, digit) counts, then output cursors (< N: fits IdT); two matrices: this pass's and the next's
+    IdT (*s_wcnt)[RW][256] = reinterpret_cast<IdT (*)[RW][256]>(dyn);
+    unsigned char *dyn_keys = dyn + 2 * RW * 256 * sizeof(IdT);
     uint32_t *k[2];
     IdT *id[2];
     if (gscratch) {
@@ -75,7 +77,7 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
         k[0] = p; k[1] = p + N;
         id[0] = reinterpret_cast<IdT *>(p + 2 * (size_t)N); id[1] = reinterpret_cast<IdT *>(p + 3 * (size_t)N);
     } else {
-        k[0] = reinterpret_cast<uint32_t *>(dyn); k[1] = k[0] + N;
+        k[0] = reinterpret_cast<uint32_t *>(dyn_keys); k[1] = k[0] + N;
         id[0] = reinterpret_cast<IdT *>(k[1] + N); id[1] = id[0] + N;
     }
     if (tid == 0) { s_minmax[0] = 0xffffffffu; s_minmax[1] = 0u; }
@@ -99,41 +101,42 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
     // digits above the highest bit in which two listed depth words differ cannot change the order
     const uint32_t diff = (mx >= mn) ? (mn ^ mx) : 0u;
     const int npass = diff ? (32 - __clz(diff) + 7) / 8 : 0;
-    // Every warp owns one contiguous segment of the array for the whole pass, so the per-(warp, digit)
-    // counts are taken once per pass and one scan in (digit, warp) order gives each warp its private
-    // output cursor for every digit: three CTA barriers per pass, and ties keep their input order.
+    // Every warp owns one contiguous segment of the array for the whole pass, so one scan of the per-(warp, digit)
+    // counts in (digit, warp) order gives each warp a private output cursor for every digit: ties keep their input
+    // order with a handful of CTA barriers per pass.  The counts of pass p+1 are taken while pass p scatters (the
+    // destination segment of an element is known from its output position), so the keys are swept once per pass.
     const int seg = ((N + RW - 1) / RW + 31) & ~31;
+    const float inv_seg = 1.0f / (float)seg;
     const int seg_lo = min(N, wid * seg), seg_hi = min(N, seg_lo + seg);
+    auto cnt_inc = [&](IdT *row, uint32_t digit) { // ++row[digit]; 16-bit counters are bumped in pairs (no 16-bit atomics)
+        if (sizeof(IdT) == 2) atomicAdd(reinterpret_cast<uint32_t *>(row) + (digit >> 1), 1u << (16u * (digit & 1u)));
+        else atomicAdd(reinterpret_cast<uint32_t *>(row) + digit, 1u);
+    };
+    int cur = 0;
+    if (npass > 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_wcnt[0][wid][lane + 32 * q] = (IdT)0;
+        __syncwarp();
+        for (int i = seg_lo + lane; i < seg_hi; i += 32) cnt_inc(s_wcnt[0][wid], k[0][i] & 255u);
+    }
     for (int p = 0; p < npass; ++p) {
         const int shift = 8 * p;
         const uint32_t *kin = k[p & 1];
         const IdT *iin = id[p & 1];
         uint32_t *kout = k[(p + 1) & 1];
         IdT *iout = id[(p + 1) & 1];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s_wcnt[wid][lane + 32 * q] = (IdT)0;
-        __syncwarp();
-        for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
-            const int i = i0 + lane;
-            const bool live = i < seg_hi;
-            const uint32_t live_mask = __ballot_sync(FULL, live);
-            if (live) {
-                const uint32_t digit = (kin[i] >> shift) & 255u;
-                const uint32_t peers = __match_any_sync(live_mask, digit);
-                if ((peers & ((1u << lane) - 1u)) == 0) s_wcnt[wid][digit] += (IdT)__popc(peers);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
+        const bool more = p + 1 < npass;
+        __syncthreads(); // the counts of this pass are complete
         {   // exclusive scan of the 256 x 32 counts in (digit, warp) order: four threads per digit, eight warps
             // each; digit totals are scanned across the CTA
             const int d = tid >> 2, part = tid & 3;
             uint32_t loc[8], run = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint32_t cc = s_wcnt[part * 8 + i][d];
+                const uint32_t cc = s_wcnt[cur][part * 8 + i][d];
                 loc[i] = run;
                 run += cc;
+                s_wcnt[cur ^ 1][part * 8 + i][d] = (IdT)0; // next pass's counters
             }
             uint32_t incl = run;
             uint32_t n = __shfl_up_sync(FULL, incl, 1, 4);
@@ -146,7 +149,7 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
             scan256_exclusive(s_hist, s_tmp);
             const uint32_t dbase = s_hist[d];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s_wcnt[part * 8 + i][d] = (IdT)(dbase + loc[i] + off);
+            for (int i = 0; i < 8; ++i) s_wcnt[cur][part * 8 + i][d] = (IdT)(dbase + loc[i] + off);
         }
         __syncthreads();
         for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
@@ -159,16 +162,18 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
                 const uint32_t digit = (key >> shift) & 255u;
                 const uint32_t peers = __match_any_sync(live_mask, digit);
                 const uint32_t r = __popc(peers & ((1u << lane) - 1u));
-                const uint32_t pos = (uint32_t)s_wcnt[wid][digit] + r;
+                const uint32_t pos = (uint32_t)s_wcnt[cur][wid][digit] + r;
                 kout[pos] = key;
                 iout[pos] = idv;
+                if (more) cnt_inc(s_wcnt[cur ^ 1][min(RW - 1, (int)(((float)pos + 0.5f) * inv_seg))], (key >> (shift + 8)) & 255u);
                 __syncwarp(live_mask);
-                if (r == 0) s_wcnt[wid][digit] += (IdT)__popc(peers);
+                if (r == 0) s_wcnt[cur][wid][digit] += (IdT)__popc(peers);
             }
             __syncwarp();
         }
-        __syncthreads();
+        cur ^= 1;
     }
+    __syncthreads();
     const IdT *fin = id[npass & 1];
     for (int r = tid; r < N; r += RT) {
         const uint32_t gid = (uint32_t)fin[r];
@@ -430,7 +435,8 @@ debug_keys_kernel(PsGeometry g, const uint32_t *__restrict__ depth, const int32_
 }
 
 size_t rank_smem_bytes(int N) { return (size_t)N * 12; }
-constexpr size_t RANK_STATIC_SMEM = 256 * 4 * 2 + 8 * 4 + 8 + RW * 256 * 2;
+constexpr size_t RANK_STATIC_SMEM = 256 * 4 + 8 * 4 + 8;
+constexpr size_t RANK_CNT_SMEM16 = 2 * RW * 256 * 2, RANK_CNT_SMEM32 = 2 * RW * 256 * 4;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 } // namespace
@@ -438,7 +444,7 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 size_t ps_rank_scratch_elems(const PsGeometry &g)
 {
     if (g.mode != PS_MODE_3D || g.N == 0 || g.V == 0) return 0;
-    if (g.N <= 65535 && rank_smem_bytes(g.N) + RANK_STATIC_SMEM + 1024 <= SMEM_LIMIT) return 0;
+    if (g.N <= 65535 && rank_smem_bytes(g.N) + RANK_CNT_SMEM16 + RANK_STATIC_SMEM + 1024 <= SMEM_LIMIT) return 0;
     return (size_t)g.V * 4 * (size_t)g.N;
 }
 
@@ -446,13 +452,15 @@ int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratc
 {
     if (g.mode != PS_MODE_3D || g.N == 0 || g.V == 0) return 0;
     if (ps_rank_scratch_elems(g) == 0) {
-        const size_t dyn = rank_smem_bytes(g.N);
+        const size_t dyn = rank_smem_bytes(g.N) + RANK_CNT_SMEM16;
         if (cudaFuncSetAttribute(depth_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
             return -1;
         depth_rank_kernel<uint16_t><<<g.V, RT, dyn, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, nullptr);
     } else {
         if (!scratch) return -1;
-        depth_rank_kernel<uint32_t><<<g.V, RT, 0, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, scratch);
+        if (cudaFuncSetAttribute(depth_rank_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_CNT_SMEM32) != cudaSuccess)
+            return -1;
+        depth_rank_kernel<uint32_t><<<g.V, RT, RANK_CNT_SMEM32, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, scratch);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

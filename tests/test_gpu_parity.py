@@ -239,7 +239,7 @@ def test_batch_invariance_full_size_c2():
 
 
 def test_3d_many_gaussians_global_rank_path():
-    """N above the shared-memory capacity of the per-view depth ranking (17.8k) takes the global-scratch variant."""
+    """N above the shared-memory capacity of the per-view depth ranking (16.4k) takes the global-scratch variant."""
     _, _, _, synth = _mods()
     vm, Ks = synth.ring_cameras(6, ds=12.0)
     p = synth.gaussians_3d(20000, 31)[None]
