@@ -543,7 +543,8 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                    const int32_t *__restrict__ worklist, uint32_t *__restrict__ blist, int32_t *__restrict__ bcount)
 {
     __shared__ int s_cnt[8][8]; // [warp][block]
-    __shared__ int s_run[8];
+    __shared__ int s_pre[8][8]; // [warp][block] output cursor of the round
+    __shared__ int s_run[8], s_tot[8];
     const int item = blockIdx.x;
     const int lin = worklist[item];
     const int view = lin / g.n_tiles, tile = lin - view * g.n_tiles;
@@ -587,22 +588,22 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             if (lane == 0) s_cnt[wid][k] = __popc(bal[k]);
         }
         __syncthreads();
-        int tot = 0; // all reads of s_cnt happen between the two barriers: the next round may overwrite it at once
-        if (threadIdx.x < 8) {
+        if (threadIdx.x < 64) { // output cursor of every (warp, block) for this round: 64 threads, 8 adds each
+            const int w = threadIdx.x >> 3, k = threadIdx.x & 7;
+            int pre = s_run[k];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) tot += s_cnt[w][threadIdx.x];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if ((m8 >> k) & 1u) {
-                int pre = s_run[k];
-#pragma unroll
-                for (int w = 0; w < 8; ++w) pre += (w < wid) ? s_cnt[w][k] : 0;
-                out[(size_t)k * len + pre + __popc(bal[k] & ((1u << lane) - 1u))] = (uint32_t)j;
-            }
+            for (int w2 = 0; w2 < 8; ++w2) pre += (w2 < w) ? s_cnt[w2][k] : 0;
+            s_pre[w][k] = pre;
+            if (w == 7) s_tot[k] = pre + s_cnt[7][k]; // running total after this round
         }
         __syncthreads();
-        if (threadIdx.x < 8) s_run[threadIdx.x] += tot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((m8 >> k) & 1u) out[(size_t)k * len + s_pre[wid][k] + __popc(bal[k] & ((1u << lane) - 1u))] = (uint32_t)j;
+        }
+        if (threadIdx.x < 8) s_run[threadIdx.x] = s_tot[threadIdx.x];
+        // s_cnt is rewritten by the next round only after every thread has passed the second barrier above, and
+        // s_pre / s_run are read by it only after its own first barrier
     }
     __syncthreads();
     if (threadIdx.x < 8) bcount[item * 8 + threadIdx.x] = s_run[threadIdx.x];
