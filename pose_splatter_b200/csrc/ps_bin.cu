@@ -407,14 +407,17 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
     for (int w = w0; w < w1; ++w) cnt += __popc(s_bm[w]);
     int out = start + block_exclusive_scan_256i(cnt, s_warp);
     const uint32_t vbase = (uint32_t)view * (uint32_t)g.N;
-    for (int w = w0; w < w1; ++w) {
+    for (int w = w0; w < w1; ++w) { // sorted ranks (3D) / finished values (2D), in order
         uint32_t bits = s_bm[w];
         while (bits) {
             const uint32_t r = (uint32_t)(w << 5) + (uint32_t)(__ffs(bits) - 1);
             bits &= bits - 1;
-            const uint32_t gid = (MODE == PS_MODE_3D) ? __ldg(order + vbase + r) : r;
-            vals[out++] = vbase + gid;
+            vals[out++] = (MODE == PS_MODE_3D) ? r : vbase + r;
         }
+    }
+    if (MODE == PS_MODE_3D) { // rank -> Gaussian with every thread gathering independently
+        __syncthreads();
+        for (int i = start + threadIdx.x; i < end; i += 256) vals[i] = vbase + __ldg(order + vbase + vals[i]);
     }
 }
 

@@ -8,7 +8,7 @@
 
 #define PS_PROJ_BLOCK 256    // (view, Gaussian) pairs per projection / partition block
 #define PS_RASTER_BATCH 256  // tile-list entries staged in shared memory per round
-#define PS_ACC_STRIDE 12     // floats per (view, Gaussian) gradient accumulator row (9 used, 16-byte aligned)
+#define PS_ACC_STRIDE 9      // floats per (view, Gaussian) gradient accumulator row
 #define PS_HIST_SMEM_TILES 8192  // per-view tile histograms live in shared memory up to this many tiles
 #define PS_RANK_THREADS 1024     // one CTA per view in the depth-ranking kernel
 #define PS_N_CLASSES 32          // tile-list size classes (floor(log2(len))) of the work list

@@ -266,9 +266,9 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
         if (!live) continue;
         const size_t idx = (size_t)v * g.N + gi;
         if (t.tiles_touched[idx] == 0) continue; // never listed -> no contribution -> zero gradient
-        const float4 *a4 = reinterpret_cast<const float4 *>(acc + idx * PS_ACC_STRIDE);
-        const float4 q0 = a4[0], q1 = a4[1], q2 = a4[2];
-        const float a[9] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x };
+        float a[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a[k] = __ldg(acc + idx * PS_ACC_STRIDE + k);
         bool any = false; // listed but never a contributor (hidden behind saturated pixels): gradient exactly zero
 #pragma unroll
         for (int k = 0; k < 9; ++k) any = any || (a[k] != 0.0f);
