@@ -422,6 +422,26 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                    "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm,
            "stage_ms_per_step": per_step, "pairs": stats, "fp32_peak_tflops": fp32_peak}
+    if primary and not fwd_only:
+        # the reference's own call shape: ONE view per render() + backward through the drop-in class (SURVEY 8d-d3 iii)
+        from pose_splatter_b200 import create_renderer
+        r1 = create_renderer(mode, W, H, device=str(dev))
+        r1.set_background_color(torch.ones(3))
+        p1 = devs[0]["params"][0].clone().requires_grad_(True)
+        vm1, K1 = devs[0]["viewmats"][0], devs[0]["Ks"][0]
+        lat = []
+        for it in range(30):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rgb1, a1 = r1.render(p1, vm1, K1)
+            (rgb1.sum() + a1.sum()).backward()
+            torch.cuda.synchronize()
+            lat.append(1e3 * (time.perf_counter() - t0))
+            p1.grad = None
+        lat = sorted(lat[5:])
+        out["single_view"] = {"latency_ms_median": lat[len(lat) // 2], "latency_ms_min": lat[0],
+                              "what": "one renderer.render(params[N,P], viewmat, K) + backward, host wall clock with a device "
+                                      "synchronisation on both sides (launch / latency bound; the batched numbers are the headline)"}
     if world == 1 and primary and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         probe_vps, _ = cpu_views_per_second(wl, cores, cores, args.n)           # short probe sizes the sample

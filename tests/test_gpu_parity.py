@@ -293,3 +293,42 @@ def test_rgba8_inference_output_matches_reference_quantisation(wl):
     want8 = (255 * rgba.clip(0, 1)).astype(np.uint8)
     assert got.shape == want8.shape and got.dtype == np.uint8
     assert np.array_equal(got, want8)
+
+
+@pytest.mark.parametrize("mode", ["3d", "2d"])
+def test_non_finite_rows_are_culled_like_the_oracle(mode):
+    """NaN / inf / huge values in some rows: those Gaussians are dropped by the contract's finite checks on both
+    sides; everything else stays bit-exact and nothing hangs."""
+    _, _, _, synth = _mods()
+    if mode == "3d":
+        vm, Ks = synth.ring_cameras(6, ds=8.0)
+        p = synth.gaussians_3d(600, 12)
+        p[5, 0] = float("nan"); p[6, 4] = float("inf"); p[7, 7] = float("nan"); p[8, 13] = float("nan")
+        p[9, 3:6] = 80.0       # exp overflow -> inf covariance
+        p[10, 6:10] = 0.0      # zero quaternion
+        p[11, 2] = 1e30
+        _compare("3d", p[None], torch.zeros(1, dtype=torch.int32), 144, 128, (1.0, 1.0, 1.0), vm[:1], Ks[:1], check_grad=False)
+    else:
+        z = np.load(GOLDEN / "ref2d_random_96x80.npz")
+        p = torch.from_numpy(z["params"]).clone()
+        p[3, 0] = float("nan"); p[4, 2] = float("inf"); p[5, 4] = float("inf"); p[6, 8] = float("nan"); p[7, 3] = 90.0
+        p[8, 0] = 1e30
+        _compare("2d", p[None], torch.zeros(1, dtype=torch.int32), int(z["W"]), int(z["H"]), z["bg"], check_grad=False)
+
+
+def test_many_views_few_gaussians():
+    """2000 views of a tiny frame set: exercises view indexing beyond the benchmark's batch shapes."""
+    _, _capi, batched, synth = _mods()
+    vm, Ks = synth.ring_cameras(6, ds=32.0)
+    F, V = 5, 2000
+    p = torch.stack([synth.gaussians_3d(64, 100 + f) for f in range(F)])
+    p[:, :, 3:6] += 2.0
+    vf = (torch.arange(V) % F).int()
+    cams = torch.arange(V) % 6
+    rgb, alpha, cnt, sv = batched.forward_raw("3d", p.to(DEV), vf.to(DEV), vm[cams].to(DEV), Ks[cams].to(DEV),
+                                              torch.ones(3, device=DEV), 36, 32, _capi.FLAG_SAVE_FOR_BACKWARD, True)
+    # view v and view v + 30 (same frame, same camera) must be identical
+    assert torch.equal(rgb[7], rgb[37]) and torch.equal(cnt[7], cnt[37]) and torch.equal(alpha[1999], alpha[1999 - 30])
+    g = batched.backward_raw(sv, p.to(DEV), vf.to(DEV), vm[cams].to(DEV), Ks[cams].to(DEV), torch.ones(3, device=DEV),
+                             torch.ones(V, 32, 36, 3, device=DEV), torch.ones(V, 32, 36, device=DEV))
+    assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
