@@ -235,7 +235,7 @@ __device__ __forceinline__ void red_add_v2(float *addr, float a, float b)
 //                      peer GPU's over NVLink), so the cross-GPU sum needs no separate collective or staging copy.
 //                      The owners zero their buffers and all ranks meet at a barrier before and after (host side).
 template <int MODE>
-__global__ void __launch_bounds__(PS_PROJ_BLOCK)
+__global__ void __launch_bounds__(PS_PROJ_BLOCK, 3)
 project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ frame_off,
                    const int32_t *__restrict__ frame_views, const float *__restrict__ viewmats,
                    const float *__restrict__ Ks, PsTable t, const float *__restrict__ acc, float *__restrict__ d_params,

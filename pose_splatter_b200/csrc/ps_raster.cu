@@ -352,7 +352,7 @@ __device__ __forceinline__ void warp_reduce9(float (&v)[8], float &v8, int lane)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_THREADS, 20)
 raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const float *__restrict__ background, const int32_t *__restrict__ last,
                   const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
