@@ -246,10 +246,10 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                                    _capi.FLAG_SAVE_FOR_BACKWARD)
         if fused:
             peer.begin()
-            batched.backward_peer_raw(saved, s["params"], s["viewmats"], s["Ks"], bg, w_rgb, w_a, peer.rank_ptrs, peer.frame_owner)
-            peer.end()
+            batched.backward_peer_raw(saved, s["params"], s["viewmats"], s["Ks"], bg, w_rgb, w_a, peer.rank_ptrs, peer.rank, peer.world)
+            g_owned = peer.end()
             saved.release()
-            return peer.buf
+            return g_owned
         d_params = batched.backward_raw(saved, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, w_rgb, w_a)
         saved.release()
         if need_reduce:
@@ -422,7 +422,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
            "config": {"workload": workload_name(wl) + (" -- FORWARD ONLY (inference)" if fwd_only else ""), "mode": mode,
                       "pass": "forward only" if fwd_only else "forward + backward", "views_per_step_per_gpu": V, "frames_per_step_per_gpu": F,
                       "cameras": n_cams, "gaussians_per_frame": args.n or cfg["n"], "isect_per_step": M,
-                      "parallelism": f"views sharded over {world} GPU(s), " + ("views split, gradient rows added into the owner rank's buffer over NVLink inside the projection-backward kernel" if fused
+                      "parallelism": f"views sharded over {world} GPU(s), " + ("views split, gradient rows pushed into the owner rank's staging buffer over NVLink by the projection-backward kernel" if fused
                                                                                  else "views split, NCCL all-reduce of d_params" if need_reduce
                                                                                  else "whole frames per rank, no collective"),
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},

@@ -127,19 +127,21 @@ int ps_backward(ps_ctx *ctx, ps_saved *saved, const float *params, const int32_t
                 void *stream);
 
 /*
- * Backward with the cross-GPU gradient sum fused in (no reference counterpart: the reference is
- * single-GPU).  For use when the cameras of one frame are rendered by different ranks: instead of writing its
- * partial d_params and all-reducing it, the projection-backward kernel adds every finished row
- * (red.global.add.v2.f32) straight into the d_params buffer of the rank that owns the frame.
- *   d_params_ranks  DEVICE array [world] of device pointers: rank r's d_params buffer [F,N,P], each mapped into
- *                   this process (peer memory over NVLink, e.g. torch symmetric memory); entry [own rank] is local
- *   frame_owner     DEVICE int32 [F]: the rank that owns each frame
- * Protocol (host side): every rank zeroes its own buffer, all ranks meet at a barrier, every rank calls this,
- * all ranks meet at a barrier again; then rank r holds the complete gradient of the frames it owns.
+ * Backward with the cross-GPU gradient exchange fused in (no reference counterpart: the reference is
+ * single-GPU).  For use when the cameras of one frame are rendered by different ranks.  Frame f is owned by rank
+ * f % world.  Instead of writing its partial d_params and all-reducing it, the projection-backward kernel pushes
+ * every finished block of rows, with coalesced stores, straight into slot [my_rank][f / world] of the owner's
+ * staging buffer -- local memory or a peer GPU's over NVLink.
+ *   stage_ranks  DEVICE array [world] of device pointers: rank r's staging buffer [world][ceil(F/world)][N][P] fp32,
+ *                each mapped into this process (e.g. torch symmetric memory); entry [my_rank] is local
+ * Protocol (host side): all ranks meet at a barrier (the owners are done with the previous step's staging), every
+ * rank calls ps_backward_peer, all ranks meet at a barrier again, then each rank calls ps_peer_sum on its own
+ * staging buffer: out [ceil(F/world)][N][P] = the complete gradient of the frames it owns (f = my_rank + world*k).
  */
 int ps_backward_peer(ps_ctx *ctx, ps_saved *saved, const float *params, const float *viewmats, const float *Ks,
-                     const float *background, const float *d_rgb, const float *d_alpha, float *const *d_params_ranks,
-                     const int32_t *frame_owner, void *stream);
+                     const float *background, const float *d_rgb, const float *d_alpha, float *const *stage_ranks,
+                     int my_rank, int world, void *stream);
+int ps_peer_sum(ps_ctx *ctx, const float *stage_local, int world, size_t n_per_slot, float *out, void *stream);
 
 int ps_saved_info_get(const ps_saved *saved, ps_saved_info *out);
 /* Copy one tap (PS_TAP_*) into dst (device or host pointer), at most `bytes`; waits on the stream. */

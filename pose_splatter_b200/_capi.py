@@ -15,7 +15,7 @@ TAPS = dict(isect_keys=1, flatten_ids=2, tile_offsets=3, last_ids=4, tiles_touch
 
 LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 
-EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy", "ps_forward", "ps_forward_rgba8", "ps_backward", "ps_backward_peer",
+EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy", "ps_forward", "ps_forward_rgba8", "ps_backward", "ps_backward_peer", "ps_peer_sum",
            "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
            "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe")
 
@@ -62,7 +62,8 @@ def load() -> ctypes.CDLL:
     lib.ps_forward.argtypes = [vp, ctypes.POINTER(RenderDesc), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp]
     lib.ps_forward_rgba8.argtypes = [vp, ctypes.POINTER(RenderDesc), vp, vp, vp, vp, vp, vp, vp]
     lib.ps_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.ps_backward_peer.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ps_backward_peer.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ip, ip, vp]
+    lib.ps_peer_sum.argtypes = [vp, vp, ip, ctypes.c_size_t, vp, vp]
     lib.ps_saved_info_get.argtypes = [vp, ctypes.POINTER(SavedInfo)]
     lib.ps_saved_copy.argtypes = [vp, vp, ip, vp, ctypes.c_size_t, vp]
     lib.ps_saved_release.argtypes = [vp, vp, vp]

@@ -134,14 +134,22 @@ def _prep(t, dtype, dev):
     return t.detach().to(device=dev, dtype=dtype).contiguous()
 
 
-def backward_peer_raw(saved: SavedForward, params, viewmats, Ks, background, d_rgb, d_alpha, rank_ptrs, frame_owner):
-    """ps_backward_peer: rows are added into the d_params buffer of each frame's owner rank (peer memory).
-    rank_ptrs: int64 device tensor [world] of buffer addresses; frame_owner: int32 device tensor [F]."""
+def backward_peer_raw(saved: SavedForward, params, viewmats, Ks, background, d_rgb, d_alpha, rank_ptrs, my_rank, world):
+    """ps_backward_peer: finished rows are pushed into the staging buffer of each frame's owner rank (peer memory).
+    rank_ptrs: int64 device tensor [world] holding every rank's staging-buffer address."""
     dev = params.device
     _capi.check(_capi.load().ps_backward_peer(_capi.context(dev), saved.handle, _capi.ptr(params), _capi.ptr(viewmats),
                                               _capi.ptr(Ks), _capi.ptr(background), _capi.ptr(d_rgb), _capi.ptr(d_alpha),
-                                              _capi.ptr(rank_ptrs), _capi.ptr(frame_owner), _capi.stream_ptr(dev)),
+                                              _capi.ptr(rank_ptrs), int(my_rank), int(world), _capi.stream_ptr(dev)),
                 "ps_backward_peer")
+
+
+def peer_sum_raw(stage: torch.Tensor, out: torch.Tensor):
+    """out [Fo,N,P] = sum over the world slots of this rank's staging buffer [world,Fo,N,P]."""
+    dev = stage.device
+    _capi.check(_capi.load().ps_peer_sum(_capi.context(dev), _capi.ptr(stage), int(stage.shape[0]), out.numel(), _capi.ptr(out),
+                                         _capi.stream_ptr(dev)), "ps_peer_sum")
+    return out
 
 
 class _RenderViews(torch.autograd.Function):

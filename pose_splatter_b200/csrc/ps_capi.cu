@@ -400,7 +400,7 @@ int ps_forward_rgba8(ps_ctx *ctx, const ps_render_desc *d, const float *params, 
 
 static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const float *viewmats, const float *Ks,
                          const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
-                         float *const *peers, const int32_t *owner, void *stream)
+                         float *const *peers, int my_rank, int world, void *stream)
 {
     if (!ctx || !sv) return fail(1, "ps_backward: NULL context or saved state");
     const PsGeometry &g = sv->g;
@@ -417,7 +417,7 @@ static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const f
     }
     if (!sv->blast || !sv->t_pen || !sv->frame_off) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
     if (!d_rgb || !d_alpha || !params || !background) return fail(1, "ps_backward: NULL buffer");
-    if (peers && !owner) return fail(1, "ps_backward_peer: NULL frame_owner");
+    if (peers && (world < 1 || my_rank < 0 || my_rank >= world)) return fail(1, "ps_backward_peer: rank %d of %d", my_rank, world);
     float *acc = nullptr;
     PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE, s));
     int rc = 0;
@@ -427,7 +427,7 @@ static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const f
         { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc, s); }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
-        { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, sv->frame_off, sv->frame_views, viewmats, Ks, sv->t, acc, d_params, peers, owner, s); }
+        { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, sv->frame_off, sv->frame_views, viewmats, Ks, sv->t, acc, d_params, peers, my_rank, world, s); }
         if (n < 0) { rc = fail(3, "ps_backward: project_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
     } while (0);
@@ -440,15 +440,25 @@ int ps_backward(ps_ctx *ctx, ps_saved *sv, const float *params, const int32_t *v
                 void *stream)
 {
     (void)view_frame; // the forward saved the views of every frame
-    return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, d_params, nullptr, nullptr, stream);
+    return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, d_params, nullptr, 0, 1, stream);
 }
 
 int ps_backward_peer(ps_ctx *ctx, ps_saved *sv, const float *params, const float *viewmats, const float *Ks,
-                     const float *background, const float *d_rgb, const float *d_alpha, float *const *d_params_ranks,
-                     const int32_t *frame_owner, void *stream)
+                     const float *background, const float *d_rgb, const float *d_alpha, float *const *stage_ranks,
+                     int my_rank, int world, void *stream)
 {
-    if (!d_params_ranks) return fail(1, "ps_backward_peer: NULL d_params_ranks");
-    return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, nullptr, d_params_ranks, frame_owner, stream);
+    if (!stage_ranks) return fail(1, "ps_backward_peer: NULL stage_ranks");
+    if (sv && (sv->M == 0 || (size_t)sv->g.V * sv->g.N == 0))
+        return fail(1, "ps_backward_peer: nothing was rendered by this rank; push zeros with a regular backward instead");
+    return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, nullptr, stage_ranks, my_rank, world, stream);
+}
+
+int ps_peer_sum(ps_ctx *ctx, const float *stage_local, int world, size_t n_per_slot, float *out, void *stream)
+{
+    if (!ctx || !stage_local || !out || world < 1) return fail(1, "ps_peer_sum: bad argument");
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_LAUNCH(ctx, ps_launch_peer_sum(stage_local, world, n_per_slot, out, (cudaStream_t)stream));
+    return 0;
 }
 
 int ps_saved_info_get(const ps_saved *sv, ps_saved_info *out)

@@ -53,10 +53,12 @@ int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *v
 // view_frame [V] -> CSR (frame_off [F+1], frame_views [V]); cursor [F] is scratch
 int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t *frame_off, int32_t *cursor,
                         int32_t *frame_views, cudaStream_t s);
-// peers == nullptr: rows stored into d_params; else rows added into peers[owner[frame]] (device array of base pointers)
+// peers == nullptr: rows stored into d_params; else rows pushed into slot [my_rank][frame / world] of the staging
+// buffer of rank frame % world (peers = device array of the ranks' staging base pointers)
 int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *frame_off, const int32_t *frame_views,
                           const float *viewmats, const float *Ks, const PsTable &t, const float *acc, float *d_params,
-                          float *const *peers, const int32_t *owner, cudaStream_t s);
+                          float *const *peers, int my_rank, int world, cudaStream_t s);
+int ps_launch_peer_sum(const float *stage, int world, size_t n, float *out, cudaStream_t s);
 
 // binning (ps_bin.cu)
 size_t ps_rank_scratch_elems(const PsGeometry &g); // uint32 elements of global scratch the ranking needs (0 if it fits smem)

@@ -222,27 +222,24 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
     for (int k = 0; k < P; ++k) out[k] += o[k];
 }
 
-__device__ __forceinline__ void red_add_v2(float *addr, float a, float b)
-{
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
 // One thread per (frame, Gaussian): loops over the views of the frame (CSR frame_off / frame_views built by the
 // forward), sums their gradients in registers and writes the row ONCE.
 //   peers == nullptr : plain stores into d_params (no atomics, no memset: rows without gradient get zeros)
-//   peers != nullptr : K8' fused gradient reduce -- the row is added with red.global.add.v2.f32 straight into the
-//                      d_params buffer of the rank that owns the frame (peers[owner[frame]]: local memory, or a
-//                      peer GPU's over NVLink), so the cross-GPU sum needs no separate collective or staging copy.
-//                      The owners zero their buffers and all ranks meet at a barrier before and after (host side).
+//   peers != nullptr : K8' fused gradient exchange.  Frame f is owned by rank f % world.  The CTA's 256 finished
+//                      rows are staged in shared memory and pushed with coalesced 8-byte stores straight into the
+//                      owner's staging buffer, slot [my_rank][f / world] (local memory, or a peer GPU's over
+//                      NVLink): the transfer of one block overlaps the arithmetic of the next, no atomics, no
+//                      collective launch.  After a barrier the owner adds its `world` slots (ps_peer_sum).
 template <int MODE>
 __global__ void __launch_bounds__(PS_PROJ_BLOCK, 3)
 project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ frame_off,
                    const int32_t *__restrict__ frame_views, const float *__restrict__ viewmats,
                    const float *__restrict__ Ks, PsTable t, const float *__restrict__ acc, float *__restrict__ d_params,
-                   float *const *__restrict__ peers, const int32_t *__restrict__ owner)
+                   float *const *__restrict__ peers, int my_rank, int world)
 {
     constexpr int P = (MODE == PS_MODE_3D) ? 14 : 9;
     __shared__ float s_cam[25];
+    __shared__ __align__(16) float s_out[PS_PROJ_BLOCK * P]; // peers mode: the CTA's rows, pushed out coalesced
     const int frame = blockIdx.y;
     const int gi = blockIdx.x * PS_PROJ_BLOCK + threadIdx.x;
     const bool live = gi < g.N;
@@ -275,10 +272,9 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
         if (!any) continue;
         project_bwd_row<MODE>(g, t, idx, r, s_cam, a, out);
     }
-    if (!live) return;
-    const size_t off = ((size_t)frame * g.N + gi) * P;
     if (peers == nullptr) {
-        float *d = d_params + off;
+        if (!live) return;
+        float *d = d_params + ((size_t)frame * g.N + gi) * P;
         if (MODE == PS_MODE_3D) { // 56-byte rows: 8-byte aligned
 #pragma unroll
             for (int k = 0; k < P; k += 2) *reinterpret_cast<float2 *>(d + k) = make_float2(out[k], out[k + 1]);
@@ -286,20 +282,34 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
 #pragma unroll
             for (int k = 0; k < P; ++k) d[k] = out[k];
         }
-    } else {
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < P; ++k) any = any || (out[k] != 0.0f);
-        if (!any) return;
-        float *d = peers[owner[frame]] + off;
-        if (MODE == PS_MODE_3D) {
-#pragma unroll
-            for (int k = 0; k < P; k += 2) red_add_v2(d + k, out[k], out[k + 1]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < P; ++k) atomicAdd(d + k, out[k]);
-        }
+        return;
     }
+    // push the block's rows (zeros included: every slot is fully rewritten every step, nothing to clear)
+#pragma unroll
+    for (int k = 0; k < P; ++k) s_out[threadIdx.x * P + k] = out[k];
+    __syncthreads();
+    const int g0 = blockIdx.x * PS_PROJ_BLOCK;
+    const int n_rows = min(PS_PROJ_BLOCK, g.N - g0);
+    const int frames_per_rank = (g.F + world - 1) / world;
+    float *dst = peers[frame % world] + (((size_t)my_rank * frames_per_rank + frame / world) * g.N + g0) * P;
+    const int n_float = n_rows * P;
+    if (((reinterpret_cast<uintptr_t>(dst) & 7u) == 0) && (n_float & 1) == 0) {
+        float2 *d2 = reinterpret_cast<float2 *>(dst);
+        const float2 *s2 = reinterpret_cast<const float2 *>(s_out);
+        for (int i = threadIdx.x; i < (n_float >> 1); i += PS_PROJ_BLOCK) d2[i] = s2[i];
+    } else {
+        for (int i = threadIdx.x; i < n_float; i += PS_PROJ_BLOCK) dst[i] = s_out[i];
+    }
+}
+
+// out[i] = sum over the `world` slots of the local staging buffer (the gradients pushed by every rank)
+__global__ void __launch_bounds__(256) peer_sum_kernel(const float *__restrict__ stage, int world, size_t n, float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.0f;
+    for (int r = 0; r < world; ++r) acc += stage[(size_t)r * n + i];
+    out[i] = acc;
 }
 
 // view -> frame map to CSR (views of every frame): one CTA; order inside a frame is arbitrary
@@ -395,14 +405,21 @@ int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t 
 
 int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *frame_off, const int32_t *frame_views,
                           const float *viewmats, const float *Ks, const PsTable &t, const float *acc, float *d_params,
-                          float *const *peers, const int32_t *owner, cudaStream_t s)
+                          float *const *peers, int my_rank, int world, cudaStream_t s)
 {
     if (g.N == 0 || g.F == 0) return 0;
     dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.F);
     if (g.mode == PS_MODE_3D)
-        project_bwd_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, owner);
+        project_bwd_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, my_rank, world);
     else
-        project_bwd_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, owner);
+        project_bwd_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, my_rank, world);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ps_launch_peer_sum(const float *stage, int world, size_t n, float *out, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    peer_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(stage, world, n, out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -41,33 +41,41 @@ def reduce_frame_grads(d_params: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class PeerGradBuffers:
-    """Fused cross-GPU gradient sum (K8'): one d_params buffer [F,N,P] per rank, allocated as symmetric memory and
-    mapped into every process of the node (NVLink peer access).  With it the projection-backward kernel adds each
-    finished row straight into the buffer of the rank that owns the frame (ps_backward_peer) -- no all-reduce, no
-    staging copy.  frame f is owned by rank `f % world`.
+    """Fused cross-GPU gradient exchange (K8').  Frame f is owned by rank f % world.  Every rank holds a staging
+    buffer [world, ceil(F/world), N, P] in symmetric memory, mapped into every process of the node (NVLink peer
+    access).  The projection-backward kernel pushes each finished block of rows straight into slot
+    [my rank][f // world] of the owner's buffer (ps_backward_peer) -- no all-reduce, no atomics; after a barrier the
+    owner adds its `world` slots.
 
         bufs = PeerGradBuffers((F, N, P), device)
-        bufs.begin()                      # zero own buffer, barrier
-        batched.backward_peer_raw(saved, params, viewmats, Ks, bg, d_rgb, d_alpha, bufs.rank_ptrs, bufs.frame_owner)
-        bufs.end()                        # barrier: bufs.buf[f] is complete for every owned frame f
+        bufs.begin()                                   # barrier: last step's staging has been consumed
+        batched.backward_peer_raw(saved, params, viewmats, Ks, bg, d_rgb, d_alpha, bufs.rank_ptrs, bufs.rank, bufs.world)
+        grads = bufs.end()                             # barrier + local sum: [len(bufs.owned), N, P] for frames bufs.owned
     """
 
     def __init__(self, shape, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
+        from . import batched
+        self._batched = batched
         group = group or dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.buf = symm_mem.empty(*shape, dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.buf, group)
+        F, N, P = shape
+        self.frames_per_rank = (F + self.world - 1) // self.world
+        self.stage = symm_mem.empty(self.world, self.frames_per_rank, N, P, dtype=torch.float32, device=device)
+        self.stage.zero_()
+        self.handle = symm_mem.rendezvous(self.stage, group)
         self.rank_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
-        self.frame_owner = (torch.arange(shape[0], device=device) % self.world).to(torch.int32)
-        self.owned = [f for f in range(shape[0]) if f % self.world == self.rank]
+        self.owned = [f for f in range(F) if f % self.world == self.rank]
+        self.out = torch.empty(self.frames_per_rank, N, P, dtype=torch.float32, device=device)
+        self.handle.barrier()
 
     def begin(self):
-        self.buf.zero_()
         self.handle.barrier()
 
-    def end(self):
+    def end(self) -> torch.Tensor:
         self.handle.barrier()
+        self._batched.peer_sum_raw(self.stage, self.out)
+        return self.out[:len(self.owned)]
 
 
 def max_over_ranks(value: float, device) -> float:

@@ -43,18 +43,17 @@ def _worker(rank, world, port, out_dir):
         _, _, _, sv = batched.forward_raw("3d", p, vf, vm, Ks, bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD)
         want = batched.backward_raw(sv, p, vf, vm, Ks, bg, w_rgb, w_a)
         psd.reduce_frame_grads(want)
-        # fused: rows added straight into the owner's buffer over peer memory
+        # fused: rows pushed straight into the owner's staging buffer over peer memory
         peer = psd.PeerGradBuffers(tuple(p.shape), dev)
         for _ in range(2):  # twice: the buffers are reused step after step
             peer.begin()
-            batched.backward_peer_raw(sv, p, vm, Ks, bg, w_rgb, w_a, peer.rank_ptrs, peer.frame_owner)
-            peer.end()
+            batched.backward_peer_raw(sv, p, vm, Ks, bg, w_rgb, w_a, peer.rank_ptrs, peer.rank, peer.world)
+            got = peer.end()
         torch.cuda.synchronize()
-        got = peer.buf
         errs = []
-        for f in peer.owned:
+        for k, f in enumerate(peer.owned):
             scale = want[f].abs().amax(0).clamp_min(1e-20)
-            errs.append(float(((got[f] - want[f]).abs().amax(0) / scale).max()))
+            errs.append(float(((got[k] - want[f]).abs().amax(0) / scale).max()))
         np.save(os.path.join(out_dir, f"err{rank}.npy"), np.array(errs + [len(peer.owned)]))
         sv.release()
     finally:
