@@ -266,8 +266,9 @@ scan_spine_kernel(long long *__restrict__ chunk_sum, int n_chunks, int32_t *__re
     if (tid == 0) {
         const long long total = s_carry;
         offsets[T] = (int32_t)(total > 0x7fffffffLL ? 0x7fffffffLL : total);
-        mailbox[0] = total;
+        mailbox[0] = total; // mapped host memory: visible to the host once the stream has drained
         mailbox[1] = cls[3 * PS_N_CLASSES];
+        __threadfence_system();
         int r = 0;
         for (int c = PS_N_CLASSES - 1; c >= 0; --c) {
             cls[c] = r;

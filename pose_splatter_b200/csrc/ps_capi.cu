@@ -145,7 +145,10 @@ struct PsSpan { int stage; cudaEvent_t a, b; };
 struct ps_ctx {
     int device;
     int64_t launches;
-    int64_t *h_total; // pinned mailbox: [0] = M, [1] = number of non-empty lists
+    // mailbox in mapped pinned host memory: the scan kernel stores {M, number of non-empty lists} straight into it
+    // (h_total = host view, d_total = device view of the same words).  No copy-engine transfer: a 16-byte memcpy
+    // would queue behind whatever bulk device->host copy the application has in flight on another stream.
+    volatile int64_t *h_total;
     int64_t *d_total;
     unsigned long long *d_stats; // [4] pair counters (PS_FLAG_RASTER_STATS)
     bool profiling;
@@ -215,8 +218,8 @@ int ps_ctx_create(int device, ps_ctx **out)
     c->launches = 0;
     c->profiling = false;
     for (int i = 0; i < PS_N_STAGES; ++i) { c->stage_ms[i] = 0.0; c->stage_calls[i] = 0; }
-    PS_CUDA(cudaMallocHost((void **)&c->h_total, 2 * sizeof(int64_t)));
-    PS_CUDA(cudaMalloc((void **)&c->d_total, 2 * sizeof(int64_t)));
+    PS_CUDA(cudaHostAlloc((void **)&c->h_total, 2 * sizeof(int64_t), cudaHostAllocMapped));
+    PS_CUDA(cudaHostGetDevicePointer((void **)&c->d_total, (void *)c->h_total, 0));
     PS_CUDA(cudaMalloc((void **)&c->d_stats, 4 * sizeof(unsigned long long)));
     PS_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
     *out = c;
@@ -227,8 +230,7 @@ int ps_ctx_destroy(ps_ctx *ctx)
 {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    cudaFreeHost(ctx->h_total);
-    cudaFree(ctx->d_total);
+    cudaFreeHost((void *)ctx->h_total);
     cudaFree(ctx->d_stats);
     for (auto &sp : ctx->pending) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->spare) cudaEventDestroy(e);
@@ -326,7 +328,6 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
                 PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, s));
             }
             { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, ctx->d_total, s)); }
-            PS_TRY_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the lists
             sv->M = ctx->h_total[0];
             sv->n_work = (int)ctx->h_total[1];
