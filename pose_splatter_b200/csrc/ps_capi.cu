@@ -420,12 +420,12 @@ static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const f
     if (!d_rgb || !d_alpha || !params || !background) return fail(1, "ps_backward: NULL buffer");
     if (peers && (world < 1 || my_rank < 0 || my_rank >= world)) return fail(1, "ps_backward_peer: rank %d of %d", my_rank, world);
     float *acc = nullptr;
-    PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE, s));
+    PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE + 4, s)); // + the rasterizer's task counter, zeroed with the rows
     int rc = 0;
     do {
-        if (cudaMemsetAsync(acc, 0, VN * PS_ACC_STRIDE * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
+        if (cudaMemsetAsync(acc, 0, (VN * PS_ACC_STRIDE + 4) * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
         int n;
-        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc, s); }
+        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc, reinterpret_cast<unsigned *>(acc + VN * PS_ACC_STRIDE), s); }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
         { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, sv->frame_off, sv->frame_views, viewmats, Ks, sv->t, acc, d_params, peers, my_rank, world, s); }

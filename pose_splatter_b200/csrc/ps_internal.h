@@ -82,7 +82,7 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
                          uint32_t *rgba8, unsigned long long *stats, cudaStream_t s);
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
-                         cudaStream_t s);
+                         unsigned *next_task /* zeroed by the caller: the persistent warps' task counter */, cudaStream_t s);
 
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);
 int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s);

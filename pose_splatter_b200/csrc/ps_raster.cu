@@ -24,6 +24,7 @@
 // torch element-wise loop src/gaussian_renderer.py:379-425 plus its autograd.
 #include "ps_contract.cuh"
 #include "ps_internal.h"
+#include <cstdlib>
 
 namespace {
 
@@ -44,12 +45,13 @@ struct BlockCtx {
     bool inside;
 };
 
-__device__ __forceinline__ BlockCtx block_ctx(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist,
-                                              const uint32_t *blist, const int32_t *bcount)
+// task = 8 * work-list item + block (0..7: x half = blk & 1, y quarter = blk >> 1)
+__device__ __forceinline__ BlockCtx block_ctx_task(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist,
+                                                   const uint32_t *blist, const int32_t *bcount, unsigned task)
 {
     BlockCtx c;
-    const int item = blockIdx.x / TASKS_PER_TILE;
-    const int blk = (blockIdx.x % TASKS_PER_TILE) * WPC + (threadIdx.x >> 5); // 0..7: x half = blk & 1, y quarter = blk >> 1
+    const int item = (int)(task >> 3);
+    const int blk = (int)(task & 7u);
     const int lin = worklist[item]; // non-empty (view, tile) lists, longest size class first
     c.view = lin / g.n_tiles;
     const int tile = lin - c.view * g.n_tiles;
@@ -65,6 +67,12 @@ __device__ __forceinline__ BlockCtx block_ctx(const PsGeometry &g, const int32_t
     c.py = c.by + (lane >> 3);
     c.inside = c.px < g.W && c.py < g.H;
     return c;
+}
+template <int W> // W = warps (pixel blocks) per CTA; CTA b handles blocks (b % (8 / W)) * W ... of item b / (8 / W)
+__device__ __forceinline__ BlockCtx block_ctx(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist,
+                                              const uint32_t *blist, const int32_t *bcount)
+{
+    return block_ctx_task(g, offsets, worklist, blist, bcount, blockIdx.x * W + (threadIdx.x >> 5));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,8 +162,8 @@ __device__ __forceinline__ uint32_t cull_chunk(const Ring &q, int st, int lane, 
     return __ballot_sync(FULL, hit);
 }
 
-template <int MODE, bool STATS>
-__global__ void __launch_bounds__(RT_THREADS)
+template <int MODE, bool STATS, int W>
+__global__ void __launch_bounds__(W * 32)
 raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const float *__restrict__ background,
                   float *__restrict__ rgb, float *__restrict__ alpha,
@@ -163,9 +171,9 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount,
                   uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats)
 {
-    __shared__ float4 s_a[WPC][NS][CH], s_b[WPC][NS][CH], s_c[WPC][NS][CH];
-    __shared__ uint32_t s_pos[WPC][NS][CH];
-    const BlockCtx c = block_ctx(g, offsets, worklist, blist, bcount);
+    __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
+    __shared__ uint32_t s_pos[W][NS][CH];
+    const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool done = !c.inside;
     if (__all_sync(FULL, done)) return; // block entirely outside the image
@@ -360,7 +368,7 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
 {
     __shared__ float4 s_a[WPC][NS][CH], s_b[WPC][NS][CH], s_c[WPC][NS][CH];
     __shared__ uint32_t s_id[WPC][NS][CH];
-    const BlockCtx c = block_ctx(g, offsets, worklist, blist, bcount);
+    const BlockCtx c = block_ctx<WPC>(g, offsets, worklist, blist, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int my_last = 0; // 1 + index in the block list of this pixel's last contributor (saved by the forward)
     float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
@@ -490,6 +498,262 @@ raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         __syncwarp(); // every lane is finished with stage st before step r + 3 is copied into it
     }
     cp_async_wait_group<0>();
+}
+
+// ---- backward v5: two phases per group of SL contributing entries --------------------------------------------------
+// Phase A (lane = pixel) replays the block list in reverse exactly like v4 but keeps only the two sequential
+// per-pixel quantities: for every contributing (pixel, entry) pair it stores (alpha*T, dL/dsigma) [3D] /
+// (g*T, dL/dq) [2D] into a warp-private pair table and hands the entry a slot (its record and accumulator row are
+// copied to the slot by one lane; the slot's two owner lanes -- lane & 15 == slot, one per 16-pixel half of the
+// block -- keep the ballot of its contributing pixels).  Two survivors are in flight per iteration (independent
+// sigma / exp chains), their sequential updates are applied in list order.
+// Phase B (lane = entry half) walks the set bits of its own mask: 3 colour FMAs + six moments
+// (sum s, s dx, s dy, s dx^2, s dx dy, s dy^2) per contributing pair, accumulated in registers -- no warp reduction,
+// and no gradient arithmetic at all for the (pixel, entry) pairs that do not contribute (84 % of them at c2).  The
+// nine gradient sums of v4 are linear in these moments and are formed once per entry; rows leave through a
+// shared-memory transpose so that the red.global.add of one entry's nine floats stay adjacent.
+constexpr int SL = 16;              // slots (entries) per phase-B group
+constexpr int PAIR_STRIDE = 33;     // float2 per slot row (32 pixels + 1 pad)
+
+// one region, two uses that never overlap in time (warp barriers in between)
+union PairTable {
+    float2 pair[SL * PAIR_STRIDE];
+    float out[32 * 9];
+};
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MODE, int BW> // BW = warps (independent pixel blocks) per CTA
+__global__ void __launch_bounds__(BW * 32, 20 / BW)
+raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
+                   const int32_t *__restrict__ worklist, const float *__restrict__ background, const int32_t *__restrict__ last,
+                   const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
+                   const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount, float *__restrict__ acc,
+                   unsigned n_tasks, unsigned *__restrict__ next_task)
+{
+    __shared__ float4 s_a[BW][NS][CH], s_b[BW][NS][CH], s_c[BW][NS][CH];
+    __shared__ uint32_t s_id[BW][NS][CH];
+    __shared__ PairTable s_pair[BW];                 // phase A -> B; reused as the 32 x 9 output transpose
+    __shared__ float4 s_w[BW][32];                  // d_rgb of the block's pixels
+    __shared__ float4 s_sr0[BW][SL], s_sr1[BW][SL]; // rec0 / rec1 of every slot's entry
+    __shared__ uint32_t s_sid[BW][SL];              // accumulator row (view * N + Gaussian) of every slot
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // persistent warps: every warp pulls (tile, block) tasks off one counter, in work-list order (longest size class
+    // first), so a warp slot is never idle while work remains (no CTA pairing, no launch gaps)
+    for (;;) {
+    unsigned task = 0;
+    if (lane == 0) task = atomicAdd(next_task, 1u);
+    task = __shfl_sync(FULL, task, 0);
+    if (task >= n_tasks) break;
+    const BlockCtx c = block_ctx_task(g, offsets, worklist, blist, bcount, task);
+    int my_last = 0;
+    float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
+    if (c.inside) {
+        const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
+        my_last = last[p];
+        if (my_last > 0) {
+            Tcur = t_pen[p];
+            w0 = d_rgb[3 * p]; w1 = d_rgb[3 * p + 1]; w2 = d_rgb[3 * p + 2];
+            S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
+        }
+    }
+    int wmax = my_last;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
+    if (wmax <= 0) continue;
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid], nullptr };
+    uint32_t (*qid)[CH] = s_id[wid];
+    float2 *pairs = s_pair[wid].pair;
+    float *outt = s_pair[wid].out;
+    float4 *sr0 = s_sr0[wid], *sr1 = s_sr1[wid];
+    uint32_t *sid = s_sid[wid];
+    s_w[wid][lane] = make_float4(w0, w1, w2, 0.0f);
+    const int len = wmax;
+    const int nchunks = (len + CH - 1) / CH;
+    const uint32_t *list = vals + c.start;
+    auto issue = [&](int r, uint32_t id) {
+        const int cj = nchunks - 1 - r;
+        if (cj >= 0 && cj * CH + lane < len) {
+            const int st = r % NS;
+            qid[st][lane] = id;
+            const float4 *src = PS_REC(t, id, 0);
+            cp_async16(&q.a[st][lane], src);
+            cp_async16(&q.b[st][lane], src + 1);
+            cp_async16(&q.c[st][lane], src + 2);
+        }
+        cp_async_commit();
+    };
+    auto fetch_pos = [&](int r) -> uint32_t {
+        const int cj = nchunks - 1 - r;
+        return (cj >= 0 && cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u;
+    };
+    uint32_t posn, posnn, idn;
+    {
+        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
+        posn = fetch_pos(2);
+        posnn = fetch_pos(3);
+        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
+        issue(0, i0);
+        issue(1, i1);
+        idn = __ldg(list + posn);
+    }
+    const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
+    const float pxf = (float)c.px + half, pyf = (float)c.py + half;
+    const float bxf = (float)c.bx + half, byf = (float)c.by + half;
+    const int slot_of_lane = lane & (SL - 1);
+    const int pbase = lane & 16; // first pixel of this lane's half of the block
+    uint32_t smask = 0;          // contributing pixels (of this lane's half) of the entry in slot `slot_of_lane`
+    int nslots = 0;
+
+    auto flush = [&]() {
+        __syncwarp(); // phase A's pair / slot stores are visible
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, ms = 0.0f, mx = 0.0f, my = 0.0f, mxx = 0.0f, mxy = 0.0f, myy = 0.0f;
+        uint32_t m = smask;
+        const float4 e0 = sr0[slot_of_lane], e1 = sr1[slot_of_lane];
+        const float sgx = e0.x - bxf, sgy = e0.y - byf; // mean relative to the block's first pixel centre
+        const float2 *prow = pairs + slot_of_lane * PAIR_STRIDE + pbase;
+        const float4 *wrow = s_w[wid] + pbase;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const float2 pr = prow[b];
+            const float4 w = wrow[b];
+            const int p = pbase + b;
+            // small integers -> float through the 2^23 mantissa trick (FP32 pipe instead of the conversion unit)
+            const float fx = __uint_as_float(0x4b000000u | (uint32_t)(p & 7)) - 8388608.0f;
+            const float fy = __uint_as_float(0x4b000000u | (uint32_t)(p >> 3)) - 8388608.0f;
+            a0 = fmaf(pr.x, w.x, a0); a1 = fmaf(pr.x, w.y, a1); a2 = fmaf(pr.x, w.z, a2);
+            float ex, ey;
+            if (MODE == PS_MODE_3D) {
+                ex = sgx - fx; ey = sgy - fy;                 // mean - pixel centre
+            } else {
+                const float dx = -(sgx - fx), dy = -(sgy - fy); // pixel - mean, rotated into the splat's axes
+                ex = fmaf(e1.y, dy, e1.x * dx);
+                ey = fmaf(e1.x, dy, -e1.y * dx);
+            }
+            const float tx = pr.y * ex, ty = pr.y * ey;
+            ms += pr.y; mx += tx; my += ty;
+            mxx = fmaf(tx, ex, mxx); mxy = fmaf(tx, ey, mxy); myy = fmaf(ty, ey, myy);
+        }
+        float v3, v4, v5, v6, v7, v8;
+        if (MODE == PS_MODE_3D) {
+            v3 = 0.5f * mxx; v4 = mxy; v5 = 0.5f * myy;
+            v6 = 2.0f * e1.x * mx + e1.y * my;
+            v7 = e1.y * mx + 2.0f * e1.z * my;
+            v8 = -ms * rcp_approx(e0.w); // sum of exp(-sigma) * v_alpha over the unclamped pairs = -(sum v_sigma) / o
+        } else {
+            v3 = 2.0f * e1.z * mx; v4 = 2.0f * e1.w * my;
+            v5 = 2.0f * (e1.z - e1.w) * mxy;
+            v6 = mxx; v7 = myy; v8 = ms;
+        }
+        __syncwarp(); // every lane has read its pairs: the table becomes the output transpose
+        float *o = outt + lane * 9;
+        o[0] = a0; o[1] = a1; o[2] = a2; o[3] = v3; o[4] = v4; o[5] = v5; o[6] = v6; o[7] = v7; o[8] = v8;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < (SL * 9 + 31) / 32; ++i) {
+            const int f = i * 32 + lane;
+            if (f < nslots * 9) {
+                const float val = outt[f] + outt[f + SL * 9]; // the entry's two halves
+                const int sl = f / 9;
+                if (val != 0.0f) atomicAdd(acc + (size_t)sid[sl] * PS_ACC_STRIDE + (f - sl * 9), val);
+            }
+        }
+        __syncwarp(); // before phase A writes pairs / slots again
+        smask = 0;
+        nslots = 0;
+    };
+    // hand the entry (ring stage st, index e) with contributor ballot cm a slot; pa / pb = this lane's pair
+    auto take_slot = [&](int st, int e, const float4 &r0, const float4 &r1, uint32_t cm, bool contrib, float pa, float pb) {
+        if (contrib) pairs[nslots * PAIR_STRIDE + lane] = make_float2(pa, pb);
+        if (lane == 0) { sr0[nslots] = r0; sr1[nslots] = r1; sid[nslots] = qid[st][e]; }
+        smask = (slot_of_lane == nslots) ? ((cm >> pbase) & 0xffffu) : smask;
+        ++nslots;
+    };
+
+    for (int r = 0; r < nchunks; ++r) {
+        issue(r + 2, idn);
+        posn = posnn;
+        idn = __ldg(list + posn);
+        posnn = fetch_pos(r + 4);
+        cp_async_wait_group<2>();
+        __syncwarp();
+        const int st = r % NS;
+        const int ci = nchunks - 1 - r;
+        const int first = ci * CH;
+        const uint32_t live = __ballot_sync(FULL, my_last > first);
+        uint32_t mask = cull_chunk<MODE>(q, st, lane, ci * CH + lane < len, c, live);
+        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        while (mask) {
+            if (nslots > SL - 2) flush(); // room for both survivors of this iteration
+            // two survivors in flight, ea (later in the list) is applied first
+            const int ea = 31 - __clz(mask);
+            mask &= ~(1u << ea);
+            const bool two = mask != 0;
+            const int eb = two ? 31 - __clz(mask) : ea;
+            mask &= ~(1u << eb);
+            const int posa = first + ea, posb = first + eb;
+            const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
+            float ga, gb; // alpha (3D) / g (2D) of the two pairs
+            bool ca, cb;  // contributes
+            float oea = 0.0f, oeb = 0.0f;
+            if (MODE == PS_MODE_3D) {
+                float dx, dy;
+                const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
+                const float sgb = ps_sigma3d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, pxf, pyf, &dx, &dy);
+                const bool canda = posa < my_last && sga >= 0.0f && sga <= r0a.z + THR_SLACK;
+                const bool candb = two && posb < my_last && sgb >= 0.0f && sgb <= r0b.z + THR_SLACK;
+                if (!__any_sync(FULL, canda || candb)) continue;
+                oea = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-sga, 0x1.715476p+0f)));
+                oeb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-sgb, 0x1.715476p+0f)));
+                ga = fminf(PS_ALPHA_MAX, oea);
+                gb = fminf(PS_ALPHA_MAX, oeb);
+                ca = canda && ga >= PS_ALPHA_MIN;
+                cb = candb && gb >= PS_ALPHA_MIN;
+            } else {
+                float dxr, dyr;
+                const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
+                const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
+                ca = posa < my_last && qa <= r0a.z;
+                cb = two && posb < my_last && qb <= r0b.z;
+                if (!__any_sync(FULL, ca || cb)) continue;
+                ga = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-qa, 0x1.715476p+0f)));
+                gb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-qb, 0x1.715476p+0f)));
+            }
+            const uint32_t cma = __ballot_sync(FULL, ca), cmb = __ballot_sync(FULL, cb);
+            if (!(cma | cmb)) continue;
+            const float4 r2a = q2[ea], r2b = q2[eb];
+            const float cwa = r2a.x * w0 + r2a.y * w1 + r2a.z * w2;
+            const float cwb = r2b.x * w0 + r2b.y * w1 + r2b.z * w2;
+            const float ia = rcp_approx(1.0f - ga), ib = rcp_approx(1.0f - gb); // 1 - g >= 1e-3 (3D) / > 0 for contributors
+            // entry a
+            const float Tba = (posa == my_last - 1) ? Tcur : Tcur * ia;
+            const float va = Tba * (cwa - S);          // dL/dalpha (3D) / dL/dg (2D)
+            const float paa = ga * Tba;
+            const float pba = (MODE == PS_MODE_3D) ? ((oea <= PS_ALPHA_MAX) ? -oea * va : 0.0f) : -ga * va;
+            Tcur = ca ? Tba : Tcur;
+            S = ca ? S + ga * (cwa - S) : S;
+            // entry b
+            const float Tbb = (posb == my_last - 1) ? Tcur : Tcur * ib;
+            const float vb = Tbb * (cwb - S);
+            const float pab = gb * Tbb;
+            const float pbb = (MODE == PS_MODE_3D) ? ((oeb <= PS_ALPHA_MAX) ? -oeb * vb : 0.0f) : -gb * vb;
+            Tcur = cb ? Tbb : Tcur;
+            S = cb ? S + gb * (cwb - S) : S;
+            if (cma) take_slot(st, ea, r0a, r1a, cma, ca, paa, pba);
+            if (cmb) take_slot(st, eb, r0b, r1b, cmb, cb, pab, pbb);
+        }
+        __syncwarp(); // every lane is finished with stage st before step r + 3 is copied into it
+    }
+    cp_async_wait_group<0>();
+    if (nslots) flush();
+    __syncwarp();
+    } // task loop
 }
 
 // Which of the eight 8x4 blocks of tile (tx, ty) can the splat contribute to?  `half` = 0.5 (3D pixel centres) or
@@ -624,10 +888,12 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
                          uint32_t *rgba8, unsigned long long *stats, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
-#define PS_FWD(MODE, ST) raster_fwd_kernel<MODE, ST><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, rgba8, stats)
-    if (g.mode == PS_MODE_3D) { if (stats) PS_FWD(PS_MODE_3D, true); else PS_FWD(PS_MODE_3D, false); }
-    else { if (stats) PS_FWD(PS_MODE_2D, true); else PS_FWD(PS_MODE_2D, false); }
+    static const bool w1 = getenv("PS_FWD_WPC1") != nullptr; // A/B switch: one warp per CTA
+#define PS_FWD(MODE, ST, W) raster_fwd_kernel<MODE, ST, W><<<(unsigned)n_work * (8 / W), W * 32, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, rgba8, stats)
+#define PS_FWD_W(MODE, ST) do { if (w1) PS_FWD(MODE, ST, 1); else PS_FWD(MODE, ST, WPC); } while (0)
+    if (g.mode == PS_MODE_3D) { if (stats) PS_FWD_W(PS_MODE_3D, true); else PS_FWD_W(PS_MODE_3D, false); }
+    else { if (stats) PS_FWD_W(PS_MODE_2D, true); else PS_FWD_W(PS_MODE_2D, false); }
+#undef PS_FWD_W
 #undef PS_FWD
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -662,10 +928,37 @@ int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s)
 
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
-                         cudaStream_t s)
+                         unsigned *next_task, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
     const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
+    static const bool use_v4 = getenv("PS_BWD_V4") != nullptr; // A/B switch for measurements: the warp-reduction backward
+    if (!use_v4) {
+        static const bool carve = [] { // 10 CTAs x 21.6 KB per SM need the full shared-memory carve-out
+            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            return true;
+        }();
+        (void)carve;
+        static int ctas_per_sm[2] = { 0, 0 }, n_sm = 0;
+        const int mi = g.mode == PS_MODE_3D ? 0 : 1;
+        if (!ctas_per_sm[mi]) {
+            int dev = 0, per = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (mi == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_3D, WPC>, RT_THREADS, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_2D, WPC>, RT_THREADS, 0);
+            ctas_per_sm[mi] = per > 0 ? per : 1;
+        }
+        const unsigned n_tasks = (unsigned)n_work * 8u;
+        const unsigned want = (n_tasks + WPC - 1) / WPC, cap = (unsigned)(n_sm * ctas_per_sm[mi]);
+        const unsigned pgrid = want < cap ? want : cap;
+        if (g.mode == PS_MODE_3D)
+            raster_bwd2_kernel<PS_MODE_3D, WPC><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, n_tasks, next_task);
+        else
+            raster_bwd2_kernel<PS_MODE_2D, WPC><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, n_tasks, next_task);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     if (g.mode == PS_MODE_3D)
         raster_bwd_kernel<PS_MODE_3D><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc);
     else
