@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 2
+#define PS_ABI_VERSION 3
 
 #define PS_MODE_2D 2 /* GaussianRenderer2D, rows of 9 floats  (src/gaussian_renderer.py:214-334) */
 #define PS_MODE_3D 3 /* GaussianRenderer3D, rows of 14 floats (src/gaussian_renderer.py:110-211) */
@@ -164,6 +164,23 @@ int ps_ctx_stage_times(ps_ctx *ctx, double *ms, int64_t *calls, int reset);
 int ps_ctx_raster_stats(ps_ctx *ctx, uint64_t *pairs, int reset, void *stream);
 /* FP32 FFMA micro-benchmark on this device: returns achieved TFLOP/s (2 flops per FMA) in *tflops. */
 int ps_fp32_peak_probe(ps_ctx *ctx, double *tflops, void *stream);
+
+/*
+ * The per-view training loss that follows render() in every training step, fused with its own backward
+ * (SURVEY.md 8f-f1).  Replaces scripts/training/train_script.py:30-36 (get_iou_loss) and :129-133 of the reference:
+ *   iou  = 1 - (sum(alpha*mask) + 1e-6) / (sum(alpha + mask - alpha*mask) + 1e-6)
+ *   ssim = ssim_lambda * (1 - SSIM(target_img, rgb))      torchmetrics StructuralSimilarityIndexMeasure(data_range=1.0)
+ *   img  = img_lambda * sum|target_img - rgb| / sum(mask)
+ * for V views at once, each view its own loss (the reference runs one view per step, batch size 1).
+ *   rgb [V,H,W,3], alpha [V,H,W]          what ps_forward wrote
+ *   target_img [V,3,H,W], target_mask [V,H,W]   as the reference's loader yields them (img[0, img_idx], mask[0, img_idx])
+ *   losses [V,3]                          (iou, ssim, img) per view
+ *   d_rgb [V,H,W,3], d_alpha [V,H,W]      gradient of sum_v (iou + ssim + img)_v: the cotangents ps_backward takes;
+ *                                         both NULL = losses only (validation, :39-66).  H, W >= 11.
+ */
+int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *rgb, const float *alpha,
+                 const float *target_img, const float *target_mask, float ssim_lambda, float img_lambda,
+                 float *losses, float *d_rgb, float *d_alpha, void *stream);
 
 /*
  * Device probe of the arithmetic contract (PSM-1): y[5][n] = exp, log(|x|+1e-30), sigmoid, sin, cos

@@ -597,4 +597,30 @@ int ps_math_probe(ps_ctx *ctx, const float *x, int n, float *y, void *stream)
     return 0;
 }
 
+int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *rgb, const float *alpha,
+                 const float *target_img, const float *target_mask, float ssim_lambda, float img_lambda,
+                 float *losses, float *d_rgb, float *d_alpha, void *stream)
+{
+    if (!ctx) return fail(1, "ps_view_loss: NULL context");
+    if (n_views < 0 || height < 0 || width < 0) return fail(1, "ps_view_loss: negative size");
+    if (n_views == 0) return 0;
+    if (height < 11 || width < 11) return fail(1, "ps_view_loss: the 11x11 SSIM window needs images of at least 11x11 pixels (got %dx%d)", width, height);
+    if (!rgb || !alpha || !target_img || !target_mask || !losses) return fail(1, "ps_view_loss: NULL buffer");
+    if ((d_rgb == nullptr) != (d_alpha == nullptr)) return fail(1, "ps_view_loss: d_rgb and d_alpha must be given together");
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    double *stats = nullptr;
+    float *adj = nullptr;
+    PS_CUDA(dev_alloc(&stats, (size_t)n_views * 8, s));
+    cudaError_t e = dev_alloc(&adj, (size_t)n_views * 9 * (size_t)height * width, s);
+    if (e != cudaSuccess) { dev_free(stats, s); return fail(2, "ps_view_loss: scratch allocation failed: %s", cudaGetErrorString(e)); }
+    const int n = ps_launch_view_loss(n_views, height, width, rgb, alpha, target_img, target_mask, ssim_lambda, img_lambda,
+                                      stats, adj, losses, d_rgb, d_alpha, s);
+    dev_free(adj, s);
+    dev_free(stats, s);
+    if (n < 0) return fail(3, "ps_view_loss: kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches += n;
+    return 0;
+}
+
 } // extern "C"

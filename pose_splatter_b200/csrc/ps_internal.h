@@ -84,5 +84,10 @@ int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
                          unsigned *next_task /* zeroed by the caller: the persistent warps' task counter */, cudaStream_t s);
 
+// per-view training loss + its gradient (ps_loss.cu); stats [V*8] doubles and adj [V*9*H*W] floats are scratch
+int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alpha, const float *timg, const float *mask,
+                        float ssim_lambda, float img_lambda, double *stats, float *adj, float *losses, float *d_rgb,
+                        float *d_alpha, cudaStream_t s);
+
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);
 int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s);
