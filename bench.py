@@ -452,6 +452,8 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         out["single_view"] = {"latency_ms_median": lat[len(lat) // 2], "latency_ms_min": lat[0],
                               "what": "one renderer.render(params[N,P], viewmat, K) + backward, host wall clock with a device "
                                       "synchronisation on both sides (launch / latency bound; the batched numbers are the headline)"}
+    if world == 1 and primary and not fwd_only and min(H, W) >= 11:
+        out["training_step"] = training_step(dev, devs, n_sets, mode, W, H, V, bg, max(3, min(steps, 5)))
     if world == 1 and primary and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         probe_vps, _ = cpu_views_per_second(wl, cores, cores, args.n)           # short probe sizes the sample
@@ -460,6 +462,96 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         out["cpu_baseline"] = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
                                "sample": f"{sample_views} views of the same workload (full N, full resolution, fwd+bwd), {dt:.1f} s on {cores} threads"}
     return out
+
+
+def training_step(dev, devs, n_sets, mode, W, H, V, bg, steps):
+    """render -> per-view loss (soft IoU + L1 + SSIM) -> backward, the reference's training step without
+    its networks (scripts/training/train_script.py:107-134), with the loss fused into one C-ABI call that also
+    emits the renderer's cotangents.  Beside it: the same loss written the reference's way (torch eager ops +
+    autograd) on the same B200, on a slice of the views."""
+    import torch
+    from pose_splatter_b200 import _capi, batched, losses
+    g = torch.Generator(device="cpu").manual_seed(11)
+    timg = torch.rand(V, 3, H, W, generator=g).to(dev)
+    tmask = (torch.rand(V, H, W, generator=g) > 0.5).float().to(dev)
+    sl, il = 1.0, 0.5
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    loss_ms = 0.0
+
+    def step(k, timed_loss=False):
+        nonlocal loss_ms
+        s = devs[k % n_sets]
+        rgb, alpha, _, saved = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H,
+                                                   _capi.FLAG_SAVE_FOR_BACKWARD)
+        if timed_loss:
+            ev[2].record()
+        parts, d_rgb, d_alpha = losses._launch(rgb, alpha, timg, tmask, sl, il, True)
+        if timed_loss:
+            ev[3].record()
+        d_params = batched.backward_raw(saved, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, d_rgb, d_alpha)
+        saved.release()
+        if timed_loss:
+            torch.cuda.synchronize()
+            loss_ms += ev[2].elapsed_time(ev[3])
+        return parts, d_params
+
+    for k in range(3):
+        step(k)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for k in range(steps):
+        step(k)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    for k in range(steps):
+        step(k, timed_loss=True)
+    loss_ms /= steps
+
+    # the reference's formulation on the same GPU: three eager torch graphs + autograd (torchmetrics' SSIM restated)
+    Vc = min(V, 96)
+    s = devs[0]
+    with torch.no_grad():
+        rgb, alpha, _, _ = batched.forward_raw(mode, s["params"], s["view_frame"], s["viewmats"], s["Ks"], bg, W, H, 0)
+    rgb, alpha = rgb[:Vc].clone(), alpha[:Vc].clone()
+    d = torch.arange(-5, 6, dtype=torch.float32, device=dev)
+    taps = torch.exp(-((d / 1.5) ** 2) / 2)
+    taps = taps / taps.sum()
+    k2d = torch.outer(taps, taps)[None, None].expand(3, 1, 11, 11).contiguous()
+
+    def eager():
+        r = rgb.requires_grad_(True)
+        a = alpha.requires_grad_(True)
+        q = r.permute(0, 3, 1, 2)
+        t, m = timg[:Vc], tmask[:Vc]
+        inter = (a * m).sum(dim=(-2, -1))
+        union = (a + m - a * m).sum(dim=(-2, -1))
+        iou = 1 - (inter + 1e-6) / (union + 1e-6)
+        stack = torch.cat([t, q, t * t, q * q, t * q])
+        o = torch.nn.functional.conv2d(stack, k2d, groups=3)
+        mp, mq, epp, eqq, epq = o.split(Vc)
+        spp, sqq, spq = torch.clamp(epp - mp * mp, min=0), torch.clamp(eqq - mq * mq, min=0), epq - mp * mq
+        smap = ((2 * mp * mq + 1e-4) * (2 * spq + 9e-4)) / ((mp * mp + mq * mq + 1e-4) * (spp + sqq + 9e-4))
+        ssim = sl * (1 - smap.mean(dim=(1, 2, 3)))
+        img = il * (t - q).abs().sum(dim=(1, 2, 3)) / m.sum(dim=(-2, -1))
+        (iou + ssim + img).sum().backward()
+        r.grad = a.grad = None
+
+    for _ in range(2):
+        eager()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(3):
+        eager()
+    ev[1].record()
+    torch.cuda.synchronize()
+    eager_ms = ev[0].elapsed_time(ev[1]) / 3 * (V / Vc)
+    return {"value": V / (ms * 1e-3), "unit": "views/s", "ms_per_step": ms, "views_per_step": V,
+            "loss_ms_per_step": loss_ms, "loss_algorithmic_gbs": V * H * W * 4 * (3 + 1 + 3 + 1 + 3 + 1) / (loss_ms * 1e-3) / 1e9,
+            "torch_eager_loss_ms_per_step": eager_ms,
+            "what": "render forward -> ps_view_loss (soft IoU + 0.5 * L1 / sum(mask) + 1.0 * (1 - SSIM), losses and "
+                    "d_rgb / d_alpha in one call) -> render backward, inputs resident; torch_eager = the same loss as "
+                    f"eager torch ops + autograd on this GPU, measured on {Vc} views and scaled to {V}"}
 
 
 if __name__ == "__main__":
