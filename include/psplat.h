@@ -183,6 +183,28 @@ int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *r
                  float *losses, float *d_rgb, float *d_alpha, void *stream);
 
 /*
+ * The parameter-head tail that produces the rows ps_forward takes, one thread per Gaussian.
+ * Replaces src/model.py:207-257 (activations of get_gaussian_params_from_volume_unified after the MLP) and, with
+ * pose != 0 in 3D mode, apply_pose_transform_3d :261-298 incl. quaternion_matrix_torch_batch :368-391 and
+ * quaternion_from_matrix_torch_batch :394-421 (a float64 torch.linalg.eigh per Gaussian, here a register-resident Jacobi).
+ *   net_out   [n,14]  3D: quats 4 | scales 3 | opacity 1 (unused) | colours 3 | delta_means 3   (the MLP output, :210-212)
+ *             [n, 9]  2D: means_2d 2 | scales_2d 2 | rotation 1 | colours 3 | opacity 1 (unused)         (:236-238)
+ *   probs_sel [n]     probs[mask]: sigmoid(volume[0] - mask_threshold) of the selected voxels            (:186-187)
+ *   grid_sel  [n,3]   self.grid.view(-1,3)[mask] (3D only)                                               (:223)
+ *   scale0    [1]     DEVICE pointer to the trainable self.scale                                         (:86,219)
+ *   voxel_size, prob_threshold, clip_lo/hi = self.voxel_size, self.prob_threshold, self.color_clip
+ *   pose, angle, p_3d_host[3] (HOST pointer)  yaw and translation of the frame (:275-280)
+ *   rows      [n,14|9] gaussian_params as render() takes them
+ * Backward: d_net_out [n,14|9], d_probs_sel [n], d_scale0 [1] (device, overwritten) from d_rows.
+ */
+int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, const float *grid_sel,
+                          const float *scale0, float voxel_size, float prob_threshold, float clip_lo, float clip_hi,
+                          int pose, double angle, const float *p_3d_host, float *rows, void *stream);
+int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, float voxel_size,
+                           float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *d_rows,
+                           float *d_net_out, float *d_probs_sel, float *d_scale0, void *stream);
+
+/*
  * Device probe of the arithmetic contract (PSM-1): y[5][n] = exp, log(|x|+1e-30), sigmoid, sin, cos
  * of x[n], computed by the same device functions the kernels use.  For the bit-exactness tests.
  */

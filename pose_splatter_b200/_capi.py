@@ -17,7 +17,8 @@ LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 
 EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy", "ps_forward", "ps_forward_rgba8", "ps_backward", "ps_backward_peer", "ps_peer_sum",
            "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
-           "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe", "ps_view_loss")
+           "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe", "ps_view_loss",
+           "ps_param_head_forward", "ps_param_head_backward")
 
 STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd", "blocks")
 FLAG_RASTER_STATS = 4
@@ -74,6 +75,9 @@ def load() -> ctypes.CDLL:
     lib.ps_ctx_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ip]
     lib.ps_ctx_raster_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ip, vp]
     lib.ps_fp32_peak_probe.argtypes = [vp, ctypes.POINTER(ctypes.c_double), vp]
+    cf, cd = ctypes.c_float, ctypes.c_double
+    lib.ps_param_head_forward.argtypes = [vp, ip, ip, vp, vp, vp, vp, cf, cf, cf, cf, ip, cd, ctypes.POINTER(cf), vp, vp]
+    lib.ps_param_head_backward.argtypes = [vp, ip, ip, vp, vp, cf, cf, cf, cf, ip, cd, vp, vp, vp, vp, vp]
     lib.ps_view_loss.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp]
     _lib = lib
     return lib

@@ -623,4 +623,38 @@ int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *r
     return 0;
 }
 
+static int head_check(ps_ctx *ctx, int mode, int n, const void *a, const void *b, const char *what)
+{
+    if (!ctx) return fail(1, "%s: NULL context", what);
+    if (mode != PS_MODE_2D && mode != PS_MODE_3D) return fail(1, "%s: unknown mode %d", what, mode);
+    if (n < 0) return fail(1, "%s: negative row count", what);
+    if (n > 0 && (!a || !b)) return fail(1, "%s: NULL buffer", what);
+    return 0;
+}
+
+int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, const float *grid_sel,
+                          const float *scale0, float voxel_size, float prob_threshold, float clip_lo, float clip_hi,
+                          int pose, double angle, const float *p_3d_host, float *rows, void *stream)
+{
+    if (int rc = head_check(ctx, mode, n, net_out, probs_sel, "ps_param_head_forward")) return rc;
+    if (n > 0 && (!rows || !scale0 || (mode == PS_MODE_3D && !grid_sel))) return fail(1, "ps_param_head_forward: NULL buffer");
+    if (pose && mode == PS_MODE_3D && !p_3d_host) return fail(1, "ps_param_head_forward: pose requested without p_3d");
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_LAUNCH(ctx, ps_launch_head_fwd(mode, n, net_out, probs_sel, grid_sel, scale0, voxel_size, prob_threshold, clip_lo, clip_hi,
+                                      pose, angle, p_3d_host, rows, (cudaStream_t)stream));
+    return 0;
+}
+
+int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, float voxel_size,
+                           float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *d_rows,
+                           float *d_net_out, float *d_probs_sel, float *d_scale0, void *stream)
+{
+    if (int rc = head_check(ctx, mode, n, net_out, probs_sel, "ps_param_head_backward")) return rc;
+    if (!d_scale0 || (n > 0 && (!d_rows || !d_net_out || !d_probs_sel))) return fail(1, "ps_param_head_backward: NULL buffer");
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_LAUNCH(ctx, ps_launch_head_bwd(mode, n, net_out, probs_sel, voxel_size, prob_threshold, clip_lo, clip_hi, pose, angle,
+                                      d_rows, d_net_out, d_probs_sel, d_scale0, (cudaStream_t)stream));
+    return 0;
+}
+
 } // extern "C"

@@ -1,0 +1,90 @@
+"""The parameter-head tail between the model's MLP and render(), on the GPU in one launch each way.
+
+Reference: src/model.py:207-257 (colour sigmoid + clip, log-scale offset `self.scale[0]`, opacity logit from the
+occupancy probability, `grid[mask] + 2 * voxel_size * tanh(delta_means)`) and apply_pose_transform_3d :261-298 (yaw +
+translation of the means; quaternion composition through a float64 `torch.linalg.eigh` per Gaussian, :368-421).
+`gaussian_rows` returns the `[N,14]` / `[N,9]` rows `render()` / `render_views` take and is differentiable w.r.t. the
+MLP output, the selected probabilities and the trainable scale offset.  Which voxels are selected (:185-204: threshold
+search and random subsampling) stays with the caller.  CUDA tensors only: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _capi
+
+
+def _call_forward(mode, net_out, probs_sel, grid_sel, scale, voxel_size, pt, clip, angle, p_3d):
+    dev = net_out.device
+    n, P = net_out.shape
+    rows = torch.empty((n, P), dtype=torch.float32, device=dev)
+    pose = angle is not None
+    p_host = (ctypes.c_float * 3)(*[float(x) for x in (p_3d if pose else (0.0, 0.0, 0.0))])
+    _capi.check(_capi.load().ps_param_head_forward(
+        _capi.context(dev), _capi.MODE_3D if mode == "3d" else _capi.MODE_2D, n, _capi.ptr(net_out), _capi.ptr(probs_sel),
+        _capi.ptr(grid_sel), _capi.ptr(scale), float(voxel_size), float(pt), float(clip[0]), float(clip[1]), int(pose),
+        float(angle) if pose else 0.0, p_host, _capi.ptr(rows), _capi.stream_ptr(dev)), "ps_param_head_forward")
+    return rows
+
+
+class _Head(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net_out, probs_sel, scale, grid_sel, mode, voxel_size, pt, clip, angle, p_3d):
+        net_c, probs_c = net_out.detach().float().contiguous(), probs_sel.detach().float().contiguous()
+        scale_c = scale.detach().float().reshape(1).contiguous()
+        grid_c = None if grid_sel is None else grid_sel.detach().float().contiguous()
+        rows = _call_forward(mode, net_c, probs_c, grid_c, scale_c, voxel_size, pt, clip, angle, p_3d)
+        ctx.save_for_backward(net_c, probs_c)
+        ctx.meta = (mode, voxel_size, pt, clip, angle, scale.shape)
+        return rows
+
+    @staticmethod
+    def backward(ctx, d_rows):
+        net_c, probs_c = ctx.saved_tensors
+        mode, voxel_size, pt, clip, angle, scale_shape = ctx.meta
+        dev = net_c.device
+        n = net_c.shape[0]
+        d_rows = d_rows.float().contiguous()
+        d_net, d_probs = torch.empty_like(net_c), torch.empty_like(probs_c)
+        d_scale = torch.empty(1, dtype=torch.float32, device=dev)
+        pose = angle is not None
+        _capi.check(_capi.load().ps_param_head_backward(
+            _capi.context(dev), _capi.MODE_3D if mode == "3d" else _capi.MODE_2D, n, _capi.ptr(net_c), _capi.ptr(probs_c),
+            float(voxel_size), float(pt), float(clip[0]), float(clip[1]), int(pose), float(angle) if pose else 0.0,
+            _capi.ptr(d_rows), _capi.ptr(d_net), _capi.ptr(d_probs), _capi.ptr(d_scale), _capi.stream_ptr(dev)),
+            "ps_param_head_backward")
+        return d_net, d_probs, d_scale.reshape(scale_shape), None, None, None, None, None, None, None
+
+
+def gaussian_rows(mode: str, net_out: torch.Tensor, probs_sel: torch.Tensor, scale: torch.Tensor, voxel_size: float,
+                  prob_threshold: float, grid_sel: torch.Tensor | None = None, color_clip=(0, 0.99), angle=None, p_3d=None):
+    """MLP output -> gaussian_params rows.
+
+    mode "3d": net_out [N,14] (quats 4 | scales 3 | opacity 1 | colours 3 | delta_means 3), grid_sel [N,3]; with `angle`
+    (float) and `p_3d` (3 floats) the pose transform of apply_pose_transform_3d is applied as well.
+    mode "2d": net_out [N,9] (means_2d 2 | scales_2d 2 | rotation 1 | colours 3 | opacity 1).
+    probs_sel [N] = probs[mask]; scale = the trainable `self.scale` ([1]).
+    """
+    mode = mode.lower()
+    if mode not in ("2d", "3d"):
+        raise ValueError(f"Unknown renderer mode: '{mode}'. Expected '2d' or '3d'.")
+    P = 14 if mode == "3d" else 9
+    if net_out.dim() != 2 or net_out.shape[1] != P:
+        raise ValueError(f"Expected {P} parameters per Gaussian, got {tuple(net_out.shape)}")
+    if net_out.device.type != "cuda":
+        raise RuntimeError(f"pose_splatter_b200.param_head runs on CUDA tensors only (got {net_out.device}); there is no CPU path")
+    if probs_sel.shape != (net_out.shape[0],):
+        raise ValueError(f"Expected probs_sel [{net_out.shape[0]}], got {tuple(probs_sel.shape)}")
+    if mode == "3d":
+        if grid_sel is None or grid_sel.shape != (net_out.shape[0], 3):
+            raise ValueError("3d mode needs grid_sel [N,3]")
+        if (angle is None) != (p_3d is None):
+            raise ValueError("angle and p_3d go together")
+        if p_3d is not None:
+            p_3d = [float(x) for x in (p_3d.detach().cpu().reshape(-1).tolist() if isinstance(p_3d, torch.Tensor) else p_3d)]
+    else:
+        grid_sel, angle, p_3d = None, None, None
+    return _Head.apply(net_out, probs_sel, scale, grid_sel, mode, float(voxel_size), float(prob_threshold),
+                       (float(color_clip[0]), float(color_clip[1])), None if angle is None else float(angle), p_3d)
