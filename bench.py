@@ -454,6 +454,8 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                       "synchronisation on both sides (launch / latency bound; the batched numbers are the headline)"}
     if world == 1 and primary and not fwd_only and min(H, W) >= 11:
         out["training_step"] = training_step(dev, devs, n_sets, mode, W, H, V, bg, max(3, min(steps, 5)))
+    if world == 1 and primary and not fwd_only and mode == "3d":
+        out["param_head"] = param_head_leg(dev, F, args.n or cfg["n"])
     if world == 1 and primary and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         probe_vps, _ = cpu_views_per_second(wl, cores, cores, args.n)           # short probe sizes the sample
@@ -462,6 +464,41 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         out["cpu_baseline"] = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
                                "sample": f"{sample_views} views of the same workload (full N, full resolution, fwd+bwd), {dt:.1f} s on {cores} threads"}
     return out
+
+
+def param_head_leg(dev, F, N):
+    """MLP output -> render() rows (activations + apply_pose_transform_3d) for the F frames of one step in
+    one launch each way; device-timed.  Bytes per row: forward 72 in + 56 out, backward 116 in + 60 out."""
+    import torch
+    from pose_splatter_b200 import param_head
+    g = torch.Generator().manual_seed(5)
+    n = F * N
+    net = torch.randn(n, 14, generator=g).to(dev).requires_grad_(True)
+    probs = (torch.rand(n, generator=g) * 0.7 + 0.27).to(dev)
+    grid = (torch.rand(n, 3, generator=g) * 0.2 - 0.1).to(dev)
+    cot = torch.randn(n, 14, generator=g).to(dev)
+    angles = torch.rand(F, generator=g, dtype=torch.float64) * 6.28 - 3.14
+    p3 = torch.rand(F, 3, generator=g) * 0.1 - 0.05
+    rf = torch.arange(F).repeat_interleave(N).int().to(dev)
+    scale = torch.tensor([-5.5], device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fw = bw = 0.0
+    reps = 5
+    for it in range(reps + 2):
+        net.grad = None
+        ev[0].record()
+        rows = param_head.gaussian_rows("3d", net, probs, scale, 0.18 / 112, 0.25, grid_sel=grid, angle=angles, p_3d=p3, row_frame=rf)
+        ev[1].record()
+        rows.backward(cot)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            fw += ev[0].elapsed_time(ev[1]) / reps
+            bw += ev[1].elapsed_time(ev[2]) / reps
+    return {"rows_per_step": n, "frames": F, "forward_ms": fw, "backward_ms": bw,
+            "forward_gbs": n * 128 / (fw * 1e-3) / 1e9, "backward_gbs": n * 176 / (bw * 1e-3) / 1e9,
+            "what": "ps_param_head_forward / backward through pose_splatter_b200.param_head.gaussian_rows (autograd), all frames of a "
+                    "step in one launch; includes the host-side pose table upload and torch's autograd bookkeeping"}
 
 
 def training_step(dev, devs, n_sets, mode, W, H, V, bg, steps):

@@ -193,16 +193,20 @@ int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *r
  *   grid_sel  [n,3]   self.grid.view(-1,3)[mask] (3D only)                                               (:223)
  *   scale0    [1]     DEVICE pointer to the trainable self.scale                                         (:86,219)
  *   voxel_size, prob_threshold, clip_lo/hi = self.voxel_size, self.prob_threshold, self.color_clip
- *   pose, angle, p_3d_host[3] (HOST pointer)  yaw and translation of the frame (:275-280)
+ *   pose, angle, p_3d_host[3] (HOST pointer)  yaw and translation of the frame (:275-280); or, for the rows of several
+ *             frames in one launch, poses [F,5] = (cos, sin, px, py, pz) per frame and row_frame [n] int32 (DEVICE; both
+ *             NULL = the scalar pose)
  *   rows      [n,14|9] gaussian_params as render() takes them
  * Backward: d_net_out [n,14|9], d_probs_sel [n], d_scale0 [1] (device, overwritten) from d_rows.
  */
 int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, const float *grid_sel,
                           const float *scale0, float voxel_size, float prob_threshold, float clip_lo, float clip_hi,
-                          int pose, double angle, const float *p_3d_host, float *rows, void *stream);
+                          int pose, double angle, const float *p_3d_host, const float *poses, const int32_t *row_frame,
+                          float *rows, void *stream);
 int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, float voxel_size,
-                           float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *d_rows,
-                           float *d_net_out, float *d_probs_sel, float *d_scale0, void *stream);
+                           float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *poses,
+                           const int32_t *row_frame, const float *d_rows, float *d_net_out, float *d_probs_sel, float *d_scale0,
+                           void *stream);
 
 /*
  * Device probe of the arithmetic contract (PSM-1): y[5][n] = exp, log(|x|+1e-30), sigmoid, sin, cos

@@ -76,8 +76,8 @@ def load() -> ctypes.CDLL:
     lib.ps_ctx_raster_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ip, vp]
     lib.ps_fp32_peak_probe.argtypes = [vp, ctypes.POINTER(ctypes.c_double), vp]
     cf, cd = ctypes.c_float, ctypes.c_double
-    lib.ps_param_head_forward.argtypes = [vp, ip, ip, vp, vp, vp, vp, cf, cf, cf, cf, ip, cd, ctypes.POINTER(cf), vp, vp]
-    lib.ps_param_head_backward.argtypes = [vp, ip, ip, vp, vp, cf, cf, cf, cf, ip, cd, vp, vp, vp, vp, vp]
+    lib.ps_param_head_forward.argtypes = [vp, ip, ip, vp, vp, vp, vp, cf, cf, cf, cf, ip, cd, ctypes.POINTER(cf), vp, vp, vp, vp]
+    lib.ps_param_head_backward.argtypes = [vp, ip, ip, vp, vp, cf, cf, cf, cf, ip, cd, vp, vp, vp, vp, vp, vp, vp]
     lib.ps_view_loss.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp]
     _lib = lib
     return lib

@@ -634,26 +634,30 @@ static int head_check(ps_ctx *ctx, int mode, int n, const void *a, const void *b
 
 int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, const float *grid_sel,
                           const float *scale0, float voxel_size, float prob_threshold, float clip_lo, float clip_hi,
-                          int pose, double angle, const float *p_3d_host, float *rows, void *stream)
+                          int pose, double angle, const float *p_3d_host, const float *poses, const int32_t *row_frame,
+                          float *rows, void *stream)
 {
     if (int rc = head_check(ctx, mode, n, net_out, probs_sel, "ps_param_head_forward")) return rc;
     if (n > 0 && (!rows || !scale0 || (mode == PS_MODE_3D && !grid_sel))) return fail(1, "ps_param_head_forward: NULL buffer");
-    if (pose && mode == PS_MODE_3D && !p_3d_host) return fail(1, "ps_param_head_forward: pose requested without p_3d");
+    if (pose && mode == PS_MODE_3D && !p_3d_host && !poses) return fail(1, "ps_param_head_forward: pose requested without p_3d");
+    if ((poses == nullptr) != (row_frame == nullptr)) return fail(1, "ps_param_head_forward: poses and row_frame go together");
     PS_CUDA(cudaSetDevice(ctx->device));
     PS_LAUNCH(ctx, ps_launch_head_fwd(mode, n, net_out, probs_sel, grid_sel, scale0, voxel_size, prob_threshold, clip_lo, clip_hi,
-                                      pose, angle, p_3d_host, rows, (cudaStream_t)stream));
+                                      pose, angle, p_3d_host, poses, row_frame, rows, (cudaStream_t)stream));
     return 0;
 }
 
 int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, float voxel_size,
-                           float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *d_rows,
-                           float *d_net_out, float *d_probs_sel, float *d_scale0, void *stream)
+                           float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *poses,
+                           const int32_t *row_frame, const float *d_rows, float *d_net_out, float *d_probs_sel, float *d_scale0,
+                           void *stream)
 {
     if (int rc = head_check(ctx, mode, n, net_out, probs_sel, "ps_param_head_backward")) return rc;
     if (!d_scale0 || (n > 0 && (!d_rows || !d_net_out || !d_probs_sel))) return fail(1, "ps_param_head_backward: NULL buffer");
     PS_CUDA(cudaSetDevice(ctx->device));
+    if ((poses == nullptr) != (row_frame == nullptr)) return fail(1, "ps_param_head_backward: poses and row_frame go together");
     PS_LAUNCH(ctx, ps_launch_head_bwd(mode, n, net_out, probs_sel, voxel_size, prob_threshold, clip_lo, clip_hi, pose, angle,
-                                      d_rows, d_net_out, d_probs_sel, d_scale0, (cudaStream_t)stream));
+                                      poses, row_frame, d_rows, d_net_out, d_probs_sel, d_scale0, (cudaStream_t)stream));
     return 0;
 }
 

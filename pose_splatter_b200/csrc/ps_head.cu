@@ -15,7 +15,18 @@ struct HeadArgs {
     int mode, n, pose;
     float voxel2, inv1mpt, pt, clip_lo, clip_hi;
     float c, s, px, py, pz; // yaw cos / sin rounded to fp32 like the reference's rot_mat, translation
+    const float *poses;     // optional [F,5] (c, s, px, py, pz) per frame: rows of several frames in one launch
+    const int32_t *row_frame; // [n] frame of every row (with poses)
 };
+
+__device__ __forceinline__ void row_pose(const HeadArgs &a, int i, float &c, float &s, float &px, float &py, float &pz)
+{
+    c = a.c; s = a.s; px = a.px; py = a.py; pz = a.pz;
+    if (a.poses) {
+        const float *p = a.poses + 5 * (size_t)a.row_frame[i];
+        c = p[0]; s = p[1]; px = p[2]; py = p[3]; pz = p[4];
+    }
+}
 
 constexpr int HEAD_THREADS = 128;
 constexpr double QEPS = 4.0 * 2.220446049250313e-16;
@@ -155,10 +166,12 @@ head_fwd_kernel(HeadArgs a, const float *__restrict__ net_out, const float *__re
     for (int k = 0; k < 3; ++k) m[k] = grid[3 * (size_t)i + k] + a.voxel2 * tanhf(in[11 + k]);
     float q[4] = { in[0], in[1], in[2], in[3] };
     if (a.pose) {
-        const float mx = m[0] * a.c - m[1] * a.s + a.px, my = m[0] * a.s + m[1] * a.c + a.py;
-        m[0] = mx; m[1] = my; m[2] = m[2] + a.pz;
+        float pc, ps, px, py, pz;
+        row_pose(a, i, pc, ps, px, py, pz);
+        const float mx = m[0] * pc - m[1] * ps + px, my = m[0] * ps + m[1] * pc + py;
+        m[0] = mx; m[1] = my; m[2] = m[2] + pz;
         QuatChain z;
-        quat_chain(q, a.c, a.s, z);
+        quat_chain(q, pc, ps, z);
         double V[4][4], t[4], lam;
         jacobi4(z.K, V);
         top_eigen(z.K, V, t, lam);
@@ -203,8 +216,10 @@ head_bwd_kernel(HeadArgs a, const float *__restrict__ net_out, const float *__re
             d[4] = g[3]; d[5] = g[4]; d[6] = g[5]; d[7] = 0.0f;
             dsc = g[3] + g[4] + g[5];
             float gm[3] = { g[0], g[1], g[2] };
+            float pc = 1.f, ps = 0.f, px, py, pz;
+            if (a.pose) row_pose(a, i, pc, ps, px, py, pz);
             if (a.pose) { // means' = Rz m + p
-                const float gx = a.c * gm[0] + a.s * gm[1], gy = -a.s * gm[0] + a.c * gm[1];
+                const float gx = pc * gm[0] + ps * gm[1], gy = -ps * gm[0] + pc * gm[1];
                 gm[0] = gx; gm[1] = gy;
             }
 #pragma unroll
@@ -217,7 +232,7 @@ head_bwd_kernel(HeadArgs a, const float *__restrict__ net_out, const float *__re
             } else {
                 const float q[4] = { in[0], in[1], in[2], in[3] };
                 QuatChain z;
-                quat_chain(q, a.c, a.s, z);
+                quat_chain(q, pc, ps, z);
                 double dq[4] = { 0.0, 0.0, 0.0, 0.0 };
                 if (!z.small) {
                     double V[4][4], t[4], lam;
@@ -253,8 +268,8 @@ head_bwd_kernel(HeadArgs a, const float *__restrict__ net_out, const float *__re
                     double dr[3][3];
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        dr[0][j] = (double)a.c * dm[0][j] + (double)a.s * dm[1][j];
-                        dr[1][j] = -(double)a.s * dm[0][j] + (double)a.c * dm[1][j];
+                        dr[0][j] = (double)pc * dm[0][j] + (double)ps * dm[1][j];
+                        dr[1][j] = -(double)ps * dm[0][j] + (double)pc * dm[1][j];
                         dr[2][j] = dm[2][j];
                     }
                     // r from the outer products o_ab = qs_a qs_b (entry (1,1) does not depend on q)
@@ -299,7 +314,8 @@ head_bwd_kernel(HeadArgs a, const float *__restrict__ net_out, const float *__re
     }
 }
 
-HeadArgs head_args(int mode, int n, float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p)
+HeadArgs head_args(int mode, int n, float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p,
+                   const float *poses, const int32_t *row_frame)
 {
     HeadArgs a;
     a.mode = mode; a.n = n; a.pose = (mode == PS_MODE_3D && pose) ? 1 : 0;
@@ -308,6 +324,8 @@ HeadArgs head_args(int mode, int n, float voxel_size, float pt, float clip_lo, f
     a.pt = pt; a.clip_lo = clip_lo; a.clip_hi = clip_hi;
     a.c = (float)cos(angle); a.s = (float)sin(angle);
     a.px = p ? p[0] : 0.f; a.py = p ? p[1] : 0.f; a.pz = p ? p[2] : 0.f;
+    a.poses = (a.pose && poses && row_frame) ? poses : nullptr;
+    a.row_frame = row_frame;
     return a;
 }
 
@@ -315,21 +333,21 @@ HeadArgs head_args(int mode, int n, float voxel_size, float pt, float clip_lo, f
 
 int ps_launch_head_fwd(int mode, int n, const float *net_out, const float *probs, const float *grid, const float *scale0,
                        float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p_host,
-                       float *rows, cudaStream_t s)
+                       const float *poses, const int32_t *row_frame, float *rows, cudaStream_t s)
 {
     if (n <= 0) return 0;
-    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, p_host);
+    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, p_host, poses, row_frame);
     head_fwd_kernel<<<(n + HEAD_THREADS - 1) / HEAD_THREADS, HEAD_THREADS, 0, s>>>(a, net_out, probs, grid, scale0, rows);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int ps_launch_head_bwd(int mode, int n, const float *net_out, const float *probs, float voxel_size, float pt, float clip_lo,
-                       float clip_hi, int pose, double angle, const float *d_rows, float *d_net, float *d_probs,
-                       float *d_scale0, cudaStream_t s)
+                       float clip_hi, int pose, double angle, const float *poses, const int32_t *row_frame,
+                       const float *d_rows, float *d_net, float *d_probs, float *d_scale0, cudaStream_t s)
 {
     if (cudaMemsetAsync(d_scale0, 0, sizeof(float), s) != cudaSuccess) return -1;
     if (n <= 0) return 0;
-    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, nullptr);
+    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, nullptr, poses, row_frame);
     head_bwd_kernel<<<(n + HEAD_THREADS - 1) / HEAD_THREADS, HEAD_THREADS, 0, s>>>(a, net_out, probs, d_rows, d_net, d_probs, d_scale0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

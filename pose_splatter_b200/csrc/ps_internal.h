@@ -92,10 +92,10 @@ int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alph
 // parameter-head tail (ps_head.cu): activations + pose transform of the rows render() takes, forward and backward
 int ps_launch_head_fwd(int mode, int n, const float *net_out, const float *probs, const float *grid, const float *scale0,
                        float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p_host,
-                       float *rows, cudaStream_t s);
+                       const float *poses, const int32_t *row_frame, float *rows, cudaStream_t s);
 int ps_launch_head_bwd(int mode, int n, const float *net_out, const float *probs, float voxel_size, float pt, float clip_lo,
-                       float clip_hi, int pose, double angle, const float *d_rows, float *d_net, float *d_probs,
-                       float *d_scale0, cudaStream_t s);
+                       float clip_hi, int pose, double angle, const float *poses, const int32_t *row_frame,
+                       const float *d_rows, float *d_net, float *d_probs, float *d_scale0, cudaStream_t s);
 
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);
 int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s);

@@ -16,56 +16,71 @@ import torch
 from . import _capi
 
 
-def _call_forward(mode, net_out, probs_sel, grid_sel, scale, voxel_size, pt, clip, angle, p_3d):
+def _pose_args(angle, p_3d, row_frame, dev):
+    """scalar pose -> (1, angle, host p, None, None); per-frame poses -> (1, 0, zeros, poses [F,5] on dev, row_frame)"""
+    zero = (ctypes.c_float * 3)(0.0, 0.0, 0.0)
+    if angle is None:
+        return 0, 0.0, zero, None, None
+    if row_frame is None:
+        return 1, float(angle), (ctypes.c_float * 3)(*[float(x) for x in p_3d]), None, None
+    ang = torch.as_tensor(angle, dtype=torch.float64).reshape(-1)
+    p = torch.as_tensor(p_3d, dtype=torch.float32).reshape(-1, 3)
+    # cos / sin in float64, then rounded to fp32: what torch.tensor([[c, -s, 0], ...]).to(float32) does (:276-277)
+    poses = torch.cat([torch.cos(ang).float()[:, None], torch.sin(ang).float()[:, None], p], 1).contiguous().to(dev)
+    return 1, 0.0, zero, poses, row_frame.to(dev, torch.int32).contiguous()
+
+
+def _call_forward(mode, net_out, probs_sel, grid_sel, scale, voxel_size, pt, clip, pose_args):
     dev = net_out.device
     n, P = net_out.shape
     rows = torch.empty((n, P), dtype=torch.float32, device=dev)
-    pose = angle is not None
-    p_host = (ctypes.c_float * 3)(*[float(x) for x in (p_3d if pose else (0.0, 0.0, 0.0))])
+    pose, angle, p_host, poses, row_frame = pose_args
     _capi.check(_capi.load().ps_param_head_forward(
         _capi.context(dev), _capi.MODE_3D if mode == "3d" else _capi.MODE_2D, n, _capi.ptr(net_out), _capi.ptr(probs_sel),
-        _capi.ptr(grid_sel), _capi.ptr(scale), float(voxel_size), float(pt), float(clip[0]), float(clip[1]), int(pose),
-        float(angle) if pose else 0.0, p_host, _capi.ptr(rows), _capi.stream_ptr(dev)), "ps_param_head_forward")
+        _capi.ptr(grid_sel), _capi.ptr(scale), float(voxel_size), float(pt), float(clip[0]), float(clip[1]), pose,
+        angle, p_host, _capi.ptr(poses), _capi.ptr(row_frame), _capi.ptr(rows), _capi.stream_ptr(dev)), "ps_param_head_forward")
     return rows
 
 
 class _Head(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, net_out, probs_sel, scale, grid_sel, mode, voxel_size, pt, clip, angle, p_3d):
+    def forward(ctx, net_out, probs_sel, scale, grid_sel, mode, voxel_size, pt, clip, angle, p_3d, row_frame):
         net_c, probs_c = net_out.detach().float().contiguous(), probs_sel.detach().float().contiguous()
         scale_c = scale.detach().float().reshape(1).contiguous()
         grid_c = None if grid_sel is None else grid_sel.detach().float().contiguous()
-        rows = _call_forward(mode, net_c, probs_c, grid_c, scale_c, voxel_size, pt, clip, angle, p_3d)
+        pose_args = _pose_args(angle, p_3d, row_frame, net_c.device)
+        rows = _call_forward(mode, net_c, probs_c, grid_c, scale_c, voxel_size, pt, clip, pose_args)
         ctx.save_for_backward(net_c, probs_c)
-        ctx.meta = (mode, voxel_size, pt, clip, angle, scale.shape)
+        ctx.meta = (mode, voxel_size, pt, clip, pose_args, scale.shape)
         return rows
 
     @staticmethod
     def backward(ctx, d_rows):
         net_c, probs_c = ctx.saved_tensors
-        mode, voxel_size, pt, clip, angle, scale_shape = ctx.meta
+        mode, voxel_size, pt, clip, (pose, angle, _, poses, row_frame), scale_shape = ctx.meta
         dev = net_c.device
         n = net_c.shape[0]
         d_rows = d_rows.float().contiguous()
         d_net, d_probs = torch.empty_like(net_c), torch.empty_like(probs_c)
         d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-        pose = angle is not None
         _capi.check(_capi.load().ps_param_head_backward(
             _capi.context(dev), _capi.MODE_3D if mode == "3d" else _capi.MODE_2D, n, _capi.ptr(net_c), _capi.ptr(probs_c),
-            float(voxel_size), float(pt), float(clip[0]), float(clip[1]), int(pose), float(angle) if pose else 0.0,
+            float(voxel_size), float(pt), float(clip[0]), float(clip[1]), pose, angle, _capi.ptr(poses), _capi.ptr(row_frame),
             _capi.ptr(d_rows), _capi.ptr(d_net), _capi.ptr(d_probs), _capi.ptr(d_scale), _capi.stream_ptr(dev)),
             "ps_param_head_backward")
-        return d_net, d_probs, d_scale.reshape(scale_shape), None, None, None, None, None, None, None
+        return d_net, d_probs, d_scale.reshape(scale_shape), None, None, None, None, None, None, None, None
 
 
 def gaussian_rows(mode: str, net_out: torch.Tensor, probs_sel: torch.Tensor, scale: torch.Tensor, voxel_size: float,
-                  prob_threshold: float, grid_sel: torch.Tensor | None = None, color_clip=(0, 0.99), angle=None, p_3d=None):
+                  prob_threshold: float, grid_sel: torch.Tensor | None = None, color_clip=(0, 0.99), angle=None, p_3d=None,
+                  row_frame: torch.Tensor | None = None):
     """MLP output -> gaussian_params rows.
 
     mode "3d": net_out [N,14] (quats 4 | scales 3 | opacity 1 | colours 3 | delta_means 3), grid_sel [N,3]; with `angle`
     (float) and `p_3d` (3 floats) the pose transform of apply_pose_transform_3d is applied as well.
     mode "2d": net_out [N,9] (means_2d 2 | scales_2d 2 | rotation 1 | colours 3 | opacity 1).
     probs_sel [N] = probs[mask]; scale = the trainable `self.scale` ([1]).
+    Rows of several frames in one launch: row_frame [N] int + angle [F], p_3d [F,3] (one pose per frame).
     """
     mode = mode.lower()
     if mode not in ("2d", "3d"):
@@ -82,9 +97,12 @@ def gaussian_rows(mode: str, net_out: torch.Tensor, probs_sel: torch.Tensor, sca
             raise ValueError("3d mode needs grid_sel [N,3]")
         if (angle is None) != (p_3d is None):
             raise ValueError("angle and p_3d go together")
-        if p_3d is not None:
+        if p_3d is not None and row_frame is None:
             p_3d = [float(x) for x in (p_3d.detach().cpu().reshape(-1).tolist() if isinstance(p_3d, torch.Tensor) else p_3d)]
+            angle = float(angle)
+        if row_frame is not None and (angle is None or row_frame.shape != (net_out.shape[0],)):
+            raise ValueError("row_frame [N] needs angle [F] and p_3d [F,3]")
     else:
-        grid_sel, angle, p_3d = None, None, None
+        grid_sel, angle, p_3d, row_frame = None, None, None, None
     return _Head.apply(net_out, probs_sel, scale, grid_sel, mode, float(voxel_size), float(prob_threshold),
-                       (float(color_clip[0]), float(color_clip[1])), None if angle is None else float(angle), p_3d)
+                       (float(color_clip[0]), float(color_clip[1])), angle, p_3d, row_frame)
