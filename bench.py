@@ -256,7 +256,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
             psd.reduce_frame_grads(d_params)
         return d_params
 
-    # --- end to end through the public API (render_views + autograd) from pinned host buffers.  Copies run on two
+    # --- end to end through the public API (render_views_vjp) from pinned host buffers.  Copies run on two
     # side streams so that step k+1's host->device copy and step k-1's device->host copy overlap step k's kernels
     # (every copy of every timed step is inside the timed region; the region ends when all three streams are idle).
     out_host = [torch.empty_like(host[0]["params"]).pin_memory() for _ in range(2)]
@@ -294,11 +294,10 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                 img_host[k % 2].copy_(img, non_blocking=True)
             img.record_stream(d2h_stream)
             return
-        p = t["params"].requires_grad_(True)
-        rgb, alpha = batched.render_views(mode, p, t["view_frame"], W, H, bg, t["viewmats"], t["Ks"])
+        # public API: forward + vector-Jacobian product with the metric's fixed cotangents (no autograd graph: the
+        # cotangent of L = sum(w_rgb * rgb) + sum(w_a * alpha) is w itself), loss value from the rendered images
+        rgb, alpha, g = batched.render_views_vjp(mode, t["params"], t["view_frame"], W, H, bg, w_rgb, w_a, t["viewmats"], t["Ks"])
         loss = torch.dot(rgb.reshape(-1), w_rgb.reshape(-1)) + torch.dot(alpha.reshape(-1), w_a.reshape(-1))
-        loss.backward()
-        g = p.grad
         if need_reduce:
             psd.reduce_frame_grads(g)
         lossd = loss.detach().reshape(1)

@@ -173,6 +173,29 @@ class _RenderViews(torch.autograd.Function):
         return d_params.to(ctx.in_dtype), None, None, None, None, None, None, None, None
 
 
+def render_views_vjp(mode: str, params: torch.Tensor, view_frame: torch.Tensor, width: int, height: int,
+                     background: torch.Tensor, d_rgb: torch.Tensor, d_alpha: torch.Tensor,
+                     viewmats: Optional[torch.Tensor] = None, Ks: Optional[torch.Tensor] = None, **opts):
+    """Forward and vector-Jacobian product in one call, without an autograd graph: for losses whose cotangents do not
+    depend on the render (the benchmark's L = sum(w_rgb * rgb) + sum(w_a * alpha)) or are produced by a
+    fused loss.  Returns rgb [V,H,W,3], alpha [V,H,W], d_params [F,N,P] = (d_rgb, d_alpha)^T d(rgb, alpha)/d params."""
+    mode = mode.lower()
+    if mode not in ("2d", "3d"):
+        raise ValueError(f"Unknown renderer mode: '{mode}'. Expected '2d' or '3d'.")
+    _check_inputs(mode, params, view_frame, viewmats, Ks, background)
+    dev = params.device
+    p = params.detach().contiguous().float()
+    vf, vm, Kd, bg = _prep(view_frame, torch.int32, dev), _prep(viewmats, torch.float32, dev), _prep(Ks, torch.float32, dev), \
+        _prep(background, torch.float32, dev)
+    V = int(vf.shape[0])
+    if d_rgb.shape != (V, height, width, 3) or d_alpha.shape != (V, height, width):
+        raise ValueError(f"Expected cotangents [V,H,W,3] and [V,H,W], got {tuple(d_rgb.shape)} and {tuple(d_alpha.shape)}")
+    rgb, alpha, _, saved = forward_raw(mode, p, vf, vm, Kd, bg, width, height, _capi.FLAG_SAVE_FOR_BACKWARD, False, opts)
+    d_params = backward_raw(saved, p, vf, vm, Kd, bg, _prep(d_rgb, torch.float32, dev), _prep(d_alpha, torch.float32, dev))
+    saved.release()
+    return rgb, alpha, d_params.to(params.dtype)
+
+
 def render_views(mode: str, params: torch.Tensor, view_frame: torch.Tensor, width: int, height: int,
                  background: torch.Tensor, viewmats: Optional[torch.Tensor] = None, Ks: Optional[torch.Tensor] = None,
                  **opts):

@@ -332,3 +332,23 @@ def test_many_views_few_gaussians():
     g = batched.backward_raw(sv, p.to(DEV), vf.to(DEV), vm[cams].to(DEV), Ks[cams].to(DEV), torch.ones(3, device=DEV),
                              torch.ones(V, 32, 36, 3, device=DEV), torch.ones(V, 32, 36, device=DEV))
     assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+def test_render_views_vjp_equals_autograd():
+    """forward + VJP without a graph == render_views + backward (same kernels, same bits)"""
+    _, _, batched, synth = _mods()
+    d = synth.make_views("c2", n_frames=2, n_cams=3, seed=8, n=900)
+    W, H = d["width"], d["height"]
+    V = len(d["view_frame"])
+    w_rgb, w_a = synth.cotangents(V, H, W, seed=2)
+    w_rgb, w_a = w_rgb.to(DEV), w_a.to(DEV)
+    bg = torch.ones(3, device=DEV)
+    p = d["params"].to(DEV).requires_grad_(True)
+    rgb, alpha = batched.render_views("3d", p, d["view_frame"].to(DEV), W, H, bg, d["viewmats"].to(DEV), d["Ks"].to(DEV))
+    ((rgb * w_rgb).sum() + (alpha * w_a).sum()).backward()
+    rgb2, alpha2, g2 = batched.render_views_vjp("3d", d["params"].to(DEV), d["view_frame"].to(DEV), W, H, bg, w_rgb, w_a,
+                                                d["viewmats"].to(DEV), d["Ks"].to(DEV))
+    assert torch.equal(rgb, rgb2) and torch.equal(alpha, alpha2)
+    # atomics make the accumulation order free: equal up to fp32 re-association
+    rel = (p.grad - g2).abs().max() / p.grad.abs().max()
+    assert rel.item() < 1e-5
