@@ -91,7 +91,7 @@ ssim_fwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
                 double *__restrict__ stats)
 {
     __shared__ float sp[LIN][LIN + 1], sq[LIN][LIN + 1];
-    __shared__ float sh[5][LIN][LT];
+    __shared__ float sh[5][LIN][LT + 1]; // + 1: the four rows a warp writes per store fall into different banks
     __shared__ double scratch[LTHREADS / 32];
     const int v = blockIdx.z;
     const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
@@ -155,13 +155,15 @@ ssim_fwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
                     const bool qfree = vqq > 0.f; // clamp(., min = 0) passes the gradient only when not clamped
                     const float N1 = 2.f * mp * mq + c1, N2 = 2.f * vpq + c2;
                     const float D1 = mp * mp + mq * mq + c1, D2 = fmaxf(vpp, 0.f) + fmaxf(vqq, 0.f) + c2;
-                    const float inv = 1.0f / (D1 * D2);
+                    // D1 >= c1, D2 >= c2 > 0: approximate reciprocals (2 ulp) are far inside the 1e-3 gradient tolerance
+                    const float i1 = __fdividef(1.0f, D1), i2 = __fdividef(1.0f, D2);
+                    const float inv = i1 * i2;
                     const float S = N1 * N2 * inv;
                     ssum += S;
                     const float dD2 = qfree ? -2.f * mq : 0.f;
-                    const float dmu = (2.f * mp * N2 - 2.f * mp * N1) * inv - S * (2.f * mq / D1 + dD2 / D2);
+                    const float dmu = (2.f * mp * N2 - 2.f * mp * N1) * inv - S * (2.f * mq * i1 + dD2 * i2);
                     g1 = coef_over_count * dmu;
-                    g2 = qfree ? coef_over_count * (-S / D2) : 0.f;
+                    g2 = qfree ? coef_over_count * (-S * i2) : 0.f;
                     g3 = coef_over_count * 2.f * N1 * inv;
                 }
                 const size_t pix = (size_t)y * d.W + x;
@@ -179,7 +181,7 @@ loss_bwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
                 const double *__restrict__ stats, float img_lambda, float *__restrict__ d_rgb, float *__restrict__ d_alpha)
 {
     __shared__ float sa[3][LIN][LIN + 1];
-    __shared__ float sh[3][LIN][LT];
+    __shared__ float sh[3][LIN][LT + 1];
     const int v = blockIdx.z;
     const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
     const size_t npix = (size_t)d.H * d.W;

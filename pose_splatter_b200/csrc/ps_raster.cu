@@ -324,6 +324,223 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     }
 }
 
+// ---- forward v6: candidate masks + per-pixel walk --------------------------------------------------------------------
+// v4 walks every surviving entry with all 32 lanes although ~5 of them are candidates.  Here lane e first computes, from
+// the splat's conic, the exact set of block pixels its ellipse sigma <= thr can reach (per pixel row the solution of a
+// quadratic, widened by 1e-3 px and 0.02 in sigma: a superset of the pixels that pass the fp32 test of v4, so no
+// result changes); the 32 x 32 bit matrix (entry, pixel) is transposed across the warp with five shuffles, and every
+// pixel lane then walks only ITS OWN candidate entries, in list order, with the same arithmetic as v4.
+
+// pixels (bit = y * 8 + x of the 8x4 block whose first pixel centre is (bxf, byf)) where the quadratic form
+// hA ux^2 + B ux uy + hC uy^2 <= lim can hold, u = pixel centre - (gx, gy)
+__device__ __forceinline__ uint32_t span_mask(float gx, float gy, float hA, float B, float hC, float lim, float bxf, float byf)
+{
+    if (!(hA > 0.0f)) return 0xffffffffu; // not an ellipse in x: let the exact test decide everywhere
+    const float inv2a = __fdividef(0.5f, hA);
+    const float gxr = gx - bxf;
+    const float four_a = 4.0f * hA;
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float uy = (byf + (float)j) - gy;
+        const float bq = B * uy;
+        const float cq = hC * uy * uy - lim;
+        const float disc = bq * bq - four_a * cq;
+        if (disc >= 0.0f) { // NaN (degenerate records) fails: such entries never pass the exact test either
+            const float sq = sqrtf(disc);
+            const float flo = fmaxf(gxr + (-bq - sq) * inv2a - 1e-3f, -1.0f);
+            const float fhi = fminf(gxr + (-bq + sq) * inv2a + 1e-3f, 8.0f);
+            const int ilo = max(0, (int)ceilf(flo)), ihi = min(7, (int)floorf(fhi));
+            if (ilo <= ihi) m |= (((2u << ihi) - 1u) & ~((1u << ilo) - 1u)) << (8 * j);
+        }
+    }
+    return m;
+}
+
+// 32 x 32 bit-matrix transpose across the warp: lane l gives row l, gets column l
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
+{
+#define PS_TSTAGE(J, M)                                                                          \
+    {                                                                                            \
+        const uint32_t y = __shfl_xor_sync(FULL, x, J);                                          \
+        x = (lane & J) ? (((y >> J) & M) | (x & ~M)) : ((x & M) | ((y & M) << J));               \
+    }
+    PS_TSTAGE(16, 0x0000ffffu) PS_TSTAGE(8, 0x00ff00ffu) PS_TSTAGE(4, 0x0f0f0f0fu) PS_TSTAGE(2, 0x33333333u) PS_TSTAGE(1, 0x55555555u)
+#undef PS_TSTAGE
+    return x;
+}
+
+template <int MODE, bool STATS, int W>
+__global__ void __launch_bounds__(W * 32)
+raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
+                   const int32_t *__restrict__ worklist, const float *__restrict__ background,
+                   float *__restrict__ rgb, float *__restrict__ alpha,
+                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
+                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount,
+                   uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats)
+{
+    __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
+    __shared__ uint32_t s_pos[W][NS][CH];
+    const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bcount);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bool done = !c.inside;
+    if (__all_sync(FULL, done)) return;
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid], s_pos[wid] };
+    const int len = c.nb;
+    const int nchunks = (len + CH - 1) / CH;
+    const uint32_t *list = vals + c.start;
+    auto issue = [&](int cj, uint32_t pos, uint32_t id) {
+        if (cj * CH + lane < len) {
+            const int st = cj % NS;
+            q.pos[st][lane] = pos;
+            const float4 *src = PS_REC(t, id, 0);
+            cp_async16(&q.a[st][lane], src);
+            cp_async16(&q.b[st][lane], src + 1);
+            cp_async16(&q.c[st][lane], src + 2);
+        }
+        cp_async_commit();
+    };
+    auto fetch_pos = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
+    uint32_t posn, posnn, idn;
+    {
+        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
+        posn = fetch_pos(2);
+        posnn = fetch_pos(3);
+        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
+        issue(0, p0, i0);
+        issue(1, p1, i1);
+        idn = __ldg(list + posn);
+    }
+    unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
+    const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
+    const float pxf = (float)c.px + half, pyf = (float)c.py + half;
+    const float bxf = (float)c.bx + half, byf = (float)c.by + half;
+    float T = 1.0f, Tpen = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    int cnt = 0;
+    int blastpos = 0;
+    for (int ci = 0; ci < nchunks; ++ci) {
+        issue(ci + 2, posn, idn);
+        posn = posnn;
+        idn = __ldg(list + posn);
+        posnn = fetch_pos(ci + 4);
+        cp_async_wait_group<2>();
+        __syncwarp();
+        const int st = ci % NS;
+        const int first = ci * CH;
+        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        // lane = entry: which live pixels of the block can it reach?
+        const uint32_t live = __ballot_sync(FULL, !done);
+        uint32_t em = 0;
+        if (ci * CH + lane < len) {
+            const float4 a0 = q0[lane], a1 = q1[lane];
+            float hA = a1.x, B = a1.y, hC = a1.z;
+            if (MODE == PS_MODE_2D) conic2d(a1, hA, B, hC);
+            em = span_mask(a0.x, a0.y, hA, B, hC, a0.z * 1.0001f + 2.0f * THR_SLACK, bxf, byf) & live;
+        }
+        // lane = pixel: my candidate entries of this chunk, ascending = list order
+        uint32_t pm = transpose32(em, lane);
+        if (STATS) {
+            const uint32_t reach = __ballot_sync(FULL, em != 0); // entries that reach a live pixel
+            st_staged += 1;
+            if (lane == 0) st_walk += __popc(reach);
+            st_eval += __popc(pm);
+        }
+        while (pm && !done) {
+            // two candidates in flight: independent alpha chains, compositing in order
+            const int ea = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const bool two = pm != 0;
+            const int eb = two ? __ffs(pm) - 1 : ea;
+            pm &= pm - 1;
+            const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
+            if (MODE == PS_MODE_3D) {
+                float dx, dy;
+                const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
+                const float sgb = ps_sigma3d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, pxf, pyf, &dx, &dy);
+                const bool canda = sga >= 0.0f && sga <= r0a.z + THR_SLACK;
+                const bool candb = two && sgb >= 0.0f && sgb <= r0b.z + THR_SLACK;
+                if (!(canda || candb)) continue;
+                const float aa = fminf(PS_ALPHA_MAX, psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-sga, 0x1.715476p+0f))));
+                const float ab = fminf(PS_ALPHA_MAX, psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-sgb, 0x1.715476p+0f))));
+                if (canda && aa >= PS_ALPHA_MIN) {
+                    const float nT = psm_mul(T, psm_sub(1.0f, aa));
+                    if (nT <= PS_T_STOP_3D) {
+                        done = true;
+                    } else {
+                        const float4 r2 = q2[ea];
+                        const float vis = psm_mul(aa, T);
+                        cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1;
+                    }
+                }
+                if (candb && !done && ab >= PS_ALPHA_MIN) {
+                    const float nT = psm_mul(T, psm_sub(1.0f, ab));
+                    if (nT <= PS_T_STOP_3D) {
+                        done = true;
+                    } else {
+                        const float4 r2 = q2[eb];
+                        const float vis = psm_mul(ab, T);
+                        cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1;
+                    }
+                }
+            } else {
+                float dxr, dyr;
+                const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
+                const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
+                const bool ina = qa <= r0a.z;
+                const bool inb = two && qb <= r0b.z;
+                if (!(ina || inb)) continue;
+                const float gva = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-qa, 0x1.715476p+0f)));
+                const float gvb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-qb, 0x1.715476p+0f)));
+                if (ina) {
+                    const float4 r2a = q2[ea];
+                    const float contrib = psm_mul(gva, T);
+                    cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1;
+                    if (T <= PS_T_STOP_2D) done = true;
+                }
+                if (inb && !done) {
+                    const float4 r2b = q2[eb];
+                    const float contrib = psm_mul(gvb, T);
+                    cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1;
+                    if (T <= PS_T_STOP_2D) done = true;
+                }
+            }
+        }
+        __syncwarp(); // lanes reconverge; every lane is finished with stage st before chunk ci + 3 is copied into it
+        if (__all_sync(FULL, done)) break;
+    }
+    cp_async_wait_group<0>();
+    if (c.inside) {
+        const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
+        const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
+        const float o0 = psm_fma(T, b0, cr), o1 = psm_fma(T, b1, cg), o2 = psm_fma(T, b2, cb), oa = psm_sub(1.0f, T);
+        if (rgb) { rgb[3 * p + 0] = o0; rgb[3 * p + 1] = o1; rgb[3 * p + 2] = o2; }
+        if (alpha) alpha[p] = oa;
+        if (rgba8) rgba8[p] = quantise_rgba8(o0, o1, o2, oa);
+        if (n_contrib) n_contrib[p] = cnt;
+        if (last) last[p] = c.start + (blastpos ? (int)__ldg(c.bl + blastpos - 1) + 1 : 0);
+        if (blast) blast[p] = blastpos;
+        if (t_pen) t_pen[p] = Tpen;
+    }
+    if (STATS) {
+        unsigned long long contributing = (unsigned long long)cnt;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            st_eval += __shfl_xor_sync(FULL, st_eval, d);
+            contributing += __shfl_xor_sync(FULL, contributing, d);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + 0, st_eval);
+            atomicAdd(stats + 1, contributing);
+            atomicAdd(stats + 2, st_walk);
+            atomicAdd(stats + 3, st_staged * CH);
+        }
+    }
+}
+
 // Sum 9 per-lane values over the warp.  v[0..7] go through a halving butterfly (4+2+1+1+1 shuffles
 // instead of 8 x 5); afterwards lane L holds the total of value (L >> 2) in v[0].
 // v8 is reduced with the plain 5-step butterfly (every lane gets the total).
@@ -888,12 +1105,18 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
                          uint32_t *rgba8, unsigned long long *stats, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    static const bool w1 = getenv("PS_FWD_WPC1") != nullptr; // A/B switch: one warp per CTA
-#define PS_FWD(MODE, ST, W) raster_fwd_kernel<MODE, ST, W><<<(unsigned)n_work * (8 / W), W * 32, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, rgba8, stats)
-#define PS_FWD_W(MODE, ST) do { if (w1) PS_FWD(MODE, ST, 1); else PS_FWD(MODE, ST, WPC); } while (0)
-    if (g.mode == PS_MODE_3D) { if (stats) PS_FWD_W(PS_MODE_3D, true); else PS_FWD_W(PS_MODE_3D, false); }
-    else { if (stats) PS_FWD_W(PS_MODE_2D, true); else PS_FWD_W(PS_MODE_2D, false); }
-#undef PS_FWD_W
+    const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
+    // 3D: v6 (candidate masks + per-pixel walk; 3.22 -> 3.04 ms at c2).  2D footprints cover half a block, where the
+    // all-lanes walk of v4 is faster (5.25 vs 5.44 ms at c3).  The pair statistics (bench only) are defined on v4's walk.
+    static const bool force_v4 = getenv("PS_FWD_V4") != nullptr; // A/B switch for measurements
+#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, rgba8, stats)
+    if (g.mode == PS_MODE_3D) {
+        if (stats) PS_FWD(raster_fwd_kernel, PS_MODE_3D, true);
+        else if (force_v4) PS_FWD(raster_fwd_kernel, PS_MODE_3D, false);
+        else PS_FWD(raster_fwd6_kernel, PS_MODE_3D, false);
+    } else {
+        if (stats) PS_FWD(raster_fwd_kernel, PS_MODE_2D, true); else PS_FWD(raster_fwd_kernel, PS_MODE_2D, false);
+    }
 #undef PS_FWD
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
