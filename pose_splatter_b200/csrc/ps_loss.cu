@@ -270,14 +270,18 @@ int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alph
                         float ssim_lambda, float img_lambda, double *stats, float *adj, float *losses, float *d_rgb,
                         float *d_alpha, cudaStream_t s)
 {
-    static bool taps_ready = false;
-    if (!taps_ready) { // exp(-(d / 1.5)^2 / 2), d = -5 .. 5, normalised (torchmetrics _gaussian)
+    static bool taps_ready[64] = {}; // __constant__ memory is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev < 64 ? dev : 63;
+    if (!taps_ready[di] || dev >= 64) { // exp(-(d / 1.5)^2 / 2), d = -5 .. 5, normalised (torchmetrics _gaussian)
         double g[11], sum = 0.0;
         for (int i = 0; i < 11; ++i) { const double dd = (double)(i - 5) / 1.5; g[i] = exp(-dd * dd / 2.0); sum += g[i]; }
         float gf[11];
         for (int i = 0; i < 11; ++i) gf[i] = (float)(g[i] / sum);
-        if (cudaMemcpyToSymbol(c_taps, gf, sizeof(gf)) != cudaSuccess) return -1;
-        taps_ready = true;
+        if (cudaMemcpyToSymbolAsync(c_taps, gf, sizeof(gf), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return -1; // gf lives on this stack frame
+        taps_ready[di] = true;
     }
     const LossDims d = { V, H, W };
     if (cudaMemsetAsync(stats, 0, (size_t)V * NSTAT * sizeof(double), s) != cudaSuccess) return -1;

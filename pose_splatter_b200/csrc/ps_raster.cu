@@ -1157,24 +1157,29 @@ int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l
     const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
     static const bool use_v4 = getenv("PS_BWD_V4") != nullptr; // A/B switch for measurements: the warp-reduction backward
     if (!use_v4) {
-        static const bool carve = [] { // 10 CTAs x 21.6 KB per SM need the full shared-memory carve-out
-            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            return true;
-        }();
-        (void)carve;
-        static int ctas_per_sm[2] = { 0, 0 }, n_sm = 0;
+        // per device (a process may drive several): full shared-memory carve-out (10 CTAs x 21.6 KB per SM) and the
+        // persistent grid = resident CTAs per SM x SMs
+        constexpr int MAX_DEV = 64;
+        static int ctas_per_sm[MAX_DEV][2] = {}, sm_count[MAX_DEV] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int di = dev < MAX_DEV ? dev : MAX_DEV - 1;
         const int mi = g.mode == PS_MODE_3D ? 0 : 1;
-        if (!ctas_per_sm[mi]) {
-            int dev = 0, per = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (mi == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_3D, WPC>, RT_THREADS, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_2D, WPC>, RT_THREADS, 0);
-            ctas_per_sm[mi] = per > 0 ? per : 1;
+        if (!ctas_per_sm[di][mi]) {
+            int per = 0;
+            cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev);
+            if (mi == 0) {
+                cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_3D, WPC>, RT_THREADS, 0);
+            } else {
+                cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_2D, WPC>, RT_THREADS, 0);
+            }
+            ctas_per_sm[di][mi] = per > 0 ? per : 1;
         }
+        const int n_sm = sm_count[di];
         const unsigned n_tasks = (unsigned)n_work * 8u;
-        const unsigned want = (n_tasks + WPC - 1) / WPC, cap = (unsigned)(n_sm * ctas_per_sm[mi]);
+        const unsigned want = (n_tasks + WPC - 1) / WPC, cap = (unsigned)(n_sm * ctas_per_sm[di][mi]);
         const unsigned pgrid = want < cap ? want : cap;
         if (g.mode == PS_MODE_3D)
             raster_bwd2_kernel<PS_MODE_3D, WPC><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, n_tasks, next_task);
