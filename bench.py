@@ -391,6 +391,13 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                "MEASURED_PEAKS.json has no FP32 figure; no tensor cores on this path",
                 "work": f"{stats['pairs_evaluated']} evaluated (pixel,Gaussian) pairs per launch x {FLOPS_PER_PAIR[dom]:.0f} FP32 ops",
                 "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / steps)}
+    # the same dominant kernel against the HBM roofline (SURVEY 8d-d4 bytes): per staged block-list entry 4 B position +
+    # 4 B id + 48 B record, per pixel 24 B of saved state and cotangents, 36 B of atomics per walked entry (backward only)
+    dom_bytes = stats["entries_staged"] * 56 + V * H * W * (24 if dom == "raster_bwd" else 20) + \
+        (stats["entries_walked"] * 36 if dom == "raster_bwd" else 0)
+    roofline["as_hbm"] = {"bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                          "note": "the rasterizers are instruction-issue bound, not HBM bound: this is how far below the HBM roofline they sit"}
     VN = V * (args.n or cfg["n"])
     # rank: depth word + listed flag in, order + rank out; partition: rect + count + rank in, 4 B slot out per entry;
     # list sort: slot in, order gather, 4 B value out per entry; scan: one int in/out per (view, tile)
