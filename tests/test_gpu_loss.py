@@ -110,3 +110,14 @@ def test_training_step_render_loss_backward_chain():
     got, ref = p.grad.cpu().numpy().reshape(-1, 14), back["d_params"].reshape(-1, 14)
     rel = np.abs(got - ref).max(0) / np.maximum(np.abs(ref).max(0), 1e-20)
     assert rel.max() <= GRAD_TOL, rel
+
+
+def test_empty_batch_and_degenerate_masks():
+    from pose_splatter_b200 import losses
+    total, parts = losses.view_loss(torch.zeros(0, 16, 16, 3, device=DEV), torch.zeros(0, 16, 16, device=DEV),
+                                    torch.zeros(0, 3, 16, 16, device=DEV), torch.zeros(0, 16, 16, device=DEV), 1.0, 1.0)
+    assert total.shape == (0,) and parts.shape == (0, 3)
+    # an all-zero target mask: the reference divides by mask.sum() = 0 (:130) -> inf / nan, not an exception
+    rgb, alpha, timg, mask = _inputs(1, 1, 16, 16)
+    total, parts = losses.view_loss(rgb.to(DEV), alpha.to(DEV), timg.to(DEV), torch.zeros_like(mask).to(DEV), 1.0, 1.0)
+    assert not torch.isfinite(parts[0, 2]) and torch.isfinite(parts[0, :2]).all()
