@@ -106,3 +106,50 @@ def gaussian_rows(mode: str, net_out: torch.Tensor, probs_sel: torch.Tensor, sca
         grid_sel, angle, p_3d, row_frame = None, None, None, None
     return _Head.apply(net_out, probs_sel, scale, grid_sel, mode, float(voxel_size), float(prob_threshold),
                        (float(color_clip[0]), float(color_clip[1])), angle, p_3d, row_frame)
+
+
+def select_voxels(volume0: torch.Tensor, mask_threshold: float, prob_threshold: float, mask_threshold_delta: float,
+                  min_n: int, max_n: int, max_steps: int = 64):
+    """Which voxels become Gaussians: the selection of src/model.py:185-204 with ONE device->host read.
+
+    The reference raises `mt` by `delta` while more than `max_n` voxels pass `sigmoid(volume[0] - mt) > pt`, then lowers
+    it while fewer than `min_n` pass -- a `mask.sum()` host sync per trial -- and finally subsamples at random if the
+    count is still above `max_n`.  Here the counts of all trial thresholds (the same sequence of repeated float additions)
+    are produced in one batched pass, read back once, and the loops are replayed on the host.  Host-side helper built
+    from torch ops (no kernel of this library); returns (mask [n] bool, probs [n], mt) exactly as the reference leaves them.
+    """
+    pt = prob_threshold
+    ups, downs = [float(mask_threshold)], []
+    for _ in range(max_steps):
+        ups.append(ups[-1] + mask_threshold_delta)
+    # the downward walk starts wherever the upward walk stopped: tabulate it from every possible start lazily below
+    trial = torch.tensor(ups, dtype=torch.float64, device=volume0.device).to(volume0.dtype)
+    counts_up = (torch.sigmoid(volume0[None, :] - trial[:, None]) > pt).sum(1).tolist()  # the one host read (upward)
+    k = 0
+    while counts_up[k] > max_n:
+        k += 1
+        if k >= len(ups):
+            raise RuntimeError("select_voxels: threshold search did not converge")
+    mt = ups[k]
+    count = counts_up[k]
+    if count < min_n:
+        downs = [mt]
+        for _ in range(max_steps):
+            downs.append(downs[-1] - mask_threshold_delta)
+        trial = torch.tensor(downs, dtype=torch.float64, device=volume0.device).to(volume0.dtype)
+        counts_dn = (torch.sigmoid(volume0[None, :] - trial[:, None]) > pt).sum(1).tolist()
+        j = 0
+        while counts_dn[j] < min_n:
+            j += 1
+            if j >= len(downs):
+                raise RuntimeError("select_voxels: threshold search did not converge")
+        mt, count = downs[j], counts_dn[j]
+    probs = torch.sigmoid(volume0 - mt)
+    mask = probs > pt
+    if count > max_n:  # :198-203, same RNG calls as the reference
+        indices = torch.nonzero(mask, as_tuple=True)[0]
+        rand_idx = torch.randperm(len(indices))[:max_n].to(mask.device)
+        keep = indices[rand_idx]
+        mask[:] = False
+        mask[keep] = True
+    return mask, probs, mt

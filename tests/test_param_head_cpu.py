@@ -57,3 +57,61 @@ def test_gradients_match_the_reference_autograd(mode):
 def test_degenerate_quaternion_is_the_identity_block():
     r = ref.quat_block(torch.tensor([[0.0, 0.0, 0.0, 0.0], [1e-9, 0.0, 0.0, 0.0]]))
     assert torch.equal(r, torch.eye(3).expand(2, 3, 3))
+
+
+def _reference_selection(vol0, **kw):
+    """the loop of src/model.py:185-204, restated for the test (thresholds, counts, random subsample)"""
+    mt, pt = kw["mask_threshold"], kw["prob_threshold"]
+    probs = torch.sigmoid(vol0 - mt)
+    mask = probs > pt
+    while mask.sum() > kw["max_n"]:
+        mt += kw["mask_threshold_delta"]
+        probs = torch.sigmoid(vol0 - mt)
+        mask = probs > pt
+    while mask.sum() < kw["min_n"]:
+        mt -= kw["mask_threshold_delta"]
+        probs = torch.sigmoid(vol0 - mt)
+        mask = probs > pt
+    if mask.sum() > kw["max_n"]:
+        indices = torch.nonzero(mask, as_tuple=True)[0]
+        rand_idx = torch.randperm(len(indices))[:kw["max_n"]]
+        keep = indices[rand_idx]
+        mask[:] = False
+        mask[keep] = True
+    return mask, probs, mt
+
+
+@pytest.mark.parametrize("case", ["in_range", "too_many", "too_few", "overshoot_then_subsample"])
+def test_select_voxels_replays_the_reference_loop(case):
+    from pose_splatter_b200 import param_head
+    g = torch.Generator().manual_seed(11)
+    vol0 = torch.randn(20000, generator=g) * 2.0
+    kw = dict(mask_threshold=0.25, prob_threshold=0.25, mask_threshold_delta=0.05, min_n=1024, max_n=16000)
+    if case == "too_many":
+        kw.update(max_n=3000, min_n=100)
+    elif case == "too_few":
+        vol0 = vol0 - 6.0
+    elif case == "overshoot_then_subsample":  # a plateau: one step down jumps from < min_n to > max_n
+        vol0 = torch.cat([torch.full((5000,), -1.0), torch.full((300,), 3.0)])
+        kw.update(min_n=1024, max_n=2000)
+    torch.manual_seed(5)
+    want_mask, want_probs, want_mt = _reference_selection(vol0.clone(), **kw)
+    torch.manual_seed(5)
+    mask, probs, mt = param_head.select_voxels(vol0, kw["mask_threshold"], kw["prob_threshold"], kw["mask_threshold_delta"],
+                                               kw["min_n"], kw["max_n"])
+    assert mt == want_mt and torch.equal(mask, want_mask) and torch.equal(probs, want_probs)
+    n = int(mask.sum())
+    assert n <= kw["max_n"] and (n >= kw["min_n"] or case == "overshoot_then_subsample")
+
+
+def test_select_voxels_matches_the_reference_fixture():
+    """the fixture's selection (made by the reference's own method) is reproduced from its volume"""
+    z = _load("3d")
+    from pose_splatter_b200 import param_head
+    vol0_grad = z["d_volume"][0]  # only used for its length
+    g = torch.Generator().manual_seed(1)
+    vol0 = torch.randn(len(vol0_grad), generator=g) * 2.0
+    vol0[:7] = 40.0
+    vol0[7:12] = 0.25 + float(np.log(0.25 / 0.75)) + 1e-7
+    mask, probs, mt = param_head.select_voxels(vol0, 0.25, 0.25, 0.05, 16, 16000)
+    assert torch.equal(mask, z["sel"]) and torch.allclose(probs[mask], z["probs_sel"], atol=0, rtol=0)
