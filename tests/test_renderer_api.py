@@ -78,3 +78,32 @@ def test_product_never_imports_the_oracle():
     for f in list(root.rglob("*.py")) + list(root.rglob("*.cu")) + list(root.rglob("*.cuh")) + list(root.rglob("*.h")):
         text = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b|#include\s+[\"<].*oracle", text, re.M), f
+
+
+def test_new_rows_fail_loudly_without_cuda():
+    """losses / param_head have no CPU path (the oracle is test infrastructure, never a fallback)"""
+    import pytest
+    import torch
+    from pose_splatter_b200 import batched, losses, param_head
+    with pytest.raises(RuntimeError, match="CUDA"):
+        losses.view_loss(torch.rand(1, 16, 16, 3), torch.rand(1, 16, 16), torch.rand(1, 3, 16, 16), torch.ones(1, 16, 16), 1.0, 1.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        param_head.gaussian_rows("3d", torch.zeros(4, 14), torch.zeros(4), torch.zeros(1), 0.1, 0.25, grid_sel=torch.zeros(4, 3))
+    with pytest.raises(ValueError, match="Expected 9 parameters"):
+        param_head.gaussian_rows("2d", torch.zeros(4, 14), torch.zeros(4), torch.zeros(1), 0.1, 0.25)
+    with pytest.raises(ValueError, match="Unknown renderer mode"):
+        param_head.gaussian_rows("4d", torch.zeros(4, 14), torch.zeros(4), torch.zeros(1), 0.1, 0.25)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        batched.render_views_vjp("3d", torch.zeros(1, 4, 14), torch.zeros(1, dtype=torch.int32), 16, 16, torch.ones(3),
+                                 torch.zeros(1, 16, 16, 3), torch.zeros(1, 16, 16), torch.eye(4)[None], torch.eye(3)[None])
+    with pytest.raises(ValueError, match="same shape"):
+        losses.get_iou_loss(torch.rand(4, 4), torch.rand(4, 5))
+
+
+def test_product_never_imports_the_oracle():
+    """only tests/, smoke() and bench.py's CPU legs may touch oracle/"""
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    for f in list((root / "pose_splatter_b200").glob("*.py")) + list((root / "gsplat").glob("*.py")) + list((root / "src").glob("*.py")):
+        text = f.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, f
