@@ -113,13 +113,11 @@ __device__ __forceinline__ void quat_chain(const float (&q)[4], float c, float s
     }
     const double m00 = m[0][0], m01 = m[0][1], m02 = m[0][2], m10 = m[1][0], m11 = m[1][1], m12 = m[1][2],
                  m20 = m[2][0], m21 = m[2][1], m22 = m[2][2];
-    const double third = 1.0 / 3.0;
     z.K[0][0] = (m00 - m11 - m22) / 3.0; z.K[1][1] = (m11 - m00 - m22) / 3.0;
     z.K[2][2] = (m22 - m00 - m11) / 3.0; z.K[3][3] = (m00 + m11 + m22) / 3.0;
     z.K[0][1] = z.K[1][0] = (m01 + m10) / 3.0; z.K[0][2] = z.K[2][0] = (m02 + m20) / 3.0;
     z.K[0][3] = z.K[3][0] = (m21 - m12) / 3.0; z.K[1][2] = z.K[2][1] = (m12 + m21) / 3.0;
     z.K[1][3] = z.K[3][1] = (m02 - m20) / 3.0; z.K[2][3] = z.K[3][2] = (m10 - m01) / 3.0;
-    (void)third;
 }
 
 // index of the largest eigenvalue and its eigenvector (select chains: no dynamic register indexing)

@@ -7,7 +7,6 @@
 #include "../../include/psplat.h"
 
 #define PS_PROJ_BLOCK 256    // (view, Gaussian) pairs per projection / partition block
-#define PS_RASTER_BATCH 256  // tile-list entries staged in shared memory per round
 #define PS_ACC_STRIDE 9      // floats per (view, Gaussian) gradient accumulator row
 #define PS_HIST_SMEM_TILES 8192  // per-view tile histograms live in shared memory up to this many tiles
 #define PS_RANK_THREADS 1024     // one CTA per view in the depth-ranking kernel
