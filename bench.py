@@ -172,10 +172,26 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: pose_splatter_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner at
+    # communicator creation) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        out = run_measurements(args, world, rank, local, dev)
+        if world > 1:
+            dist.destroy_process_group()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def run_measurements(args, world, rank, local, dev):
     out = measure(args, args.workload, args.steps, world, rank, local, dev, primary=True)
     if args.workload == "c2" and not args.no_secondary and not args.n and not args.split_frames and not args.forward_only:
         # the metric names two configurations; the 2D one (BASELINE.json configs[2]) rides along, briefly
@@ -183,10 +199,7 @@ def run_b200(args):
         if rank == 0:
             out["also"] = {"c3": {k: other[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline",
                                                         "stage_ms_per_step", "pairs")}}
-    if rank == 0:
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 def ncu_traffic(wl, kernel):
