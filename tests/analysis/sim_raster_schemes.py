@@ -5,7 +5,7 @@ per-block lists chunk by chunk and counts, for every 32-entry chunk of every 8x4
   bal : candidate pairs (balanced alpha evaluation, 32 pairs per iteration) + ordered pass = max candidates per pixel
 and turns them into warp-instruction estimates with the per-iteration costs measured by ncu's source counters for the
 existing kernels (v4: 64 per walked entry; v6: 110 per two-entry iteration + 290 per chunk set-up).
-CPU only: uses the oracle (test infrastructure) for projection and binning.  python tools/sim_raster_schemes.py [views]"""
+CPU only; lives under tests/ because it uses the oracle (test infrastructure) for projection and binning.  python tests/analysis/sim_raster_schemes.py [views]"""
 import sys
 
 import numpy as np
