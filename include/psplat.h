@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 3
+#define PS_ABI_VERSION 4
 
 #define PS_MODE_2D 2 /* GaussianRenderer2D, rows of 9 floats  (src/gaussian_renderer.py:214-334) */
 #define PS_MODE_3D 3 /* GaussianRenderer3D, rows of 14 floats (src/gaussian_renderer.py:110-211) */
@@ -213,6 +213,15 @@ int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, c
  * of x[n], computed by the same device functions the kernels use.  For the bit-exactness tests.
  */
 int ps_math_probe(ps_ctx *ctx, const float *x, int n, float *y, void *stream);
+
+/*
+ * Device probe of the 3D adapter stage (src/gaussian_renderer.py:183-193), through the device functions the projection
+ * kernels call: act [n,14] = means | exp(log_scales) | q / (|q| + 1e-8) | clamp(colours, 0, 1) | sigmoid(logit), i.e. the
+ * tensors the reference hands to gsplat.rendering.rasterization (:196-208); with v_act [n,14] also d_rows [n,14] = J^T v_act,
+ * what autograd propagates through those lines.  For the fixture test against the reference's own code
+ * (tests/golden/adapter3d_reference.npz).  v_act and d_rows may both be NULL.
+ */
+int ps_adapter3d_probe(ps_ctx *ctx, const float *rows, int n, const float *v_act, float *act, float *d_rows, void *stream);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,22 @@ def project(mode, params, W, H, viewmat=None, K=None, **opts):
     return dict(geom=geom, rgb=rgb, rect=rect, tile_rect=trect, low=low, tiles=tiles)
 
 
+def adapter3d(params, v_act=None):
+    """The 3D adapter stage alone (src/gaussian_renderer.py:183-193): activated [N,14] = means | scales | quats |
+    colours | opacity as gsplat's rasterization() receives them; with v_act [N,14] also J^T v_act (float64)."""
+    params = _c32(params)
+    N = params.shape[0]
+    act = np.zeros((N, 14), np.float32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    if v_act is None:
+        lib().ora3d_adapter(_f(params), N, _f(act), None, None)
+        return act
+    v = np.ascontiguousarray(v_act, np.float64)
+    d = np.zeros((N, 14), np.float64)
+    lib().ora3d_adapter(_f(params), N, _f(act), v.ctypes.data_as(dp), d.ctypes.data_as(dp))
+    return act, d
+
+
 def bin_view(tab, W, H, view=0, n_stride=None):
     """Stages K2-K4 for one view: keys/vals (sorted) and tile offsets [n_tiles+1]."""
     N = tab["tiles"].shape[0]

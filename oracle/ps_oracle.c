@@ -169,6 +169,57 @@ typedef struct {
     float c00, c01, c11, det;        /* blurred 2D covariance */
 } ora_proj3d_tmp;
 
+/* The adapter of GaussianRenderer3D.render, src/gaussian_renderer.py:183-193: scales = exp(log_scales),
+ * quats = q / (|q| + 1e-8), colours = clamp(c, 0, 1), opacities = sigmoid(logit).  activated != 0: identity. */
+static void adapter3d_one(const float *row, int activated, float *s, float *qa, float *qn_raw, float *rgb, float *o)
+{
+    for (int k = 0; k < 3; ++k) s[k] = activated ? row[3 + k] : d_exp(row[3 + k]);
+    float qw = row[6], qx = row[7], qy = row[8], qz = row[9];
+    float n2 = fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, qw * qw)));
+    float qn = sqrtf(n2);
+    *qn_raw = qn;
+    float den = qn + 1e-8f;
+    if (activated) { qa[0] = qw; qa[1] = qx; qa[2] = qy; qa[3] = qz; }
+    else { qa[0] = qw / den; qa[1] = qx / den; qa[2] = qy / den; qa[3] = qz / den; }
+    for (int k = 0; k < 3; ++k) rgb[k] = activated ? row[10 + k] : fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
+    *o = activated ? row[13] : d_sigmoid(row[13]);
+}
+
+/* vector-Jacobian product of the adapter: v_act = dL/d(means | scales | quats | colours | opacity) as
+ * gsplat.rendering.rasterization receives them  ->  d += dL/d(raw row) (what autograd does through :183-193) */
+static void adapter3d_vjp_one(const float *row, const float *s, float qn_raw, float o, const double *v_act, double *d)
+{
+    for (int k = 0; k < 3; ++k) d[k] += v_act[k];
+    for (int k = 0; k < 3; ++k) d[3 + k] += v_act[3 + k] * s[k]; /* scale = exp(log_scale) */
+    /* qa = q / (|q| + 1e-8) */
+    double n = qn_raw, den = n + 1e-8;
+    double dq = v_act[6] * row[6] + v_act[7] * row[7] + v_act[8] * row[8] + v_act[9] * row[9];
+    for (int k = 0; k < 4; ++k) {
+        double g0 = v_act[6 + k] / den;
+        if (n > 0.0) g0 -= dq / (den * den) * (row[6 + k] / n);
+        d[6 + k] += g0;
+    }
+    for (int k = 0; k < 3; ++k)
+        if (row[10 + k] >= 0.0f && row[10 + k] <= 1.0f) d[10 + k] += v_act[10 + k];
+    d[13] += v_act[13] * (double)o * (1.0 - (double)o);
+}
+
+/* Adapter stage alone (parity fixture tests/golden/adapter3d_reference.npz): act [N,14] and, if v_act is given,
+ * d_params [N,14] += J^T v_act */
+void ora3d_adapter(const float *params, int N, float *act, const double *v_act, double *d_params)
+{
+    for (int i = 0; i < N; ++i) {
+        const float *row = params + 14 * (size_t)i;
+        float s[3], qa[4], qn, rgb[3], o;
+        adapter3d_one(row, 0, s, qa, &qn, rgb, &o);
+        float *a = act + 14 * (size_t)i;
+        for (int k = 0; k < 3; ++k) { a[k] = row[k]; a[3 + k] = s[k]; a[10 + k] = rgb[k]; }
+        for (int k = 0; k < 4; ++k) a[6 + k] = qa[k];
+        a[13] = o;
+        if (v_act) adapter3d_vjp_one(row, s, qn, o, v_act + 14 * (size_t)i, d_params + 14 * (size_t)i);
+    }
+}
+
 static int project3d_one(const float *row, const float *V, const float *K, int W, int H,
                          float near_plane, float far_plane, float radius_clip, float eps2d,
                          float *geom, float *rgb, int *rect, int *tile_rect, uint32_t *low,
@@ -177,16 +228,8 @@ static int project3d_one(const float *row, const float *V, const float *K, int W
     /* adapter: src/gaussian_renderer.py:183-193.  activated != 0: the row already holds scales, quaternion,
      * colours and opacity as gsplat.rendering.rasterization receives them (src/model.py:342-361): no exp, no
      * q/(|q|+1e-8), no clamp, no sigmoid (gsplat still normalises the quaternion itself) */
-    for (int k = 0; k < 3; ++k) t->s[k] = activated ? row[3 + k] : d_exp(row[3 + k]);
-    float qw = row[6], qx = row[7], qy = row[8], qz = row[9];
-    float n2 = fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, qw * qw)));
-    float qn = sqrtf(n2);
-    t->qn_raw = qn;
-    float den = qn + 1e-8f;
-    if (activated) { t->qa[0] = qw; t->qa[1] = qx; t->qa[2] = qy; t->qa[3] = qz; }
-    else { t->qa[0] = qw / den; t->qa[1] = qx / den; t->qa[2] = qy / den; t->qa[3] = qz / den; }
-    for (int k = 0; k < 3; ++k) rgb[k] = activated ? row[10 + k] : fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
-    float o = activated ? row[13] : d_sigmoid(row[13]);
+    float o;
+    adapter3d_one(row, activated, t->s, t->qa, &t->qn_raw, rgb, &o);
 
     for (int k = 0; k < 8; ++k) geom[k] = 0.0f;
     rect[0] = rect[1] = rect[2] = rect[3] = 0;
@@ -698,11 +741,14 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         /* colour and opacity do not depend on visibility of the projection */
         int ok = project3d_one(row, V, K, W, H, near_plane, far_plane, radius_clip, eps2d,
                                geom, rgb, rect, trect, &low, &t, activated);
-        for (int k = 0; k < 3; ++k)
-            if (activated || (row[10 + k] >= 0.0f && row[10 + k] <= 1.0f)) d[10 + k] += a[k];
-        double o = geom[5];
-        d[13] += activated ? a[8] : a[8] * o * (1.0 - o);
-        if (!ok) continue;
+        double v_act[14] = { 0 }; /* gradient w.r.t. the activated values (what gsplat's backward returns) */
+        for (int k = 0; k < 3; ++k) v_act[10 + k] = a[k];
+        v_act[13] = a[8];
+        if (!ok) {
+            if (activated) { for (int k = 0; k < 14; ++k) d[k] += v_act[k]; }
+            else adapter3d_vjp_one(row, t.s, t.qn_raw, geom[5], v_act, d);
+            continue;
+        }
         double fx = K[0], fy = K[4];
         /* conic = inverse(cov2d): G_S = -X G_X X with G_X = [[vA, vB/2],[vB/2, vC]] */
         double XA = geom[2], XB = geom[3], XC = geom[4];
@@ -750,7 +796,7 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         double Rw[3][3];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) Rw[r][c] = V[4 * r + c];
-        for (int c = 0; c < 3; ++c) d[c] += Rw[0][c] * vpc[0] + Rw[1][c] * vpc[1] + Rw[2][c] * vpc[2];
+        for (int c = 0; c < 3; ++c) v_act[c] = Rw[0][c] * vpc[0] + Rw[1][c] * vpc[1] + Rw[2][c] * vpc[2];
         double GS[3][3];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) {
@@ -772,7 +818,7 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         double GR[3][3], vs[3] = { 0, 0, 0 };
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) { GR[r][c] = GM[r][c] * t.s[c]; vs[c] += Rq[r][c] * GM[r][c]; }
-        for (int k = 0; k < 3; ++k) d[3 + k] += activated ? vs[k] : vs[k] * t.s[k]; /* scale = exp(log_scale) */
+        for (int k = 0; k < 3; ++k) v_act[3 + k] = vs[k];
         /* R(qh) */
         double w = t.qh[0], qx = t.qh[1], qy = t.qh[2], qz = t.qh[3];
         double vq[4];
@@ -785,14 +831,8 @@ void ora3d_project_bwd(const float *params, int N, const float *V, const float *
         double va[4];
         double qhv[4] = { w, qx, qy, qz };
         for (int k = 0; k < 4; ++k) va[k] = (vq[k] - dot * qhv[k]) * t.inv2;
-        if (activated) { for (int k = 0; k < 4; ++k) d[6 + k] += va[k]; continue; }
-        /* qa = q / (|q| + 1e-8) */
-        double n = t.qn_raw, den = n + 1e-8;
-        double dq = va[0] * row[6] + va[1] * row[7] + va[2] * row[8] + va[3] * row[9];
-        for (int k = 0; k < 4; ++k) {
-            double g0 = va[k] / den;
-            if (n > 0.0) g0 -= dq / (den * den) * (row[6 + k] / n);
-            d[6 + k] += g0;
-        }
+        for (int k = 0; k < 4; ++k) v_act[6 + k] = va[k];
+        if (activated) { for (int k = 0; k < 14; ++k) d[k] += v_act[k]; }
+        else adapter3d_vjp_one(row, t.s, t.qn_raw, geom[5], v_act, d);
     }
 }

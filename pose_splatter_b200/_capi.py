@@ -18,7 +18,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy", "ps_forward", "ps_forward_rgba8", "ps_backward", "ps_backward_peer", "ps_peer_sum",
            "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
            "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe", "ps_view_loss",
-           "ps_param_head_forward", "ps_param_head_backward")
+           "ps_param_head_forward", "ps_param_head_backward", "ps_adapter3d_probe")
 
 STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd", "blocks")
 FLAG_RASTER_STATS = 4
@@ -71,6 +71,7 @@ def load() -> ctypes.CDLL:
     lib.ps_ctx_launch_count.argtypes = [vp]
     lib.ps_ctx_launch_count.restype = ctypes.c_int64
     lib.ps_math_probe.argtypes = [vp, vp, ip, vp, vp]
+    lib.ps_adapter3d_probe.argtypes = [vp, vp, ip, vp, vp, vp, vp]
     lib.ps_ctx_set_profiling.argtypes = [vp, ip]
     lib.ps_ctx_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ip]
     lib.ps_ctx_raster_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ip, vp]

@@ -597,6 +597,16 @@ int ps_math_probe(ps_ctx *ctx, const float *x, int n, float *y, void *stream)
     return 0;
 }
 
+int ps_adapter3d_probe(ps_ctx *ctx, const float *rows, int n, const float *v_act, float *act, float *d_rows, void *stream)
+{
+    if (!ctx) return fail(1, "ps_adapter3d_probe: NULL context");
+    if (n > 0 && (!rows || !act)) return fail(1, "ps_adapter3d_probe: NULL buffer");
+    if ((v_act == nullptr) != (d_rows == nullptr)) return fail(1, "ps_adapter3d_probe: v_act and d_rows go together");
+    PS_CUDA(cudaSetDevice(ctx->device));
+    PS_LAUNCH(ctx, ps_launch_adapter3d_probe(rows, n, v_act, act, d_rows, (cudaStream_t)stream));
+    return 0;
+}
+
 int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *rgb, const float *alpha,
                  const float *target_img, const float *target_mask, float ssim_lambda, float img_lambda,
                  float *losses, float *d_rgb, float *d_alpha, void *stream)

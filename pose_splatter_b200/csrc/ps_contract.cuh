@@ -159,6 +159,45 @@ PS_HD void ps_record_clear(PsRecord *rec)
     rec->thr = 0.0f;
 }
 
+// The adapter of GaussianRenderer3D.render (src/gaussian_renderer.py:183-193): scales = exp(log_scales),
+// quats = q / (|q| + 1e-8), colours = clamp(c, 0, 1), opacities = sigmoid(logit) -- the values the reference hands to
+// gsplat.rendering.rasterization (:196-208).  activated != 0: the row already holds them (identity).
+// Pinned by tests/golden/adapter3d_reference.npz (the reference's own lines, gsplat stubbed).
+PS_HD void ps_adapter3d(const float *row, int activated, float *s, float *qa, float *qn_raw, float *rgb, float *o)
+{
+    for (int k = 0; k < 3; ++k) s[k] = activated ? row[3 + k] : psm_exp(row[3 + k]);
+    float qw = row[6], qx = row[7], qy = row[8], qz = row[9];
+    float n2 = psm_fma(qz, qz, psm_fma(qy, qy, psm_fma(qx, qx, psm_mul(qw, qw))));
+    float qn = psm_sqrt(n2);
+    *qn_raw = qn;
+    float den = psm_add(qn, 1e-8f);
+    if (activated) { qa[0] = qw; qa[1] = qx; qa[2] = qy; qa[3] = qz; }
+    else {
+        qa[0] = psm_div(qw, den); qa[1] = psm_div(qx, den);
+        qa[2] = psm_div(qy, den); qa[3] = psm_div(qz, den);
+    }
+    for (int k = 0; k < 3; ++k) rgb[k] = activated ? row[10 + k] : fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
+    *o = activated ? row[13] : psm_sigmoid(row[13]);
+}
+
+// Vector-Jacobian product of the adapter (what autograd does through :183-193): v_act = gradient w.r.t. the activated
+// values (means | scales | quats | colours | opacity, the layout gsplat's backward returns)  ->  out[14] = gradient w.r.t.
+// the raw row.  Free-form fp32 (gradients are tolerance-checked).
+PS_HD void ps_adapter3d_vjp(const float *row, const float *s, float qn_raw, float o, const float *v_act, float *out)
+{
+    for (int k = 0; k < 3; ++k) out[k] = v_act[k];
+    for (int k = 0; k < 3; ++k) out[3 + k] = v_act[3 + k] * s[k];
+    const float n = qn_raw, den = n + 1e-8f;
+    const float dq = v_act[6] * row[6] + v_act[7] * row[7] + v_act[8] * row[8] + v_act[9] * row[9];
+    for (int k = 0; k < 4; ++k) {
+        float g0 = v_act[6 + k] / den;
+        if (n > 0.0f) g0 -= dq / (den * den) * (row[6 + k] / n);
+        out[6 + k] = g0;
+    }
+    for (int k = 0; k < 3; ++k) out[10 + k] = (row[10 + k] >= 0.0f && row[10 + k] <= 1.0f) ? v_act[10 + k] : 0.0f;
+    out[13] = v_act[13] * o * (1.0f - o);
+}
+
 // Adapter activations + EWA projection of one Gaussian for one camera. Returns 1 if visible.
 // activated != 0: the row already holds scales / quaternion / colours / opacity as gsplat's rasterization() takes
 // them (the legacy PoseSplatter.splat call, src/model.py:342-361): no exp, no q/(|q|+1e-8), no clamp, no sigmoid.
@@ -166,19 +205,8 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
                        float far_plane, float radius_clip, float eps2d, PsRecord *rec, PsProj3dAux *t, int activated = 0)
 {
     ps_record_clear(rec);
-    for (int k = 0; k < 3; ++k) t->s[k] = activated ? row[3 + k] : psm_exp(row[3 + k]);
-    float qw = row[6], qx = row[7], qy = row[8], qz = row[9];
-    float n2 = psm_fma(qz, qz, psm_fma(qy, qy, psm_fma(qx, qx, psm_mul(qw, qw))));
-    float qn = psm_sqrt(n2);
-    t->qn_raw = qn;
-    float den = psm_add(qn, 1e-8f);
-    if (activated) { t->qa[0] = qw; t->qa[1] = qx; t->qa[2] = qy; t->qa[3] = qz; }
-    else {
-        t->qa[0] = psm_div(qw, den); t->qa[1] = psm_div(qx, den);
-        t->qa[2] = psm_div(qy, den); t->qa[3] = psm_div(qz, den);
-    }
-    for (int k = 0; k < 3; ++k) rec->r2[k] = activated ? row[10 + k] : fminf(fmaxf(row[10 + k], 0.0f), 1.0f);
-    float o = activated ? row[13] : psm_sigmoid(row[13]);
+    float o;
+    ps_adapter3d(row, activated, t->s, t->qa, &t->qn_raw, rec->r2, &o);
     rec->r1[3] = o;
 
     float a0 = t->qa[0], a1 = t->qa[1], a2 = t->qa[2], a3 = t->qa[3];

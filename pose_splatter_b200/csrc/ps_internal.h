@@ -97,4 +97,5 @@ int ps_launch_head_bwd(int mode, int n, const float *net_out, const float *probs
                        const float *d_rows, float *d_net, float *d_probs, float *d_scale0, cudaStream_t s);
 
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);
+int ps_launch_adapter3d_probe(const float *rows, int n, const float *v_act, float *act, float *d_rows, cudaStream_t s);
 int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s);

@@ -121,10 +121,14 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
         PsProj3dAux x;
         const int ok = ps_project3d(r, cam, cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x,
                                     g.activated);
+        // v[14]: gradient w.r.t. the activated values (means | scales | quats | colours | opacity), i.e. what gsplat's
+        // backward hands to autograd; the adapter's own vector-Jacobian product maps it to the raw row below
+        float v[14];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o[10 + k] = (g.activated || (r[10 + k] >= 0.0f && r[10 + k] <= 1.0f)) ? a[k] : 0.0f;
-        const float op = rec.r1[3];
-        o[13] = g.activated ? a[8] : a[8] * op * (1.0f - op);
+        for (int k = 0; k < 14; ++k) v[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[10 + k] = a[k];
+        v[13] = a[8];
         if (ok) {
             const float *V = cam, *K = cam + 16;
             const float fx = K[0], fy = K[4];
@@ -166,7 +170,7 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
             if (!x.clampy) { vpc1 += -fy * rz2 * GJ[1][2]; vpc2 += 2.0f * fy * x.ty * rz3 * GJ[1][2]; }
             else { vpc2 += fy * x.ty * rz3 * GJ[1][2]; }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) o[c] = V[c] * vpc0 + V[4 + c] * vpc1 + V[8 + c] * vpc2;
+            for (int c = 0; c < 3; ++c) v[c] = V[c] * vpc0 + V[4 + c] * vpc1 + V[8 + c] * vpc2;
             // G_Sigma = Rwc^T GSc Rwc
             float Tm[3][3], GS[3][3];
 #pragma unroll
@@ -191,7 +195,7 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
                 float vs = 0.0f;
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr) { GR[rr][c] = GM[rr][c] * x.s[c]; vs += x.R[3 * rr + c] * GM[rr][c]; }
-                o[3 + c] = g.activated ? vs : vs * x.s[c];
+                v[3 + c] = vs;
             }
             const float w = x.qh[0], qx = x.qh[1], qy = x.qh[2], qz = x.qh[3];
             float vq[4];
@@ -200,22 +204,14 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
             vq[2] = 2.0f * (-2.0f * qy * GR[0][0] + qx * GR[0][1] + w * GR[0][2] + qx * GR[1][0] + qz * GR[1][2] - w * GR[2][0] + qz * GR[2][1] - 2.0f * qy * GR[2][2]);
             vq[3] = 2.0f * (-2.0f * qz * GR[0][0] - w * GR[0][1] + qx * GR[0][2] + w * GR[1][0] - 2.0f * qz * GR[1][1] + qy * GR[1][2] + qx * GR[2][0] + qy * GR[2][1]);
             const float dot = vq[0] * w + vq[1] * qx + vq[2] * qy + vq[3] * qz;
-            float va[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) va[k] = (vq[k] - dot * x.qh[k]) * x.inv2;
-            if (g.activated) {
+            for (int k = 0; k < 4; ++k) v[6 + k] = (vq[k] - dot * x.qh[k]) * x.inv2;
+        }
+        if (g.activated) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) o[6 + k] = va[k];
-            } else {
-                const float n = x.qn_raw, den = n + 1e-8f;
-                const float dq = va[0] * r[6] + va[1] * r[7] + va[2] * r[8] + va[3] * r[9];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float g0 = va[k] / den;
-                    if (n > 0.0f) g0 -= dq / (den * den) * (r[6 + k] / n);
-                    o[6 + k] = g0;
-                }
-            }
+            for (int k = 0; k < 14; ++k) o[k] = v[k];
+        } else {
+            ps_adapter3d_vjp(r, x.s, x.qn_raw, rec.r1[3], v, o);
         }
     }
 #pragma unroll
@@ -380,7 +376,40 @@ __global__ void math_probe_kernel(const float *x, int n, float *y)
     y[4 * n + i] = cs;
 }
 
+// adapter stage alone, through the device functions the projection kernels use (parity probe)
+__global__ void adapter3d_probe_kernel(const float *__restrict__ rows, int n, const float *__restrict__ v_act,
+                                       float *__restrict__ act, float *__restrict__ d_rows)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r[14], s[3], qa[4], qn, rgb[3], o;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) r[k] = rows[(size_t)i * 14 + k];
+    ps_adapter3d(r, 0, s, qa, &qn, rgb, &o);
+    float *a = act + (size_t)i * 14;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a[k] = r[k]; a[3 + k] = s[k]; a[10 + k] = rgb[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[6 + k] = qa[k];
+    a[13] = o;
+    if (v_act && d_rows) {
+        float v[14], out[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) v[k] = v_act[(size_t)i * 14 + k];
+        ps_adapter3d_vjp(r, s, qn, o, v, out);
+#pragma unroll
+        for (int k = 0; k < 14; ++k) d_rows[(size_t)i * 14 + k] = out[k];
+    }
+}
+
 } // namespace
+
+int ps_launch_adapter3d_probe(const float *rows, int n, const float *v_act, float *act, float *d_rows, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    adapter3d_probe_kernel<<<(n + 127) / 128, 128, 0, s>>>(rows, n, v_act, act, d_rows);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
                       const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = _capi.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.ps_abi_version() == 3
+    assert lib.ps_abi_version() == 4
 
 
 def test_context_creation_fails_loudly_without_gpu():

@@ -149,6 +149,27 @@ def test_2d_against_reference_goldens(name):
     assert rel.max() <= GRAD_TOL, rel
 
 
+@pytest.mark.parametrize("name", ["ref2d_c3_workload_576x512_n16000", "ref2d_c3_spread_576x512_n16000",
+                                  "ref2d_c3_grad_576x512_n1024", "ref2d_c5_workload_1152x1024_n4096"])
+def test_2d_against_reference_goldens_full_size(name):
+    """CUDA 2D path vs outputs of the unmodified reference class at the metric's sizes (make_golden_fullsize.py):
+    576x512 N = 16000 (bench workload view; whole-image spread), fwd+bwd at 576x512 N = 1024, 1152x1024 N = 4096."""
+    z = np.load(GOLDEN / f"{name}.npz")
+    W, H = int(z["W"]), int(z["H"])
+    has_grad = "grad" in z.files
+    w_rgb = w_a = None
+    if has_grad:
+        w_rgb, w_a = golden_cotangents(int(z["seed_w"]), H, W)
+        w_rgb, w_a = w_rgb[None], w_a[None]
+    got = _run_product("2d", torch.from_numpy(z["params"])[None], torch.zeros(1, dtype=torch.int32), W, H, z["bg"],
+                       w_rgb=w_rgb, w_a=w_a)
+    assert np.abs(got["rgb"][0] - z["rgb"]).max() <= RGB_TOL
+    assert np.abs(got["alpha"][0] - z["alpha"]).max() <= RGB_TOL
+    if has_grad:
+        rel = column_rel_err(got["d_params"][0], z["grad"])
+        assert rel.max() <= GRAD_TOL, rel
+
+
 @pytest.mark.parametrize("name", ["ref2d_random_96x80", "ref2d_adversarial_70x50", "ref2d_c1_192x171"])
 def test_2d_against_oracle_bit_exact_binning(name):
     z = np.load(GOLDEN / f"{name}.npz")
@@ -198,10 +219,11 @@ def test_autograd_function_matches_raw_backward():
 # ------------------------------------------------------------------------------------------
 # BASELINE.json full sizes
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("wl,cams", [("c2", 2), ("c3", 1), ("c1", 2)])
+@pytest.mark.parametrize("wl,cams", [("c2", 2), ("c3", 1), ("c1", 2), ("c5_3d", 1), ("c5_2d", 1)])
 def test_full_size_workload_against_oracle(wl, cams):
     """Full N and full resolution of the benchmark configs (c2: 3D 288x256 N=16000; c3: 2D 576x512 N=16000;
-    c1: 2D 192x171 N=4096): every bit-exact stage and the tolerances, against the oracle."""
+    c1: 2D 192x171 N=4096; c5: 1152x1024 N=16000 in both modes): every bit-exact stage and the tolerances,
+    against the oracle."""
     _, _, _, synth = _mods()
     d = synth.make_views(wl, n_frames=1, n_cams=cams, seed=21)
     _compare(d["mode"], d["params"], d["view_frame"], d["width"], d["height"], (1.0, 1.0, 1.0), d["viewmats"], d["Ks"])

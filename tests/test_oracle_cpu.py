@@ -35,6 +35,28 @@ def test_oracle_2d_matches_reference_fixture(name):
     assert rel.max() <= GRAD_TOL, rel
 
 
+FULLSIZE_2D = ["ref2d_c3_workload_576x512_n16000", "ref2d_c3_spread_576x512_n16000", "ref2d_c3_grad_576x512_n1024",
+               "ref2d_c5_workload_1152x1024_n4096"]
+
+
+@pytest.mark.parametrize("name", FULLSIZE_2D)
+def test_oracle_2d_matches_reference_fixture_full_size(name):
+    """Outputs of the unmodified reference class at the sizes the metric is quoted on (make_golden_fullsize.py):
+    c3 576x512 with N = 16000 (the bench workload itself and a whole-image spread), fwd+bwd at 576x512 N = 1024,
+    and 1152x1024 (c5) with N = 4096."""
+    z = np.load(GOLDEN / f"{name}.npz")
+    W, H = int(z["W"]), int(z["H"])
+    if "grad" in z.files:
+        w_rgb, w_a = golden_cotangents(int(z["seed_w"]), H, W)
+        o = ora.render("2d", z["params"], W, H, z["bg"], w_rgb=w_rgb.numpy(), w_a=w_a.numpy())
+        rel = column_rel_err(o["d_params"], z["grad"])
+        assert rel.max() <= GRAD_TOL, rel
+    else:
+        o = ora.render("2d", z["params"], W, H, z["bg"])
+    assert np.abs(o["rgb"] - z["rgb"]).max() <= RGB_TOL
+    assert np.abs(o["alpha"] - z["alpha"]).max() <= RGB_TOL
+
+
 def test_oracle_2d_reference_known_answers():
     """The reference's own single / two Gaussian cases (tests/test_gaussian_renderer.py:58-125): its actual rows."""
     z = np.load(GOLDEN / "ref2d_known_answers.npz")

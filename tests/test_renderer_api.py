@@ -100,7 +100,7 @@ def test_new_rows_fail_loudly_without_cuda():
         losses.get_iou_loss(torch.rand(4, 4), torch.rand(4, 5))
 
 
-def test_product_never_imports_the_oracle():
+def test_shims_and_host_modules_never_import_the_oracle():
     """only tests/, smoke() and bench.py's CPU legs may touch oracle/"""
     from pathlib import Path
     root = Path(__file__).resolve().parent.parent
