@@ -28,7 +28,11 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 METRIC = "fwd+bwd rendered views/s (6-cam, 576\u00d7512 2D / 288\u00d7256 3D GS) at 1/2/4/8 B200"
-FLOPS_PER_PAIR = {"raster_fwd": 27.0, "raster_bwd": 60.0}  # SURVEY.md 8d-d4 pair model (FP32 ops per evaluated pair)
+# SURVEY.md 8d-d4 pair model, split by what a pair actually costs: every evaluated pair pays the
+# sigma / alpha evaluation (2 sub, 9 sigma, 2 exp scaling, o*e, min, 3 compares = 21 forward; + T recovery = 24 backward);
+# only contributing pairs pay compositing (6 colour FMA-flops forward) or the gradient terms (36 backward)
+FLOPS_EVAL = {"raster_fwd": 21.0, "raster_bwd": 24.0}
+FLOPS_CONTRIB = {"raster_fwd": 6.0, "raster_bwd": 36.0}
 
 
 def parse():
@@ -198,7 +202,33 @@ def run_measurements(args, world, rank, local, dev):
         other = measure(args, "c3", max(2, min(3, args.steps)), world, rank, local, dev, primary=False)
         if rank == 0:
             out["also"] = {"c3": {k: other[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline",
-                                                        "stage_ms_per_step", "pairs")}}
+                                                        "stage_ms_per_step", "pairs", "per_kernel")}}
+    return out
+
+
+def per_kernel_traffic(wl, mode, V, N, M, n_lists, stats_all, stage_ms):
+    """Algorithmic bytes per launch of every HBM-relevant kernel (formulas of DESIGN.md section 7) beside the DRAM bytes of
+    the committed ncu capture (profiles/ncu_traffic.json) and the live CUDA-event time of its stage."""
+    VN = V * N
+    P = 14 if mode == "3d" else 9
+    f, b = stats_all["fwd"], stats_all["bwd"]
+    rows_in = VN * 4 * P // (6 if mode == "3d" else 1)   # 3D: six cameras share a frame's rows
+    alg = {
+        "project": rows_in + VN * (64 + 8 + 4 + (4 if mode == "3d" else 0)),
+        "partition": VN * (4 + 8 + 32 + (4 if mode == "3d" else 0)) + M * 4,
+        "sort_split": M * (8 if mode == "3d" else 4) + f["entries_staged"] * 4,
+        "raster_fwd": f["entries_staged"] * 52 + n_lists * 256 * 28,
+        "raster_bwd": b["entries_staged"] * 52 + n_lists * 256 * 24 + b["entries_walked"] * 36,
+        "project_bwd": VN * (4 + 36 + 64) + 2 * rows_in,
+    }
+    stage_of = {"project": "project", "partition": "partition", "sort_split": "sort", "raster_fwd": "raster_fwd",
+                "raster_bwd": "raster_bwd", "project_bwd": "project_bwd"}
+    out = {}
+    for k, a in alg.items():
+        dram = ncu_traffic(wl, k)
+        ms = stage_ms[stage_of[k]][0]
+        out[k] = {"alg_bytes": int(a), "dram_bytes": dram, "ratio": (dram / a) if (dram and a) else None,
+                  "stage_ms": ms, "alg_gbs": a / (ms * 1e-3) / 1e9 if ms else None}
     return out
 
 
@@ -368,13 +398,14 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     drain_e2e()
     ms_e2e, _, _ = timed(step_e2e, steps, e2e=True)
 
-    # pair counts of one step (untimed) for the FP32 roofline of the rasterizers
+    # pair counts of one step (untimed): the SAME forward / backward kernels with their counters compiled in
     s0 = devs[0]
     _capi.raster_stats(dev, reset=True)
-    batched.forward_raw(mode, s0["params"], s0["view_frame"], s0["viewmats"], s0["Ks"], bg, W, H, _capi.FLAG_RASTER_STATS)
-    stats = _capi.raster_stats(dev, reset=True)
     _, _, _, sv = batched.forward_raw(mode, s0["params"], s0["view_frame"], s0["viewmats"], s0["Ks"], bg, W, H,
-                                      _capi.FLAG_SAVE_FOR_BACKWARD)
+                                      _capi.FLAG_SAVE_FOR_BACKWARD | _capi.FLAG_RASTER_STATS)
+    if not fwd_only:
+        batched.backward_raw(sv, s0["params"], s0["view_frame"], s0["viewmats"], s0["Ks"], bg, w_rgb, w_a)
+    stats_all = _capi.raster_stats(dev, reset=True)
     info = sv.info()
     M = int(info.n_isect)
     n_lists = int(info.n_lists)
@@ -397,44 +428,51 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     per_step = {k: v[0] / steps for k, v in stages.items()}
     dom = "raster_fwd" if fwd_only else max(("raster_fwd", "raster_bwd"), key=lambda k: per_step[k])
     dom_ms = stage_ms[dom][0]
-    achieved_tf = stats["pairs_evaluated"] * FLOPS_PER_PAIR[dom] / (dom_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+    stats = stats_all["bwd" if dom == "raster_bwd" else "fwd"]  # counters of the dominant kernel itself
+    # FP32 work of the pair model: every evaluated pair pays the alpha evaluation, only the
+    # contributing ones pay the compositing / gradient terms
+    flops = stats["pairs_evaluated"] * FLOPS_EVAL[dom] + stats["pairs_contributing"] * FLOPS_CONTRIB[dom]
+    achieved_tf = flops / (dom_ms * 1e-3) / 1e12
+    kname = {"raster_fwd": "raster_fwd6_kernel" if mode == "3d" else "raster_fwd_kernel", "raster_bwd": "raster_bwd2_kernel"}[dom]
+    roofline = {"bound": "fp32", "kernel": dom, "cuda_kernel": kname, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(wl, dom),
                 "peak_source": "FFMA micro-benchmark run in this process (ps_fp32_peak_probe), 2 flops per FMA; "
                                "MEASURED_PEAKS.json has no FP32 figure; no tensor cores on this path",
-                "work": f"{stats['pairs_evaluated']} evaluated (pixel,Gaussian) pairs per launch x {FLOPS_PER_PAIR[dom]:.0f} FP32 ops",
+                "work": f"counters of {kname} itself (same kernel, STATS template path): {stats['pairs_evaluated']} evaluated pairs x "
+                        f"{FLOPS_EVAL[dom]:.0f} + {stats['pairs_contributing']} contributing pairs x {FLOPS_CONTRIB[dom]:.0f} FP32 ops per launch",
                 "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / steps)}
-    # the same dominant kernel against the HBM roofline (SURVEY 8d-d4 bytes): per staged block-list entry 4 B position +
-    # 4 B id + 48 B record, per pixel 24 B of saved state and cotangents, 36 B of atomics per walked entry (backward only)
-    dom_bytes = stats["entries_staged"] * 56 + V * H * W * (24 if dom == "raster_bwd" else 20) + \
+    # the same kernel against the HBM roofline: per staged block-list entry 4 B id + 48 B record, per pixel OF A NON-EMPTY
+    # TILE 24 B (saved state + cotangents; forward: 20 B written + 8 B saved), 36 B of atomics per contributing entry (backward)
+    dom_bytes = stats["entries_staged"] * 52 + n_lists * 256 * (24 if dom == "raster_bwd" else 28) + \
         (stats["entries_walked"] * 36 if dom == "raster_bwd" else 0)
     roofline["as_hbm"] = {"bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                          "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes": dom_bytes,
                           "note": "the rasterizers are instruction-issue bound, not HBM bound: this is how far below the HBM roofline they sit"}
     VN = V * (args.n or cfg["n"])
-    # rank: depth word + listed flag in, order + rank out; partition: rect + count + rank in, 4 B slot out per entry;
-    # list sort: slot in, order gather, 4 B value out per entry; scan: one int in/out per (view, tile)
-    # block lists: list id + 32 B (3D) / 16 B (2D) record gather in, ~1.8 block entries of 4 B out per list entry
-    sort_bytes = ((VN * 16 if mode == "3d" else 0) + VN * 16 + M * 4 + M * 12 + 8 * V * info.tiles_x * info.tiles_y
-                  + M * (4 + (32 if mode == "3d" else 16) + 8))
+    # rank: depth word + listed flag in, order + rank out; partition: rect + count + rank + 32 B of record in, 4 B slot word
+    # out per entry; sort + split: slot word in, order gather, 4 B per block-list entry out; scan: one int in/out per
+    # (view, tile)
+    sort_bytes = ((VN * 16 if mode == "3d" else 0) + VN * (16 + 32) + M * 4 + M * (8 if mode == "3d" else 4)
+                  + stats_all["fwd"]["entries_staged"] * 4 + 8 * V * info.tiles_x * info.tiles_y)
     sort_ms = stage_ms["rank"][0] + stage_ms["scan"][0] + stage_ms["partition"][0] + stage_ms["sort"][0] + stage_ms["blocks"][0]
     proj_bytes = VN * ((56 if mode == "3d" else 36) + 48 + 8 + 4)
-    binning = {"kernels": "depth_rank+scan+partition+list_sort+block_lists", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+    binning = {"kernels": "depth_rank+scan+partition+sort_split", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
                "unit": "GB/s", "frac": (sort_bytes / (sort_ms * 1e-3) / 1e9) / hbm_peak if sort_ms else None, "ms_per_step": sort_ms,
                "work": f"M={M} list entries in {n_lists} non-empty (view,tile) lists, {VN} (view,Gaussian) records",
                "project": {"achieved": proj_bytes / (stage_ms['project'][0] * 1e-3) / 1e9 if stage_ms['project'][0] else None,
                            "unit": "GB/s", "avg_launch_ms": stage_ms["project"][0]}}
-    # the HBM-bound kernel of the path: block_lists.  Algorithmic bytes per tile-list entry: 4 (list id) + 32 (the two
-    # cull words of the splat record) + 4 per block-list entry written
-    blk_ms = stage_ms["blocks"][0]
-    blk_bytes = M * 36 + stats["entries_staged"] * 4
-    roof_hbm = {"bound": "hbm", "kernel": "block_lists", "achieved": blk_bytes / (blk_ms * 1e-3) / 1e9 if blk_ms else None,
+    # the HBM-side kernel of the binning: sort + block split (sort_split_kernel).  Algorithmic bytes per tile-list entry:
+    # 4 (slot word in) + 4 (depth-order gather, 3D) + 4 per block-list entry written
+    blk_ms = stage_ms["sort"][0]
+    blk_entries = stats_all["fwd"]["entries_staged"]
+    blk_bytes = M * (8 if mode == "3d" else 4) + blk_entries * 4
+    roof_hbm = {"bound": "hbm", "kernel": "sort_split", "achieved": blk_bytes / (blk_ms * 1e-3) / 1e9 if blk_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "frac": (blk_bytes / (blk_ms * 1e-3) / 1e9) / hbm_peak if blk_ms else None,
-                "traffic": ncu_traffic(wl, "block_lists"), "peak_source": hbm_src,
-                "work": f"{M} tile-list entries x 36 B in + {stats['entries_staged']} block-list entries x 4 B out",
+                "traffic": ncu_traffic(wl, "sort_split"), "peak_source": hbm_src, "algorithmic_bytes": blk_bytes,
+                "work": f"{M} tile-list slot words in + ~{blk_entries} block-list entries x 4 B out (staged entries, rounded up to chunks of 32)",
                 "avg_launch_ms": blk_ms,
-                "note": "DRAM traffic is above the algorithmic bytes because a 32-byte gather costs a 64-byte DRAM access and "
-                        "records are shared by tiles that run far apart (size-ordered work list); see DESIGN.md section 7"}
+                "note": "work list + sort + block split of every list in one kernel, no record gathers; latency bound (DESIGN.md section 7)"}
+    per_kernel = per_kernel_traffic(wl, mode, V, args.n or cfg["n"], M, n_lists, stats_all, stage_ms)
     out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
@@ -450,7 +488,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                    "d2h_bytes_per_step": int(V * H * W * 4) if fwd_only else int(out_host[0].numel() * 4 + 4),
                    "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm, "binning": binning,
-           "stage_ms_per_step": per_step, "pairs": stats, "fp32_peak_tflops": fp32_peak}
+           "stage_ms_per_step": per_step, "pairs": stats_all, "per_kernel": per_kernel, "fp32_peak_tflops": fp32_peak}
     if primary and not fwd_only:
         # the reference's own call shape: ONE view per render() + backward through the drop-in class (SURVEY 8d-d3 iii)
         from pose_splatter_b200 import create_renderer

@@ -28,7 +28,7 @@ extern "C" {
 
 #define PS_FLAG_SAVE_FOR_BACKWARD 1 /* keep the state ps_backward needs                        */
 #define PS_FLAG_KEEP_BINNING 2      /* also materialise the sorted int64 keys and keep last ids for the debug taps */
-#define PS_FLAG_RASTER_STATS 4      /* count (pixel, Gaussian) pairs in the forward rasterizer (bench only) */
+#define PS_FLAG_RASTER_STATS 4      /* count (pixel, Gaussian) pairs inside the rasterizers, forward and backward (bench only) */
 #define PS_FLAG_ACTIVATED_INPUTS 8  /* 3D rows = means | scales | quats | colours | opacity as gsplat's rasterization()
                                        takes them (src/model.py:342-361): no exp / q/(|q|+1e-8) / clamp / sigmoid, and
                                        the gradient is w.r.t. those values                                          */
@@ -57,7 +57,9 @@ extern "C" {
 #define PS_TAP_REC2 8          /* float4 [V*N] 3D: r,g,b,0       2D: r,g,b,0                     */
 #define PS_TAP_DEPTH 9         /* uint32 [V*N] 3D: bits of the camera-space depth (key low word)  */
 
-typedef struct ps_ctx ps_ctx;     /* per-device context (stream-ordered scratch pool, pinned mailbox) */
+typedef struct ps_ctx ps_ctx;     /* per-device context (stream-ordered scratch pool, pinned mailbox slots); calls on one
+                                     context may come from several host threads: every forward owns its mailbox slot and
+                                     its ps_saved, shared bookkeeping is locked                                          */
 typedef struct ps_saved ps_saved; /* state of one forward kept for its backward / taps               */
 
 typedef struct ps_render_desc {
@@ -158,9 +160,12 @@ int64_t ps_ctx_launch_count(const ps_ctx *ctx);
  */
 int ps_ctx_set_profiling(ps_ctx *ctx, int on);
 int ps_ctx_stage_times(ps_ctx *ctx, double *ms, int64_t *calls, int reset);
-/* pairs[0] = pairs evaluated (lane passed the warp-level cull and was still active),
- * pairs[1] = contributing pairs, pairs[2] = tile-list entries walked by warps after culling,
- * pairs[3] = tile-list entries staged; accumulated by forwards run with PS_FLAG_RASTER_STATS. */
+/* Pair counters of the kernels that ran with PS_FLAG_RASTER_STATS (the SAME kernels that are timed, with the counters
+ * compiled in; a backward counts when its forward had the flag).  pairs[8]:
+ *   [0] forward: (pixel, entry) pairs whose sigma / q was evaluated   [4] backward: the same for the replay
+ *   [1] forward: contributing pairs                                   [5] backward: contributing pairs
+ *   [2] forward: block-list entries that reach a live pixel           [6] backward: entries that pass the chunk cull
+ *   [3] forward: block-list entries staged (chunks x 32)              [7] backward: entries staged               */
 int ps_ctx_raster_stats(ps_ctx *ctx, uint64_t *pairs, int reset, void *stream);
 /* FP32 FFMA micro-benchmark on this device: returns achieved TFLOP/s (2 flops per FMA) in *tflops. */
 int ps_fp32_peak_probe(ps_ctx *ctx, double *tflops, void *stream);
@@ -183,6 +188,14 @@ int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *r
                  float *losses, float *d_rgb, float *d_alpha, void *stream);
 
 /*
+ * The soft-IoU term alone -- get_iou_loss(predicted_mask, target_mask, eps=1e-6) of scripts/training/train_script.py:30-36,
+ * also used on its own for validation (:39-66): losses [V] = 1 - (sum(a m) + 1e-6) / (sum(a + m - a m) + 1e-6) and, if
+ * d_alpha is not NULL, its gradient [V,H,W].  Any image size; an all-zero target mask gives a finite value (the eps).
+ */
+int ps_iou_loss(ps_ctx *ctx, int n_views, int height, int width, const float *alpha, const float *target_mask, float *losses,
+                float *d_alpha, void *stream);
+
+/*
  * The parameter-head tail that produces the rows ps_forward takes, one thread per Gaussian.
  * Replaces src/model.py:207-257 (activations of get_gaussian_params_from_volume_unified after the MLP) and, with
  * pose != 0 in 3D mode, apply_pose_transform_3d :261-298 incl. quaternion_matrix_torch_batch :368-391 and
@@ -194,18 +207,18 @@ int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *r
  *   scale0    [1]     DEVICE pointer to the trainable self.scale                                         (:86,219)
  *   voxel_size, prob_threshold, clip_lo/hi = self.voxel_size, self.prob_threshold, self.color_clip
  *   pose, angle, p_3d_host[3] (HOST pointer)  yaw and translation of the frame (:275-280); or, for the rows of several
- *             frames in one launch, poses [F,5] = (cos, sin, px, py, pz) per frame and row_frame [n] int32 (DEVICE; both
- *             NULL = the scalar pose)
+ *             frames in one launch, poses [n_frames,5] = (cos, sin, px, py, pz) per frame and row_frame [n] int32 (DEVICE;
+ *             both NULL = the scalar pose); a row whose frame id is outside [0, n_frames) comes out as NaN
  *   rows      [n,14|9] gaussian_params as render() takes them
  * Backward: d_net_out [n,14|9], d_probs_sel [n], d_scale0 [1] (device, overwritten) from d_rows.
  */
 int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, const float *grid_sel,
                           const float *scale0, float voxel_size, float prob_threshold, float clip_lo, float clip_hi,
                           int pose, double angle, const float *p_3d_host, const float *poses, const int32_t *row_frame,
-                          float *rows, void *stream);
+                          int n_frames, float *rows, void *stream);
 int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, float voxel_size,
                            float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *poses,
-                           const int32_t *row_frame, const float *d_rows, float *d_net_out, float *d_probs_sel, float *d_scale0,
+                           const int32_t *row_frame, int n_frames, const float *d_rows, float *d_net_out, float *d_probs_sel, float *d_scale0,
                            void *stream);
 
 /*

@@ -18,7 +18,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libpsplat.so"
 EXPORTS = ("ps_abi_version", "ps_last_error", "ps_ctx_create", "ps_ctx_destroy", "ps_forward", "ps_forward_rgba8", "ps_backward", "ps_backward_peer", "ps_peer_sum",
            "ps_saved_info_get", "ps_saved_copy", "ps_saved_release", "ps_ctx_launch_count", "ps_math_probe",
            "ps_ctx_set_profiling", "ps_ctx_stage_times", "ps_ctx_raster_stats", "ps_fp32_peak_probe", "ps_view_loss",
-           "ps_param_head_forward", "ps_param_head_backward", "ps_adapter3d_probe")
+           "ps_param_head_forward", "ps_param_head_backward", "ps_adapter3d_probe", "ps_iou_loss")
 
 STAGES = ("project", "rank", "scan", "partition", "sort", "raster_fwd", "raster_bwd", "project_bwd", "blocks")
 FLAG_RASTER_STATS = 4
@@ -77,8 +77,9 @@ def load() -> ctypes.CDLL:
     lib.ps_ctx_raster_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ip, vp]
     lib.ps_fp32_peak_probe.argtypes = [vp, ctypes.POINTER(ctypes.c_double), vp]
     cf, cd = ctypes.c_float, ctypes.c_double
-    lib.ps_param_head_forward.argtypes = [vp, ip, ip, vp, vp, vp, vp, cf, cf, cf, cf, ip, cd, ctypes.POINTER(cf), vp, vp, vp, vp]
-    lib.ps_param_head_backward.argtypes = [vp, ip, ip, vp, vp, cf, cf, cf, cf, ip, cd, vp, vp, vp, vp, vp, vp, vp]
+    lib.ps_param_head_forward.argtypes = [vp, ip, ip, vp, vp, vp, vp, cf, cf, cf, cf, ip, cd, ctypes.POINTER(cf), vp, vp, ip, vp, vp]
+    lib.ps_param_head_backward.argtypes = [vp, ip, ip, vp, vp, cf, cf, cf, cf, ip, cd, vp, vp, ip, vp, vp, vp, vp, vp]
+    lib.ps_iou_loss.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, vp]
     lib.ps_view_loss.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp]
     _lib = lib
     return lib
@@ -120,10 +121,11 @@ def stage_times(device: torch.device, reset: bool = True):
 
 
 def raster_stats(device: torch.device, reset: bool = True):
-    out = (ctypes.c_uint64 * 4)()
+    """Pair counters of the rasterizer kernels that ran with FLAG_RASTER_STATS: {"fwd": {...}, "bwd": {...}}."""
+    out = (ctypes.c_uint64 * 8)()
     check(load().ps_ctx_raster_stats(context(device), out, int(reset), stream_ptr(device)), "ps_ctx_raster_stats")
-    return dict(pairs_evaluated=int(out[0]), pairs_contributing=int(out[1]), entries_walked=int(out[2]),
-                entries_staged=int(out[3]))
+    names = ("pairs_evaluated", "pairs_contributing", "entries_walked", "entries_staged")
+    return {"fwd": {n: int(out[i]) for i, n in enumerate(names)}, "bwd": {n: int(out[4 + i]) for i, n in enumerate(names)}}
 
 
 def fp32_peak_tflops(device: torch.device) -> float:

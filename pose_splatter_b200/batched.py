@@ -78,6 +78,14 @@ def _check_inputs(mode, params, view_frame, viewmats, Ks, background):
         raise ValueError("3D rendering needs viewmats [V,4,4] and Ks [V,3,3]")
     if background.shape != (3,):
         raise ValueError(f"Expected color shape (3,), got {background.shape}")
+    if view_frame.dim() != 1:
+        raise ValueError(f"Expected view_frame [V], got {tuple(view_frame.shape)}")
+    V = int(view_frame.shape[0])
+    if mode == "3d" and (tuple(viewmats.shape) != (V, 4, 4) or tuple(Ks.shape) != (V, 3, 3)):
+        raise ValueError(f"Expected viewmats [{V},4,4] and Ks [{V},3,3], got {tuple(viewmats.shape)} and {tuple(Ks.shape)}")
+    if not view_frame.is_cuda and V > 0 and (int(view_frame.min()) < 0 or int(view_frame.max()) >= params.shape[0]):
+        # a host-side map is checked for free; a device-side one is guarded inside the kernels (such views render nothing)
+        raise ValueError(f"view_frame entries must lie in [0, {params.shape[0]})")
 
 
 def forward_raw(mode, params, view_frame, viewmats, Ks, background, width, height, flags=0, want_counts=False, opts=None):

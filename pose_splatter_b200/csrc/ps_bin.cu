@@ -19,6 +19,7 @@
 // The sorted int64 keys are implied by (list id, depth word of vals[i]); ps_launch_debug_keys
 // materialises them for the bit-exact parity taps only.
 #include "ps_contract.cuh"
+#include "ps_cull.cuh"
 #include "ps_internal.h"
 
 namespace {
@@ -26,6 +27,7 @@ namespace {
 constexpr int RT = PS_RANK_THREADS;
 constexpr int RW = RT / 32;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t PS_SLOT_KEY_MASK = (1u << PS_SLOT_MASK_SHIFT) - 1u;
 
 // exclusive scan of s[0..255] in place, result total returned to every thread; all RT threads call
 __device__ __forceinline__ uint32_t scan256_exclusive(uint32_t *s, uint32_t *s_tmp)
@@ -317,6 +319,10 @@ build_worklist_kernel(const int32_t *__restrict__ offsets, int T, int32_t *__res
     }
 }
 
+// Every listed Gaussian drops one slot word into the list of every tile it touches: its depth rank (3D) / row index
+// (2D) in the low 24 bits and, above them, the 8-bit mask of the tile's 8x4 pixel blocks its footprint can reach
+// (ps_block_mask8 on the record the thread already holds: the block lists are later built from these masks without
+// touching the records again).
 template <int MODE>
 __global__ void __launch_bounds__(PS_PROJ_BLOCK)
 partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, int32_t *__restrict__ fill,
@@ -330,18 +336,28 @@ partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, i
     const int touched = live ? t.tiles_touched[idx] : 0;
     int tx0 = 0, ty0 = 0, tx1 = 0, ty1 = 0;
     uint32_t val = 0;
+    float gx = 0.0f, gy = 0.0f, thr = 0.0f, hA = 0.0f, B = 0.0f, hC = 0.0f;
     if (touched) {
         const uint2 tr = t.tile_rect[idx];
         tx0 = tr.x & 0xffff; ty0 = tr.x >> 16; tx1 = tr.y & 0xffff; ty1 = tr.y >> 16;
         val = (MODE == PS_MODE_3D) ? t.rank[idx] : (uint32_t)gi;
+        const float4 r0 = __ldg(PS_REC(t, idx, 0)), r1 = __ldg(PS_REC(t, idx, 1));
+        gx = r0.x; gy = r0.y; thr = r0.z;
+        hA = r1.x; B = r1.y; hC = r1.z;
+        if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
     }
+    const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
+    auto slot_word = [&](int tx, int ty) -> uint32_t {
+        const uint32_t m8 = ps_block_mask8(gx, gy, hA, B, hC, thr, half, tx, ty) & ps_blocks_inside8(tx, ty, g.W, g.H);
+        return val | (m8 << PS_SLOT_MASK_SHIFT);
+    };
     const int32_t *off_v = offsets + (size_t)v * g.n_tiles;
     int32_t *fill_v = fill + (size_t)v * g.n_tiles;
     if (!use_smem) { // very large tile grids: reserve every slot with a global atomic
         for (int ty = ty0; ty < ty1; ++ty)
             for (int tx = tx0; tx < tx1; ++tx) {
                 const int tl = ty * g.tiles_x + tx;
-                slots[off_v[tl] + atomicAdd(&fill_v[tl], 1)] = val;
+                slots[off_v[tl] + atomicAdd(&fill_v[tl], 1)] = slot_word(tx, ty);
             }
         return;
     }
@@ -362,7 +378,7 @@ partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, i
     for (int ty = ty0; ty < ty1; ++ty)
         for (int tx = tx0; tx < tx1; ++tx) {
             const int tl = ty * g.tiles_x + tx;
-            slots[s_base[tl] + atomicAdd(&s_cnt[tl], 1)] = val;
+            slots[s_base[tl] + atomicAdd(&s_cnt[tl], 1)] = slot_word(tx, ty);
         }
 }
 
@@ -398,7 +414,7 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
     for (int w = threadIdx.x; w < words; w += 256) s_bm[w] = 0u;
     __syncthreads();
     for (int i = start + threadIdx.x; i < end; i += 256) {
-        const uint32_t r = slots[i];
+        const uint32_t r = slots[i] & PS_SLOT_KEY_MASK;
         atomicOr(&s_bm[r >> 5], 1u << (r & 31u));
     }
     __syncthreads();
@@ -419,6 +435,110 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
     if (MODE == PS_MODE_3D) { // rank -> Gaussian with every thread gathering independently
         __syncthreads();
         for (int i = start + threadIdx.x; i < end; i += 256) vals[i] = vbase + __ldg(order + vbase + vals[i]);
+    }
+}
+
+// One CTA per non-empty list: sorts it AND splits it into the lists of the tile's eight 8x4 pixel blocks, without
+// reading a single splat record.  The keys of a list are unique integers < N, so nine bitmaps in shared memory (the
+// whole list + one per block, filled from the slot words' block masks) and their popcount prefixes give every entry
+// its position in the sorted tile list and in every block list it belongs to; the entry is then scattered there.
+//   vals  [start + pos]              = view * N + Gaussian           (the sorted tile list: gsplat's flatten_ids;
+//                                                                     NULL = not materialised, only the taps read it)
+//   blist [8 start + k len + pos_k]  = view * N + Gaussian           (block k's list, same order)
+//   bpos  [8 start + k len + pos_k]  = pos                           (only for the last-id tap, may be NULL)
+// Shared memory: 18 words per 32 keys (9 bitmaps + 9 prefix arrays).
+constexpr int SPLIT_THREADS = 256;
+constexpr int SPLIT_MAPS = 9;
+
+template <int MODE>
+__global__ void __launch_bounds__(SPLIT_THREADS)
+sort_split_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_t *__restrict__ offsets,
+                  const int32_t *__restrict__ worklist, const uint32_t *__restrict__ slots, uint32_t *__restrict__ vals,
+                  uint32_t *__restrict__ blist, uint32_t *__restrict__ bpos, int32_t *__restrict__ bcount,
+                  const int32_t *__restrict__ n_lists)
+{
+    extern __shared__ uint32_t s_dyn32[]; // bm [9][words] | pre [9][words]
+    __shared__ int s_wsum[SPLIT_THREADS / 32][SPLIT_MAPS];
+    const int item = blockIdx.x;
+    if (item >= __ldg(n_lists)) return; // the grid may be an upper bound (sync-free small calls)
+    const int lin = worklist[item];
+    const int start = offsets[lin], end = offsets[lin + 1], len = end - start;
+    const int view = lin / g.n_tiles;
+    const int words = (g.N + 31) >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t *bm = s_dyn32, *pre = s_dyn32 + SPLIT_MAPS * words;
+    for (int w = tid; w < SPLIT_MAPS * words; w += SPLIT_THREADS) bm[w] = 0u;
+    __syncthreads();
+    for (int i = start + tid; i < end; i += SPLIT_THREADS) {
+        const uint32_t sw = __ldg(slots + i);
+        const uint32_t r = sw & PS_SLOT_KEY_MASK;
+        uint32_t m8 = sw >> PS_SLOT_MASK_SHIFT;
+        const uint32_t bit = 1u << (r & 31u);
+        atomicOr(&bm[r >> 5], bit);
+        while (m8) {
+            const int k = __ffs(m8) - 1;
+            m8 &= m8 - 1;
+            atomicOr(&bm[(1 + k) * words + (r >> 5)], bit);
+        }
+    }
+    __syncthreads();
+    // exclusive popcount prefix of every bitmap: thread t owns a contiguous run of words
+    const int wpt = (words + SPLIT_THREADS - 1) / SPLIT_THREADS;
+    const int w0 = min(words, tid * wpt), w1 = min(words, w0 + wpt);
+    int cnt[SPLIT_MAPS], incl[SPLIT_MAPS];
+#pragma unroll
+    for (int j = 0; j < SPLIT_MAPS; ++j) {
+        int c = 0;
+        for (int w = w0; w < w1; ++w) c += __popc(bm[j * words + w]);
+        cnt[j] = c;
+        int x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += n;
+        }
+        incl[j] = x;
+        if (lane == 31) s_wsum[wid][j] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SPLIT_MAPS; ++j) {
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SPLIT_THREADS / 32; ++w) {
+            const int sgm = s_wsum[w][j];
+            base += (w < wid) ? sgm : 0;
+            total += sgm;
+        }
+        int run = base + incl[j] - cnt[j];
+        for (int w = w0; w < w1; ++w) {
+            pre[j * words + w] = (uint32_t)run;
+            run += __popc(bm[j * words + w]);
+        }
+        if (j > 0 && tid == 0) bcount[item * 8 + (j - 1)] = total;
+    }
+    __syncthreads();
+    const uint32_t vbase = (uint32_t)view * (uint32_t)g.N;
+    uint32_t *bl = blist + 8 * (size_t)start;
+    uint32_t *bp = bpos ? bpos + 8 * (size_t)start : nullptr;
+    for (int i = start + tid; i < end; i += SPLIT_THREADS) {
+        const uint32_t sw = __ldg(slots + i);
+        const uint32_t r = sw & PS_SLOT_KEY_MASK;
+        uint32_t m8 = sw >> PS_SLOT_MASK_SHIFT;
+        const uint32_t word = r >> 5, below = (1u << (r & 31u)) - 1u;
+        const uint32_t id = (MODE == PS_MODE_3D) ? vbase + __ldg(order + vbase + r) : vbase + r;
+        uint32_t pos = 0;
+        if (vals) { // the sorted tile list itself is only materialised for the parity taps
+            pos = pre[word] + __popc(bm[word] & below);
+            vals[start + pos] = id;
+        }
+        while (m8) {
+            const int k = __ffs(m8) - 1;
+            m8 &= m8 - 1;
+            const uint32_t pk = pre[(1 + k) * words + word] + __popc(bm[(1 + k) * words + word] & below);
+            bl[(size_t)k * len + pk] = id;
+            if (bp) bp[(size_t)k * len + pk] = pos;
+        }
     }
 }
 
@@ -516,6 +636,26 @@ int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l
     } else {
         if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
         sort_lists_kernel<PS_MODE_2D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals);
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// the fused sort + block split needs 18 shared-memory words per 32 Gaussians (72 KB at N = 128 K)
+bool ps_split_fits_smem(const PsGeometry &g)
+{
+    return (size_t)((g.N + 31) / 32) * 2 * SPLIT_MAPS * sizeof(uint32_t) <= 160 * 1024;
+}
+
+int ps_launch_sort_split(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
+{
+    if (n_work <= 0) return 0;
+    const size_t dyn = (size_t)((g.N + 31) / 32) * 2 * SPLIT_MAPS * sizeof(uint32_t);
+    if (g.mode == PS_MODE_3D) {
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_split_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        sort_split_kernel<PS_MODE_3D><<<n_work, SPLIT_THREADS, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, l.blist, l.bpos, l.bcount, l.n_lists);
+    } else {
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_split_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        sort_split_kernel<PS_MODE_2D><<<n_work, SPLIT_THREADS, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, l.blist, l.bpos, l.bcount, l.n_lists);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <unordered_map>
@@ -142,15 +144,20 @@ void dev_free(T *&p, cudaStream_t s)
 
 struct PsSpan { int stage; cudaEvent_t a, b; };
 
+// One forward's mailbox: {M, number of non-empty lists} stored by the scan kernel straight into mapped pinned host
+// memory (h = host view, d = device view of the same words).  No copy-engine transfer: a 16-byte memcpy would queue
+// behind whatever bulk device->host copy the application has in flight on another stream.  Every forward takes its
+// own slot (concurrent calls on one context never share one); like the arena blocks, a returned slot is reused on the
+// stream it was last written on, or after that stream has drained.
+struct PsMailbox { volatile int64_t *h; int64_t *d; cudaStream_t stream; };
+
 struct ps_ctx {
     int device;
-    int64_t launches;
-    // mailbox in mapped pinned host memory: the scan kernel stores {M, number of non-empty lists} straight into it
-    // (h_total = host view, d_total = device view of the same words).  No copy-engine transfer: a 16-byte memcpy
-    // would queue behind whatever bulk device->host copy the application has in flight on another stream.
-    volatile int64_t *h_total;
-    int64_t *d_total;
-    unsigned long long *d_stats; // [4] pair counters (PS_FLAG_RASTER_STATS)
+    std::atomic<int64_t> launches;
+    std::mutex mu;                       // guards everything below
+    std::vector<PsMailbox> mail_free;
+    std::vector<void *> mail_chunks;     // pinned allocations the slots live in
+    unsigned long long *d_stats;         // [8] pair counters (PS_FLAG_RASTER_STATS): forward [0..3], backward [4..7]
     bool profiling;
     std::vector<PsSpan> pending;
     std::vector<cudaEvent_t> spare;
@@ -159,6 +166,40 @@ struct ps_ctx {
 };
 
 namespace {
+constexpr int MAIL_WORDS = 4, MAIL_CHUNK = 64;
+
+cudaError_t mail_take(ps_ctx *ctx, cudaStream_t s, PsMailbox *out)
+{
+    std::unique_lock<std::mutex> lock(ctx->mu);
+    if (ctx->mail_free.empty()) {
+        int64_t *h = nullptr, *d = nullptr;
+        cudaError_t e = cudaHostAlloc((void **)&h, sizeof(int64_t) * MAIL_WORDS * MAIL_CHUNK, cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        e = cudaHostGetDevicePointer((void **)&d, (void *)h, 0);
+        if (e != cudaSuccess) { cudaFreeHost(h); return e; }
+        memset(h, 0, sizeof(int64_t) * MAIL_WORDS * MAIL_CHUNK);
+        ctx->mail_chunks.push_back(h);
+        for (int i = 0; i < MAIL_CHUNK; ++i) ctx->mail_free.push_back({ h + MAIL_WORDS * i, d + MAIL_WORDS * i, s });
+    }
+    int pick = (int)ctx->mail_free.size() - 1;
+    for (int i = pick; i >= 0; --i)
+        if (ctx->mail_free[i].stream == s) { pick = i; break; }
+    PsMailbox mb = ctx->mail_free[pick];
+    ctx->mail_free.erase(ctx->mail_free.begin() + pick);
+    lock.unlock();
+    if (mb.stream != s) cudaStreamSynchronize(mb.stream); // a write queued by its previous user cannot land in our call
+    mb.stream = s;
+    *out = mb;
+    return cudaSuccess;
+}
+
+void mail_give(ps_ctx *ctx, const PsMailbox &mb)
+{
+    if (!mb.h) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->mail_free.push_back(mb);
+}
+
 // brackets one stage with CUDA events on the launching stream when profiling is on
 struct StageTimer {
     ps_ctx *ctx; cudaStream_t s; PsSpan span; bool on;
@@ -166,9 +207,12 @@ struct StageTimer {
     {
         if (!on) return;
         span.stage = stage;
-        for (cudaEvent_t *e : { &span.a, &span.b }) {
-            if (!ctx->spare.empty()) { *e = ctx->spare.back(); ctx->spare.pop_back(); }
-            else if (cudaEventCreate(e) != cudaSuccess) { on = false; return; }
+        {
+            std::lock_guard<std::mutex> lock(ctx->mu);
+            for (cudaEvent_t *e : { &span.a, &span.b }) {
+                if (!ctx->spare.empty()) { *e = ctx->spare.back(); ctx->spare.pop_back(); }
+                else if (cudaEventCreate(e) != cudaSuccess) { on = false; return; }
+            }
         }
         cudaEventRecord(span.a, s);
     }
@@ -176,6 +220,7 @@ struct StageTimer {
     {
         if (!on) return;
         cudaEventRecord(span.b, s);
+        std::lock_guard<std::mutex> lock(ctx->mu);
         ctx->pending.push_back(span);
     }
 };
@@ -185,14 +230,34 @@ struct ps_saved {
     PsGeometry g;
     PsTable t;
     PsLists l;
+    ps_ctx *ctx;
+    cudaStream_t stream;  // the forward's stream
+    PsMailbox mail;
+    bool resolved;        // M / n_work below are known on the host (sync-free small calls resolve them lazily)
+    bool stats;           // the forward ran with PS_FLAG_RASTER_STATS: the backward counts its pairs too
     int64_t M;
-    int n_work;     // non-empty (view, tile) lists
+    int n_work;           // non-empty (view, tile) lists
+    int64_t cap_M;        // capacity of the list arrays (= M, or the worst case V * N * n_tiles of a sync-free call)
+    int cap_work;         // grid bound for the per-list kernels (= n_work, or V * n_tiles)
     uint64_t *keys; // sorted int64 keys, materialised only with PS_FLAG_KEEP_BINNING
     int32_t *last;  // [V,H,W] tile-list position + 1 of the last contributor (PS_FLAG_KEEP_BINNING: tap only)
     int32_t *blast; // [V,H,W] block-list index + 1 of the last contributor (what the backward starts from)
     int32_t *frame_off, *frame_views; // CSR: the views of every frame (projection backward sums them per row)
     float *t_pen;   // [V,H,W]
 };
+
+namespace {
+// M and the list count of a sync-free forward, read once its stream has drained
+int saved_resolve(ps_saved *sv)
+{
+    if (sv->resolved) return 0;
+    if (cudaStreamSynchronize(sv->stream) != cudaSuccess) return fail(2, "cudaStreamSynchronize failed while reading the forward's mailbox");
+    sv->M = sv->mail.h[0];
+    sv->n_work = (int)sv->mail.h[1];
+    sv->resolved = true;
+    return 0;
+}
+} // namespace
 
 extern "C" {
 
@@ -218,10 +283,8 @@ int ps_ctx_create(int device, ps_ctx **out)
     c->launches = 0;
     c->profiling = false;
     for (int i = 0; i < PS_N_STAGES; ++i) { c->stage_ms[i] = 0.0; c->stage_calls[i] = 0; }
-    PS_CUDA(cudaHostAlloc((void **)&c->h_total, 2 * sizeof(int64_t), cudaHostAllocMapped));
-    PS_CUDA(cudaHostGetDevicePointer((void **)&c->d_total, (void *)c->h_total, 0));
-    PS_CUDA(cudaMalloc((void **)&c->d_stats, 4 * sizeof(unsigned long long)));
-    PS_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+    PS_CUDA(cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long)));
+    PS_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
     *out = c;
     return 0;
 }
@@ -230,7 +293,8 @@ int ps_ctx_destroy(ps_ctx *ctx)
 {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    cudaFreeHost((void *)ctx->h_total);
+    cudaDeviceSynchronize();
+    for (void *h : ctx->mail_chunks) cudaFreeHost(h);
     cudaFree(ctx->d_stats);
     for (auto &sp : ctx->pending) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->spare) cudaEventDestroy(e);
@@ -242,7 +306,7 @@ int ps_ctx_destroy(ps_ctx *ctx)
     return 0;
 }
 
-int64_t ps_ctx_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t ps_ctx_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 static void saved_free(ps_saved *sv, cudaStream_t s)
 {
@@ -250,9 +314,12 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
     dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
     dev_free(sv->t.depth, s);
     dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
-    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bcount, s);
+    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bpos, s); dev_free(sv->l.bcount, s);
     dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->blast, s); dev_free(sv->t_pen, s);
     sv->frame_off = sv->frame_views = nullptr; // live inside the offsets allocation
+    sv->l.n_lists = nullptr;                   // lives inside cls
+    if (sv->ctx) mail_give(sv->ctx, sv->mail);
+    sv->mail.h = nullptr;
 }
 
 static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *params, const int32_t *view_frame,
@@ -279,6 +346,9 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
     ps_saved *sv = new (std::nothrow) ps_saved();
     if (!sv) return fail(4, "ps_forward: out of host memory");
     memset(sv, 0, sizeof *sv);
+    sv->ctx = ctx;
+    sv->stream = s;
+    sv->stats = (d->flags & PS_FLAG_RASTER_STATS) != 0;
     PsGeometry &g = sv->g;
     g.mode = d->mode; g.W = d->width; g.H = d->height; g.F = d->n_frames; g.N = d->n_gauss; g.V = d->n_views;
     g.tiles_x = (g.W + PS_TILE - 1) / PS_TILE; g.tiles_y = (g.H + PS_TILE - 1) / PS_TILE;
@@ -302,8 +372,17 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
         const size_t npix = (size_t)g.V * g.H * g.W;
         if (T > 0x7ffffff0ULL) { rc = fail(1, "ps_forward: %zu (view, tile) lists exceed 2^31", T); goto out; }
         if (g.N > (1 << 20)) { rc = fail(1, "ps_forward: at most 2^20 Gaussians per frame (got %d)", g.N); goto out; }
+        const bool split = ps_split_fits_smem(g); // sort + block split in one kernel (else: list sort, then record gathers)
+        // Small calls (the reference's own call shape: one view per render()) never wait for the host: the list arrays
+        // are sized for the worst case M = V * N * n_tiles and the per-list kernels are launched over all V * n_tiles
+        // lists, reading the exact counts on the device.  Large batches size everything exactly from the mailbox
+        // (one stream synchronisation): the worst case would not fit, and empty CTAs would cost more than the wait.
+        static const bool force_sync = getenv("PS_FORCE_SYNC") != nullptr; // A/B switch for measurements
+        const size_t worst = VN * (size_t)g.n_tiles;
+        const bool sync_free = !keep && !force_sync && split && VN > 0 && T <= 16384 && worst <= ((size_t)1 << 31) / 40;
         sv->M = 0;
         sv->n_work = 0;
+        sv->resolved = true;
         // offsets [T+1] | frame_off [F+1] | frame_views [V] | csr cursor [F] share one allocation: tiny pool
         // allocations split the large free blocks the next call wants to reuse
         PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1 + (size_t)g.F + 1 + (size_t)g.V + (size_t)g.F, s));
@@ -311,9 +390,11 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
         sv->frame_views = sv->frame_off + g.F + 1;
         csr_cursor = sv->frame_views + g.V;
         PS_TRY_CUDA(dev_alloc(&sv->l.cls, (size_t)PS_CLS_WORDS, s));
+        sv->l.n_lists = sv->l.cls + 3 * PS_N_CLASSES;
         PS_TRY_CUDA(dev_alloc(&scan_scratch, ps_scan_scratch_elems(g), s));
         PS_TRY_CUDA(cudaMemsetAsync(sv->l.offsets, 0, (T + 1) * sizeof(int32_t), s));
         if (VN > 0) {
+            PS_TRY_CUDA(mail_take(ctx, s, &sv->mail));
             PS_TRY_CUDA(dev_alloc(&sv->t.rec, 4 * VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
@@ -327,28 +408,43 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
                 StageTimer tm(ctx, PS_STAGE_RANK, s);
                 PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, s));
             }
-            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, ctx->d_total, s)); }
-            PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of the forward: M sizes the lists
-            sv->M = ctx->h_total[0];
-            sv->n_work = (int)ctx->h_total[1];
-            if (sv->M > 0x7fffffffLL) { rc = fail(1, "ps_forward: %lld tile intersections exceed 2^31", (long long)sv->M); goto out; }
+            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, sv->mail.d, s)); }
+            if (sync_free) {
+                sv->resolved = false;
+                sv->cap_M = (int64_t)worst;
+                sv->cap_work = (int)T;
+            } else {
+                PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of a large forward: M sizes the lists
+                sv->M = sv->mail.h[0];
+                sv->n_work = (int)sv->mail.h[1];
+                if (sv->M > 0x7fffffffLL) { rc = fail(1, "ps_forward: %lld tile intersections exceed 2^31", (long long)sv->M); goto out; }
+                sv->cap_M = sv->M;
+                sv->cap_work = sv->n_work;
+            }
         }
-        const int64_t M = sv->M;
-        if (M > 0) {
+        const size_t capM = (size_t)sv->cap_M, capW = (size_t)sv->cap_work;
+        if (capM > 0) {
             PS_TRY_CUDA(dev_alloc(&sv->l.fill, T, s));
-            PS_TRY_CUDA(dev_alloc(&sv->l.worklist, (size_t)sv->n_work, s));
-            PS_TRY_CUDA(dev_alloc(&sv->l.slots, (size_t)M, s));
-            PS_TRY_CUDA(dev_alloc(&sv->l.vals, (size_t)M, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.worklist, capW, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.slots, capM, s));
+            if (keep || !split) PS_TRY_CUDA(dev_alloc(&sv->l.vals, capM, s)); // the tile list: taps / the gather fallback
+            PS_TRY_CUDA(dev_alloc(&sv->l.blist, 8 * capM, s));
+            PS_TRY_CUDA(dev_alloc(&sv->l.bcount, 8 * capW, s));
+            if (keep) PS_TRY_CUDA(dev_alloc(&sv->l.bpos, 8 * capM, s));
             PS_TRY_CUDA(cudaMemsetAsync(sv->l.fill, 0, T * sizeof(int32_t), s));
             { StageTimer tm(ctx, PS_STAGE_PARTITION, s); PS_TRY_LAUNCH(ps_launch_partition(g, sv->t, sv->l, s)); }
-            { StageTimer tm(ctx, PS_STAGE_SORT, s);
-              PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
-              PS_TRY_LAUNCH(ps_launch_sort_lists(g, sv->t, sv->l, sv->n_work, s)); }
-            PS_TRY_CUDA(dev_alloc(&sv->l.blist, (size_t)8 * (size_t)M, s));
-            PS_TRY_CUDA(dev_alloc(&sv->l.bcount, (size_t)8 * (size_t)sv->n_work, s));
-            { StageTimer tm(ctx, PS_STAGE_BLOCKS, s); PS_TRY_LAUNCH(ps_launch_block_lists(g, sv->t, sv->l, sv->n_work, s)); }
+            if (split) {
+                StageTimer tm(ctx, PS_STAGE_SORT, s);
+                PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
+                PS_TRY_LAUNCH(ps_launch_sort_split(g, sv->t, sv->l, sv->cap_work, s));
+            } else {
+                { StageTimer tm(ctx, PS_STAGE_SORT, s);
+                  PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
+                  PS_TRY_LAUNCH(ps_launch_sort_lists(g, sv->t, sv->l, sv->n_work, s)); }
+                { StageTimer tm(ctx, PS_STAGE_BLOCKS, s); PS_TRY_LAUNCH(ps_launch_block_lists(g, sv->t, sv->l, sv->n_work, s)); }
+            }
             if (keep) {
-                PS_TRY_CUDA(dev_alloc(&sv->keys, (size_t)M, s));
+                PS_TRY_CUDA(dev_alloc(&sv->keys, capM, s));
                 PS_TRY_LAUNCH(ps_launch_debug_keys(g, sv->t, sv->l, sv->n_work, sv->keys, s));
             }
         }
@@ -361,16 +457,16 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             if (keep) PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
             PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, rgba8, s));
-            PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->n_work, background, rgb, alpha, n_contrib,
-                                               sv->last, sv->blast, sv->t_pen, rgba8, (d->flags & PS_FLAG_RASTER_STATS) ? ctx->d_stats : nullptr, s));
+            PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->cap_work, background, rgb, alpha, n_contrib,
+                                               sv->last, sv->blast, sv->t_pen, rgba8, sv->stats ? ctx->d_stats : nullptr, s));
         }
     }
 out:
     dev_free(rank_scratch, s);
     dev_free(scan_scratch, s);
-    dev_free(sv->l.fill, s); dev_free(sv->l.slots, s); dev_free(sv->l.cls, s);
+    dev_free(sv->l.fill, s); dev_free(sv->l.slots, s);
     dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
-    if (rc == 0 && !keep) { dev_free(sv->t.tile_rect, s); dev_free(sv->t.depth, s); }
+    if (rc == 0 && !keep) { dev_free(sv->t.tile_rect, s); dev_free(sv->t.depth, s); dev_free(sv->l.vals, s); }
     if (rc != 0 || !(save || keep)) {
         saved_free(sv, s);
         delete sv;
@@ -411,21 +507,30 @@ static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const f
     const size_t n_out = (size_t)g.F * g.N * P;
     if (n_out == 0) return 0;
     if (!peers && !d_params) return fail(1, "ps_backward: NULL d_params");
+    if (peers && (world < 1 || my_rank < 0 || my_rank >= world)) return fail(1, "ps_backward_peer: rank %d of %d", my_rank, world);
     const size_t VN = (size_t)g.V * g.N;
-    if (VN == 0 || sv->M == 0 || (size_t)g.H * g.W == 0) { // nothing was rendered: the gradient is zero
-        if (!peers) PS_CUDA(cudaMemsetAsync(d_params, 0, n_out * sizeof(float), s));
+    // nothing was rendered (known on the host): the gradient is zero.  In peer mode the zeros are still PUSHED: every
+    // staging slot is rewritten every step, so the owners never add a stale slot.
+    const bool nothing = VN == 0 || (sv->resolved && sv->M == 0) || (size_t)g.H * g.W == 0;
+    if (nothing && !peers) {
+        PS_CUDA(cudaMemsetAsync(d_params, 0, n_out * sizeof(float), s));
         return 0;
     }
-    if (!sv->blast || !sv->t_pen || !sv->frame_off) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
-    if (!d_rgb || !d_alpha || !params || !background) return fail(1, "ps_backward: NULL buffer");
-    if (peers && (world < 1 || my_rank < 0 || my_rank >= world)) return fail(1, "ps_backward_peer: rank %d of %d", my_rank, world);
+    if (!nothing && (!sv->blast || !sv->t_pen)) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
+    if (!sv->frame_off) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
+    if (!params || !background || (!nothing && (!d_rgb || !d_alpha))) return fail(1, "ps_backward: NULL buffer");
     float *acc = nullptr;
-    PS_CUDA(dev_alloc(&acc, VN * PS_ACC_STRIDE + 4, s)); // + the rasterizer's task counter, zeroed with the rows
+    const size_t acc_rows = VN > 0 ? VN : 1;
+    PS_CUDA(dev_alloc(&acc, acc_rows * PS_ACC_STRIDE + 4, s)); // + the rasterizer's task counter, zeroed with the rows
     int rc = 0;
     do {
-        if (cudaMemsetAsync(acc, 0, (VN * PS_ACC_STRIDE + 4) * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
-        int n;
-        { StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s); n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->n_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc, reinterpret_cast<unsigned *>(acc + VN * PS_ACC_STRIDE), s); }
+        if (cudaMemsetAsync(acc, 0, (acc_rows * PS_ACC_STRIDE + 4) * sizeof(float), s) != cudaSuccess) { rc = fail(2, "ps_backward: memset failed"); break; }
+        int n = 0;
+        if (!nothing) {
+            StageTimer tm(ctx, PS_STAGE_RASTER_BWD, s);
+            n = ps_launch_raster_bwd(g, sv->t, sv->l, sv->cap_work, background, sv->blast, sv->t_pen, d_rgb, d_alpha, acc,
+                                     reinterpret_cast<unsigned *>(acc + acc_rows * PS_ACC_STRIDE), sv->stats ? ctx->d_stats : nullptr, s);
+        }
         if (n < 0) { rc = fail(3, "ps_backward: raster_bwd launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         ctx->launches += n;
         { StageTimer tm(ctx, PS_STAGE_PROJECT_BWD, s); n = ps_launch_project_bwd(g, params, sv->frame_off, sv->frame_views, viewmats, Ks, sv->t, acc, d_params, peers, my_rank, world, s); }
@@ -449,8 +554,6 @@ int ps_backward_peer(ps_ctx *ctx, ps_saved *sv, const float *params, const float
                      int my_rank, int world, void *stream)
 {
     if (!stage_ranks) return fail(1, "ps_backward_peer: NULL stage_ranks");
-    if (sv && (sv->M == 0 || (size_t)sv->g.V * sv->g.N == 0))
-        return fail(1, "ps_backward_peer: nothing was rendered by this rank; push zeros with a regular backward instead");
     return backward_impl(ctx, sv, params, viewmats, Ks, background, d_rgb, d_alpha, nullptr, stage_ranks, my_rank, world, stream);
 }
 
@@ -465,6 +568,7 @@ int ps_peer_sum(ps_ctx *ctx, const float *stage_local, int world, size_t n_per_s
 int ps_saved_info_get(const ps_saved *sv, ps_saved_info *out)
 {
     if (!sv || !out) return fail(1, "ps_saved_info_get: NULL argument");
+    if (int rc = saved_resolve(const_cast<ps_saved *>(sv))) return rc;
     memset(out, 0, sizeof *out);
     out->n_isect = sv->M;
     out->tile_bits = sv->g.tile_bits; out->view_bits = sv->g.view_bits;
@@ -478,6 +582,7 @@ int ps_saved_info_get(const ps_saved *sv, ps_saved_info *out)
 int ps_saved_copy(ps_ctx *ctx, const ps_saved *sv, int what, void *dst, size_t bytes, void *stream)
 {
     if (!ctx || !sv || !dst) return fail(1, "ps_saved_copy: NULL argument");
+    if (int rc = saved_resolve(const_cast<ps_saved *>(sv))) return rc;
     const PsGeometry &g = sv->g;
     const size_t VN = (size_t)g.V * g.N, npix = (size_t)g.V * g.H * g.W;
     const void *src = nullptr;
@@ -532,16 +637,19 @@ int ps_ctx_stage_times(ps_ctx *ctx, double *ms, int64_t *calls, int reset)
 {
     if (!ctx) return fail(1, "ps_ctx_stage_times: NULL context");
     PS_CUDA(cudaSetDevice(ctx->device));
-    for (auto &sp : ctx->pending) {
+    std::vector<PsSpan> done;
+    { std::lock_guard<std::mutex> lock(ctx->mu); done.swap(ctx->pending); }
+    for (auto &sp : done) {
         PS_CUDA(cudaEventSynchronize(sp.b));
         float t = 0.0f;
         PS_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+        std::lock_guard<std::mutex> lock(ctx->mu);
         ctx->stage_ms[sp.stage] += t;
         ctx->stage_calls[sp.stage] += 1;
         ctx->spare.push_back(sp.a);
         ctx->spare.push_back(sp.b);
     }
-    ctx->pending.clear();
+    std::lock_guard<std::mutex> lock(ctx->mu);
     for (int i = 0; i < PS_N_STAGES; ++i) {
         if (ms) ms[i] = ctx->stage_ms[i];
         if (calls) calls[i] = ctx->stage_calls[i];
@@ -555,8 +663,8 @@ int ps_ctx_raster_stats(ps_ctx *ctx, uint64_t *pairs, int reset, void *stream)
     if (!ctx || !pairs) return fail(1, "ps_ctx_raster_stats: NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
     PS_CUDA(cudaSetDevice(ctx->device));
-    PS_CUDA(cudaMemcpyAsync(pairs, ctx->d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    if (reset) PS_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(uint64_t), s));
+    PS_CUDA(cudaMemcpyAsync(pairs, ctx->d_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (reset) PS_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(uint64_t), s));
     PS_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
@@ -633,6 +741,24 @@ int ps_view_loss(ps_ctx *ctx, int n_views, int height, int width, const float *r
     return 0;
 }
 
+int ps_iou_loss(ps_ctx *ctx, int n_views, int height, int width, const float *alpha, const float *target_mask, float *losses,
+                float *d_alpha, void *stream)
+{
+    if (!ctx) return fail(1, "ps_iou_loss: NULL context");
+    if (n_views < 0 || height < 0 || width < 0) return fail(1, "ps_iou_loss: negative size");
+    if (n_views == 0) return 0;
+    if (!alpha || !target_mask || !losses) return fail(1, "ps_iou_loss: NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    double *stats = nullptr;
+    PS_CUDA(dev_alloc(&stats, (size_t)n_views * 8, s));
+    const int n = ps_launch_iou_loss(n_views, height, width, alpha, target_mask, stats, losses, d_alpha, s);
+    dev_free(stats, s);
+    if (n < 0) return fail(3, "ps_iou_loss: kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches += n;
+    return 0;
+}
+
 static int head_check(ps_ctx *ctx, int mode, int n, const void *a, const void *b, const char *what)
 {
     if (!ctx) return fail(1, "%s: NULL context", what);
@@ -645,7 +771,7 @@ static int head_check(ps_ctx *ctx, int mode, int n, const void *a, const void *b
 int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, const float *grid_sel,
                           const float *scale0, float voxel_size, float prob_threshold, float clip_lo, float clip_hi,
                           int pose, double angle, const float *p_3d_host, const float *poses, const int32_t *row_frame,
-                          float *rows, void *stream)
+                          int n_frames, float *rows, void *stream)
 {
     if (int rc = head_check(ctx, mode, n, net_out, probs_sel, "ps_param_head_forward")) return rc;
     if (n > 0 && (!rows || !scale0 || (mode == PS_MODE_3D && !grid_sel))) return fail(1, "ps_param_head_forward: NULL buffer");
@@ -653,13 +779,13 @@ int ps_param_head_forward(ps_ctx *ctx, int mode, int n, const float *net_out, co
     if ((poses == nullptr) != (row_frame == nullptr)) return fail(1, "ps_param_head_forward: poses and row_frame go together");
     PS_CUDA(cudaSetDevice(ctx->device));
     PS_LAUNCH(ctx, ps_launch_head_fwd(mode, n, net_out, probs_sel, grid_sel, scale0, voxel_size, prob_threshold, clip_lo, clip_hi,
-                                      pose, angle, p_3d_host, poses, row_frame, rows, (cudaStream_t)stream));
+                                      pose, angle, p_3d_host, poses, row_frame, n_frames, rows, (cudaStream_t)stream));
     return 0;
 }
 
 int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, const float *probs_sel, float voxel_size,
                            float prob_threshold, float clip_lo, float clip_hi, int pose, double angle, const float *poses,
-                           const int32_t *row_frame, const float *d_rows, float *d_net_out, float *d_probs_sel, float *d_scale0,
+                           const int32_t *row_frame, int n_frames, const float *d_rows, float *d_net_out, float *d_probs_sel, float *d_scale0,
                            void *stream)
 {
     if (int rc = head_check(ctx, mode, n, net_out, probs_sel, "ps_param_head_backward")) return rc;
@@ -667,7 +793,7 @@ int ps_param_head_backward(ps_ctx *ctx, int mode, int n, const float *net_out, c
     PS_CUDA(cudaSetDevice(ctx->device));
     if ((poses == nullptr) != (row_frame == nullptr)) return fail(1, "ps_param_head_backward: poses and row_frame go together");
     PS_LAUNCH(ctx, ps_launch_head_bwd(mode, n, net_out, probs_sel, voxel_size, prob_threshold, clip_lo, clip_hi, pose, angle,
-                                      poses, row_frame, d_rows, d_net_out, d_probs_sel, d_scale0, (cudaStream_t)stream));
+                                      poses, row_frame, n_frames, d_rows, d_net_out, d_probs_sel, d_scale0, (cudaStream_t)stream));
     return 0;
 }
 

@@ -1,0 +1,73 @@
+// ps_cull.cuh -- conservative footprint tests shared by the binning (ps_bin.cu) and the rasterizers (ps_raster.cu).
+// None of them decides a result: they only drop (pixel block, splat) pairs whose exact per-pixel test
+// (3D: sigma <= log(255 * opacity) + slack, 2D: q <= L) is guaranteed to fail for every pixel of the block.
+#pragma once
+
+#include "ps_contract.cuh"
+
+#define PS_THR_SLACK 0.01f      // slack on sigma <= log(255*opacity): covers the rounding of exp / log / sigma
+#define PS_SLOT_MASK_SHIFT 24   // list slot word = depth rank (3D) / row index (2D) in the low 24 bits | 8-bit block mask
+
+// 2D: q = dxr^2 iax + dyr^2 iay with (dxr, dyr) = R (dx, dy) is the quadratic form hA dx^2 + B dx dy + hC dy^2
+__device__ __forceinline__ void ps_conic2d(const float4 &r1, float &hA, float &B, float &hC)
+{
+    const float cc = r1.x * r1.x, ss = r1.y * r1.y;
+    hA = cc * r1.z + ss * r1.w;
+    hC = ss * r1.z + cc * r1.w;
+    B = 2.0f * r1.x * r1.y * (r1.z - r1.w);
+}
+
+// Which of the eight 8x4 pixel blocks of tile (tx, ty) can the splat contribute to?  `half` = 0.5 (3D pixel centres) or
+// 0 (2D: integer pixel centres).  sigma(u) = hA ux^2 + hC uy^2 + B ux uy (u = pixel - mean) is convex with its minimum
+// at u = 0, so over a box that does not contain 0 the minimum lies on an edge facing the mean; along such an edge it is
+// a 1-D parabola.  The per-column / per-row terms are shared by the blocks: their pixel-centre boxes are bounded by
+// 4 vertical and 8 horizontal lines.  NaN / inf (degenerate conics) count as a hit.
+__device__ __forceinline__ uint32_t ps_block_mask8(float gx, float gy, float hA, float B, float hC, float thr, float half, int tx, int ty)
+{
+    const float lim = thr * 1.0001f + 2.0f * PS_THR_SLACK;
+    const float kx = __fdividef(-B, 2.0f * hC), ky = __fdividef(-B, 2.0f * hA);
+    const float X0 = ((float)(tx * PS_TILE) + half) - gx, Y0 = ((float)(ty * PS_TILE) + half) - gy;
+    float ux0[2], ux1[2], cx[2], tx_[2], ax[2], bx_[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        ux0[i] = X0 + 8.0f * i;
+        ux1[i] = X0 + (8.0f * i + 7.0f);
+        cx[i] = fminf(fmaxf(0.0f, ux0[i]), ux1[i]);
+        tx_[i] = kx * cx[i];          // unconstrained minimiser along the vertical line ux = cx
+        ax[i] = hA * cx[i] * cx[i];
+        bx_[i] = B * cx[i];
+    }
+    float uy0[4], uy1[4], cy[4], ty_[4], ay[4], by_[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uy0[j] = Y0 + 4.0f * j;
+        uy1[j] = Y0 + (4.0f * j + 3.0f);
+        cy[j] = fminf(fmaxf(0.0f, uy0[j]), uy1[j]);
+        ty_[j] = ky * cy[j];
+        ay[j] = hC * cy[j] * cy[j];
+        by_[j] = B * cy[j];
+    }
+    uint32_t m8 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = k & 1, j = k >> 1;
+        const float t1 = fminf(fmaxf(tx_[i], uy0[j]), uy1[j]);
+        const float s1 = ax[i] + (hC * t1 + bx_[i]) * t1;
+        const float t2 = fminf(fmaxf(ty_[j], ux0[i]), ux1[i]);
+        const float s2 = ay[j] + (hA * t2 + by_[j]) * t2;
+        const bool inx = cx[i] == 0.0f, iny = cy[j] == 0.0f;
+        const bool hit = (inx && iny) || (!inx && !(s1 > lim)) || (!iny && !(s2 > lim));
+        m8 |= hit ? (1u << k) : 0u;
+    }
+    return m8;
+}
+
+// blocks of tile (tx, ty) that have at least one pixel inside the W x H image
+__device__ __forceinline__ uint32_t ps_blocks_inside8(int tx, int ty, int W, int H)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (tx * PS_TILE + (k & 1) * 8 < W && ty * PS_TILE + (k >> 1) * 4 < H) m |= 1u << k;
+    return m;
+}

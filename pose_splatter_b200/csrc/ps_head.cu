@@ -17,13 +17,19 @@ struct HeadArgs {
     float c, s, px, py, pz; // yaw cos / sin rounded to fp32 like the reference's rot_mat, translation
     const float *poses;     // optional [F,5] (c, s, px, py, pz) per frame: rows of several frames in one launch
     const int32_t *row_frame; // [n] frame of every row (with poses)
+    int n_frames;             // rows of `poses`
 };
 
 __device__ __forceinline__ void row_pose(const HeadArgs &a, int i, float &c, float &s, float &px, float &py, float &pz)
 {
     c = a.c; s = a.s; px = a.px; py = a.py; pz = a.pz;
     if (a.poses) {
-        const float *p = a.poses + 5 * (size_t)a.row_frame[i];
+        const unsigned f = (unsigned)a.row_frame[i];
+        if (f >= (unsigned)a.n_frames) { // a frame id outside the pose table: never read out of bounds, poison the row
+            c = s = px = py = pz = __int_as_float(0x7fc00000);
+            return;
+        }
+        const float *p = a.poses + 5 * (size_t)f;
         c = p[0]; s = p[1]; px = p[2]; py = p[3]; pz = p[4];
     }
 }
@@ -313,9 +319,10 @@ head_bwd_kernel(HeadArgs a, const float *__restrict__ net_out, const float *__re
 }
 
 HeadArgs head_args(int mode, int n, float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p,
-                   const float *poses, const int32_t *row_frame)
+                   const float *poses, const int32_t *row_frame, int n_frames)
 {
     HeadArgs a;
+    a.n_frames = n_frames;
     a.mode = mode; a.n = n; a.pose = (mode == PS_MODE_3D && pose) ? 1 : 0;
     a.voxel2 = (float)(2.0 * (double)voxel_size);
     a.inv1mpt = (float)(1.0 / (1.0 - (double)pt));
@@ -331,21 +338,21 @@ HeadArgs head_args(int mode, int n, float voxel_size, float pt, float clip_lo, f
 
 int ps_launch_head_fwd(int mode, int n, const float *net_out, const float *probs, const float *grid, const float *scale0,
                        float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p_host,
-                       const float *poses, const int32_t *row_frame, float *rows, cudaStream_t s)
+                       const float *poses, const int32_t *row_frame, int n_frames, float *rows, cudaStream_t s)
 {
     if (n <= 0) return 0;
-    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, p_host, poses, row_frame);
+    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, p_host, poses, row_frame, n_frames);
     head_fwd_kernel<<<(n + HEAD_THREADS - 1) / HEAD_THREADS, HEAD_THREADS, 0, s>>>(a, net_out, probs, grid, scale0, rows);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int ps_launch_head_bwd(int mode, int n, const float *net_out, const float *probs, float voxel_size, float pt, float clip_lo,
-                       float clip_hi, int pose, double angle, const float *poses, const int32_t *row_frame,
+                       float clip_hi, int pose, double angle, const float *poses, const int32_t *row_frame, int n_frames,
                        const float *d_rows, float *d_net, float *d_probs, float *d_scale0, cudaStream_t s)
 {
     if (cudaMemsetAsync(d_scale0, 0, sizeof(float), s) != cudaSuccess) return -1;
     if (n <= 0) return 0;
-    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, nullptr, poses, row_frame);
+    const HeadArgs a = head_args(mode, n, voxel_size, pt, clip_lo, clip_hi, pose, angle, nullptr, poses, row_frame, n_frames);
     head_bwd_kernel<<<(n + HEAD_THREADS - 1) / HEAD_THREADS, HEAD_THREADS, 0, s>>>(a, net_out, probs, d_rows, d_net, d_probs, d_scale0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -42,8 +42,11 @@ struct PsLists {
     uint32_t *slots;    // [M] depth ranks (3D) / row indices (2D) in list order, unsorted inside a list
     uint32_t *vals;     // [M] view*N + Gaussian, sorted (tile, depth | row)
     uint32_t *blist;    // [8*M] per-block lists: tile with range [s, s+len) owns [8s, 8s+8len), block k at +k*len;
-                        //       entries = positions relative to s, ascending
+                        //       entries = view*N + Gaussian, in tile-list order
+    uint32_t *bpos;     // [8*M] or NULL: position (relative to s) in the tile list of every block-list entry (last-id tap)
     int32_t *bcount;    // [8*n_work] length of every block list, indexed by work-list item
+    const int32_t *n_lists; // device: number of non-empty lists (= cls[3 * PS_N_CLASSES]); kernels launched over an upper
+                            // bound of it exit beyond this count
 };
 
 // every launcher returns the number of kernels it launched (for gpu_launches) or -1 on error
@@ -68,6 +71,9 @@ int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, long long *chunk
 int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s);
 int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t s);
 int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
+// sort + split into the eight block lists in one kernel (no record gathers); needs ps_split_fits_smem(g)
+bool ps_split_fits_smem(const PsGeometry &g);
+int ps_launch_sort_split(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
 int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint64_t *keys, cudaStream_t s);
 
 // rasterizers (ps_raster.cu)
@@ -81,19 +87,23 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
                          uint32_t *rgba8, unsigned long long *stats, cudaStream_t s);
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
-                         unsigned *next_task /* zeroed by the caller: the persistent warps' task counter */, cudaStream_t s);
+                         unsigned *next_task /* zeroed by the caller: the persistent warps' task counter */,
+                         unsigned long long *stats /* NULL, or this kernel's pair counters [4..7] */, cudaStream_t s);
 
 // per-view training loss + its gradient (ps_loss.cu); stats [V*8] doubles and adj [V*9*H*W] floats are scratch
 int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alpha, const float *timg, const float *mask,
                         float ssim_lambda, float img_lambda, double *stats, float *adj, float *losses, float *d_rgb,
                         float *d_alpha, cudaStream_t s);
 
+int ps_launch_iou_loss(int V, int H, int W, const float *alpha, const float *mask, double *stats, float *losses, float *d_alpha,
+                       cudaStream_t s);
+
 // parameter-head tail (ps_head.cu): activations + pose transform of the rows render() takes, forward and backward
 int ps_launch_head_fwd(int mode, int n, const float *net_out, const float *probs, const float *grid, const float *scale0,
                        float voxel_size, float pt, float clip_lo, float clip_hi, int pose, double angle, const float *p_host,
-                       const float *poses, const int32_t *row_frame, float *rows, cudaStream_t s);
+                       const float *poses, const int32_t *row_frame, int n_frames, float *rows, cudaStream_t s);
 int ps_launch_head_bwd(int mode, int n, const float *net_out, const float *probs, float voxel_size, float pt, float clip_lo,
-                       float clip_hi, int pose, double angle, const float *poses, const int32_t *row_frame,
+                       float clip_hi, int pose, double angle, const float *poses, const int32_t *row_frame, int n_frames,
                        const float *d_rows, float *d_net, float *d_probs, float *d_scale0, cudaStream_t s);
 
 int ps_launch_math_probe(const float *x, int n, float *y, cudaStream_t s);

@@ -56,7 +56,7 @@ loss_reduce_kernel(LossDims d, const float *__restrict__ rgb, const float *__res
         sI += av * mv;
         sU += av + mv - av * mv;
         sM += mv;
-        sL += fabsf(t[i] - q[3 * i]) + fabsf(t[npix + i] - q[3 * i + 1]) + fabsf(t[2 * npix + i] - q[3 * i + 2]);
+        if (rgb) sL += fabsf(t[i] - q[3 * i]) + fabsf(t[npix + i] - q[3 * i + 1]) + fabsf(t[2 * npix + i] - q[3 * i + 2]);
     }
     double r;
     r = block_sum((double)sI, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 0, r);
@@ -187,7 +187,7 @@ loss_bwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
     const size_t npix = (size_t)d.H * d.W;
     const int tid = threadIdx.x;
     const double I = stats[v * NSTAT + 0] + 1e-6, U = stats[v * NSTAT + 1] + 1e-6, msum = stats[v * NSTAT + 2];
-    const float l1 = (float)((double)img_lambda / msum);
+    const float l1 = img_lambda == 0.0f ? 0.0f : (float)((double)img_lambda / msum); // lambda 0: no 0 * 0 / 0 for an empty mask
     const float iou_m = (float)(-1.0 / U), iou_c = (float)(I / (U * U)); // d(1 - I/U)/da = -m/U + I (1 - m) / U^2
     const int c = tid & 31, r0 = (tid >> 5) * 4;
     float g[4][3];
@@ -259,8 +259,26 @@ __global__ void loss_finalize_kernel(LossDims d, const double *__restrict__ stat
     const double *s = stats + v * NSTAT;
     const double count = 3.0 * (double)(d.H - 2 * HALO) * (double)(d.W - 2 * HALO);
     losses[3 * v + 0] = (float)(1.0 - (s[0] + 1e-6) / (s[1] + 1e-6));
-    losses[3 * v + 1] = (float)((double)ssim_lambda * (1.0 - s[4] / count));
-    losses[3 * v + 2] = (float)((double)img_lambda * s[3] / s[2]);
+    // a term whose weight is zero is exactly zero (an empty target mask would otherwise give 0 * 0 / 0 = NaN)
+    losses[3 * v + 1] = ssim_lambda == 0.0f ? 0.0f : (float)((double)ssim_lambda * (1.0 - s[4] / count));
+    losses[3 * v + 2] = img_lambda == 0.0f ? 0.0f : (float)((double)img_lambda * s[3] / s[2]);
+}
+
+// soft IoU alone (scripts/training/train_script.py:30-36): losses [V], d_alpha [V,H,W] from the sums of loss_reduce
+__global__ void __launch_bounds__(LTHREADS)
+iou_bwd_kernel(LossDims d, const float *__restrict__ mask, const double *__restrict__ stats, float *__restrict__ losses,
+               float *__restrict__ d_alpha)
+{
+    const int v = blockIdx.y;
+    const size_t npix = (size_t)d.H * d.W;
+    const double I = stats[v * NSTAT + 0] + 1e-6, U = stats[v * NSTAT + 1] + 1e-6;
+    if (blockIdx.x == 0 && threadIdx.x == 0) losses[v] = (float)(1.0 - I / U);
+    if (!d_alpha) return;
+    const float iou_m = (float)(-1.0 / U), iou_c = (float)(I / (U * U));
+    for (size_t i = (size_t)blockIdx.x * LTHREADS + threadIdx.x; i < npix; i += (size_t)gridDim.x * LTHREADS) {
+        const float m = mask[v * npix + i];
+        d_alpha[v * npix + i] = iou_m * m + iou_c * (1.f - m);
+    }
 }
 
 } // namespace
@@ -303,4 +321,18 @@ int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alph
     }
     loss_finalize_kernel<<<(V + 127) / 128, 128, 0, s>>>(d, stats, ssim_lambda, img_lambda, losses);
     return cudaGetLastError() == cudaSuccess ? n : -1;
+}
+
+// stats: [V * 8] doubles of scratch.  Any image size (no SSIM window).
+int ps_launch_iou_loss(int V, int H, int W, const float *alpha, const float *mask, double *stats, float *losses, float *d_alpha,
+                       cudaStream_t s)
+{
+    const LossDims d = { V, H, W };
+    if (cudaMemsetAsync(stats, 0, (size_t)V * NSTAT * sizeof(double), s) != cudaSuccess) return -1;
+    const size_t npix = (size_t)H * W;
+    int bx = (int)((npix + LTHREADS * 8 - 1) / (LTHREADS * 8));
+    bx = bx < 1 ? 1 : (bx > 64 ? 64 : bx);
+    loss_reduce_kernel<<<dim3(bx, V), LTHREADS, 0, s>>>(d, nullptr, alpha, nullptr, mask, stats);
+    iou_bwd_kernel<<<dim3(bx, V), LTHREADS, 0, s>>>(d, mask, stats, losses, d_alpha);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -40,7 +40,9 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
     const int g0 = blockIdx.x * PS_PROJ_BLOCK;
     const int n_rows = min(PS_PROJ_BLOCK, g.N - g0);
     const int frame = view_frame[v];
-    stage_rows<P>(params + ((size_t)frame * g.N + g0) * P, n_rows, s_rows);
+    // a frame id outside [0, F) never reads out of bounds: the view renders nothing (the backward's CSR drops it too)
+    const bool bad_frame = (unsigned)frame >= (unsigned)g.F;
+    if (!bad_frame) stage_rows<P>(params + ((size_t)frame * g.N + g0) * P, n_rows, s_rows);
     if (use_smem)
         for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) s_cnt[i] = 0;
     if (MODE == PS_MODE_3D && threadIdx.x < 25) {
@@ -50,7 +52,9 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
     int32_t *cnt_v = tile_counts + (size_t)v * g.n_tiles;
     if ((int)threadIdx.x < n_rows) {
         PsRecord rec;
-        if (MODE == PS_MODE_3D) {
+        if (bad_frame) {
+            ps_record_clear(&rec);
+        } else if (MODE == PS_MODE_3D) {
             PsProj3dAux aux;
             ps_project3d(s_rows + threadIdx.x * P, s_cam, s_cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip,
                          g.eps2d, &rec, &aux, g.activated);

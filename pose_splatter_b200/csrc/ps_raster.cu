@@ -4,12 +4,13 @@
 //   8x4 pixel blocks: an entry goes to a block only if the splat can contribute there (3D: exact
 //   ellipse-vs-box test, min of sigma over the block's pixel centres against log(255*opacity); 2D: the
 //   splat's pixel rectangle meets the block).  One CTA per tile, one list entry per thread, ordered
-//   multi-split with ballots.  The block lists hold positions in the tile list (4 B each).
+//   multi-split with ballots.  The block lists hold view * N + Gaussian (4 B each).  [fallback for N too large for the
+//   bitmap split of ps_bin.cu, which builds the same lists without reading a record]
 // forward / backward: the unit of work is one WARP = one pixel block; a CTA is two such warps that share
 //   nothing (no __syncthreads), so a block that finishes early frees its slot: this workload is dominated by
 //   a few very long lists in which, at any depth, only some blocks still have live pixels.
 //   Tasks are launched in the size order of the work list.  A warp streams its block list 32 entries at a
-//   time (one per lane): position -> Gaussian id -> cp.async of the 48-byte splat record into a warp-private
+//   time (one per lane): Gaussian id -> cp.async of the 48-byte splat record into a warp-private
 //   3-stage ring in shared memory, two chunks ahead of use; the lane re-culls its entry against the bounding
 //   box of the pixels that are still live (forward: not terminated; backward: still have contributors at or
 //   before this chunk); survivors (ballot) are walked in list order with broadcast reads of the ring.
@@ -23,13 +24,14 @@
 // Replaces gsplat rasterize_to_pixels_3dgs_fwd/bwd (absent from the reference tree) and the
 // torch element-wise loop src/gaussian_renderer.py:379-425 plus its autograd.
 #include "ps_contract.cuh"
+#include "ps_cull.cuh"
 #include "ps_internal.h"
 #include <cstdlib>
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr float THR_SLACK = 0.01f;  // slack on sigma <= log(255*opacity): covers the rounding of exp / log / sigma
+constexpr float THR_SLACK = PS_THR_SLACK;
 constexpr int CH = 32;              // list entries per chunk (one per lane)
 constexpr int NS = 3;               // ring stages per warp
 constexpr int WPC = 2;              // warps (pixel blocks) per CTA
@@ -39,7 +41,8 @@ constexpr int TASKS_PER_TILE = 8 / WPC;
 struct BlockCtx {
     int view, start, len;   // tile list [start, start + len)
     int nb;                 // entries of this block's list
-    const uint32_t *bl;     // this block's list: positions relative to `start`, ascending
+    const uint32_t *bl;     // this block's list: view * N + Gaussian of its entries, in tile-list order
+    const uint32_t *bp;     // tile-list positions (relative to `start`) of the entries, or NULL (last-id tap only)
     int px, py;             // this lane's pixel
     int bx, by;             // block origin
     bool inside;
@@ -47,7 +50,7 @@ struct BlockCtx {
 
 // task = 8 * work-list item + block (0..7: x half = blk & 1, y quarter = blk >> 1)
 __device__ __forceinline__ BlockCtx block_ctx_task(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist,
-                                                   const uint32_t *blist, const int32_t *bcount, unsigned task)
+                                                   const uint32_t *blist, const uint32_t *bpos, const int32_t *bcount, unsigned task)
 {
     BlockCtx c;
     const int item = (int)(task >> 3);
@@ -60,6 +63,7 @@ __device__ __forceinline__ BlockCtx block_ctx_task(const PsGeometry &g, const in
     c.len = offsets[lin + 1] - c.start;
     c.nb = bcount[item * 8 + blk];
     c.bl = blist + 8 * (size_t)c.start + (size_t)blk * c.len;
+    c.bp = bpos ? bpos + 8 * (size_t)c.start + (size_t)blk * c.len : nullptr;
     const int lane = threadIdx.x & 31;
     c.bx = tx * PS_TILE + (blk & 1) * 8;
     c.by = ty * PS_TILE + (blk >> 1) * 4;
@@ -70,9 +74,9 @@ __device__ __forceinline__ BlockCtx block_ctx_task(const PsGeometry &g, const in
 }
 template <int W> // W = warps (pixel blocks) per CTA; CTA b handles blocks (b % (8 / W)) * W ... of item b / (8 / W)
 __device__ __forceinline__ BlockCtx block_ctx(const PsGeometry &g, const int32_t *offsets, const int32_t *worklist,
-                                              const uint32_t *blist, const int32_t *bcount)
+                                              const uint32_t *blist, const uint32_t *bpos, const int32_t *bcount)
 {
-    return block_ctx_task(g, offsets, worklist, blist, bcount, blockIdx.x * W + (threadIdx.x >> 5));
+    return block_ctx_task(g, offsets, worklist, blist, bpos, bcount, blockIdx.x * W + (threadIdx.x >> 5));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,15 +112,6 @@ __device__ __forceinline__ bool ellipse_hits_box(float gx, float gy, float hA, f
     return !(best > thr * 1.0001f + 2.0f * THR_SLACK);
 }
 
-// 2D: q = dxr^2 iax + dyr^2 iay with (dxr, dyr) = R (dx, dy) is the quadratic form hA dx^2 + B dx dy + hC dy^2
-__device__ __forceinline__ void conic2d(const float4 &r1, float &hA, float &B, float &hC)
-{
-    const float cc = r1.x * r1.x, ss = r1.y * r1.y;
-    hA = cc * r1.z + ss * r1.w;
-    hC = ss * r1.z + cc * r1.w;
-    B = 2.0f * r1.x * r1.y * (r1.z - r1.w);
-}
-
 // bounding box (in block-local pixel coordinates) of the lanes set in `active` (lane = y * 8 + x); active != 0
 __device__ __forceinline__ void active_box(uint32_t active, int &x0, int &x1, int &y0, int &y1)
 {
@@ -141,7 +136,6 @@ __device__ __forceinline__ uint32_t quantise_rgba8(float r, float g, float b, fl
 // The warp-private ring: stage st holds chunk data for 32 entries.
 struct Ring {
     float4 (*a)[CH], (*b)[CH], (*c)[CH];
-    uint32_t (*pos)[CH]; // position of the entry in the tile list (relative)
 };
 
 // lane-parallel cull of the staged chunk against the live-pixel box -> ballot of surviving entries
@@ -155,7 +149,7 @@ __device__ __forceinline__ uint32_t cull_chunk(const Ring &q, int st, int lane, 
         const float4 a0 = q.a[st][lane], a1 = q.b[st][lane];
         const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f; // pixel centres: +0.5 in 3D, integers in 2D
         float hA = a1.x, B = a1.y, hC = a1.z;
-        if (MODE == PS_MODE_2D) conic2d(a1, hA, B, hC);
+        if (MODE == PS_MODE_2D) ps_conic2d(a1, hA, B, hC);
         hit = ellipse_hits_box(a0.x, a0.y, hA, B, hC, a0.z, (float)(c.bx + ax0) + half, (float)(c.bx + ax1) + half,
                                (float)(c.by + ay0) + half, (float)(c.by + ay1) + half);
     }
@@ -168,25 +162,24 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                   const int32_t *__restrict__ worklist, const float *__restrict__ background,
                   float *__restrict__ rgb, float *__restrict__ alpha,
                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
-                  float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount,
-                  uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats)
+                  float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const uint32_t *__restrict__ bpos,
+                  const int32_t *__restrict__ bcount, uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats,
+                  const int32_t *__restrict__ n_lists)
 {
     __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
-    __shared__ uint32_t s_pos[W][NS][CH];
-    const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bcount);
+    // the grid may be sized from an upper bound of the number of non-empty lists (sync-free small calls)
+    if ((int)((blockIdx.x * W + (threadIdx.x >> 5)) >> 3) >= __ldg(n_lists)) return;
+    const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bpos, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool done = !c.inside;
     if (__all_sync(FULL, done)) return; // block entirely outside the image
-    const Ring q = { s_a[wid], s_b[wid], s_c[wid], s_pos[wid] };
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
     const int len = c.nb;
     const int nchunks = (len + CH - 1) / CH;
-    const uint32_t *list = vals + c.start;
-    // chunk cj: list position (ld) -> Gaussian id (dependent ld) -> record copies (cp.async); the three steps of
-    // consecutive chunks are software-pipelined: positions run 4 chunks ahead, ids 3, records 2
-    auto issue = [&](int cj, uint32_t pos, uint32_t id) { // one commit group per chunk, also when it does not exist
+    // chunk cj: Gaussian id (ld) -> record copies (cp.async); software-pipelined: ids run 4 chunks ahead, records 2
+    auto issue = [&](int cj, uint32_t id) { // one commit group per chunk, also when it does not exist
         if (cj * CH + lane < len) {
             const int st = cj % NS;
-            q.pos[st][lane] = pos;
             const float4 *src = PS_REC(t, id, 0);
             cp_async16(&q.a[st][lane], src);
             cp_async16(&q.b[st][lane], src + 1);
@@ -194,16 +187,14 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         }
         cp_async_commit();
     };
-    auto fetch_pos = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
-    uint32_t posn, posnn, idn;
+    auto fetch_id = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
+    uint32_t idn, idnn;
     {
-        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
-        posn = fetch_pos(2);
-        posnn = fetch_pos(3);
-        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
-        issue(0, p0, i0);
-        issue(1, p1, i1);
-        idn = __ldg(list + posn);
+        const uint32_t i0 = fetch_id(0), i1 = fetch_id(1);
+        idn = fetch_id(2);
+        idnn = fetch_id(3);
+        issue(0, i0);
+        issue(1, i1);
     }
 
     unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
@@ -213,10 +204,9 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     int cnt = 0;
     int blastpos = 0; // 1 + index (in the block list) of the last contributor
     for (int ci = 0; ci < nchunks; ++ci) {
-        issue(ci + 2, posn, idn);
-        posn = posnn;
-        idn = __ldg(list + posn);
-        posnn = fetch_pos(ci + 4);
+        issue(ci + 2, idn);
+        idn = idnn;
+        idnn = fetch_id(ci + 4);
         cp_async_wait_group<2>(); // chunk ci has landed (this lane's copies); the barrier makes all lanes' visible
         __syncwarp();
         const int st = ci % NS;
@@ -302,7 +292,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         if (alpha) alpha[p] = oa;
         if (rgba8) rgba8[p] = quantise_rgba8(o0, o1, o2, oa);
         if (n_contrib) n_contrib[p] = cnt;
-        if (last) last[p] = c.start + (blastpos ? (int)__ldg(c.bl + blastpos - 1) + 1 : 0); // tile-list position
+        if (last) last[p] = c.start + ((blastpos && c.bp) ? (int)__ldg(c.bp + blastpos - 1) + 1 : 0); // tile-list position
         if (blast) blast[p] = blastpos;
         if (t_pen) t_pen[p] = Tpen;
     }
@@ -376,23 +366,24 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                    const int32_t *__restrict__ worklist, const float *__restrict__ background,
                    float *__restrict__ rgb, float *__restrict__ alpha,
                    int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
-                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount,
-                   uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats)
+                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const uint32_t *__restrict__ bpos,
+                   const int32_t *__restrict__ bcount, uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats,
+                  const int32_t *__restrict__ n_lists)
 {
     __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
-    __shared__ uint32_t s_pos[W][NS][CH];
-    const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bcount);
+    // the grid may be sized from an upper bound of the number of non-empty lists (sync-free small calls)
+    if ((int)((blockIdx.x * W + (threadIdx.x >> 5)) >> 3) >= __ldg(n_lists)) return;
+    const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bpos, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool done = !c.inside;
     if (__all_sync(FULL, done)) return;
-    const Ring q = { s_a[wid], s_b[wid], s_c[wid], s_pos[wid] };
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
     const int len = c.nb;
     const int nchunks = (len + CH - 1) / CH;
-    const uint32_t *list = vals + c.start;
-    auto issue = [&](int cj, uint32_t pos, uint32_t id) {
+    // chunk cj: Gaussian id (ld) -> record copies (cp.async); software-pipelined: ids run 4 chunks ahead, records 2
+    auto issue = [&](int cj, uint32_t id) { // one commit group per chunk, also when it does not exist
         if (cj * CH + lane < len) {
             const int st = cj % NS;
-            q.pos[st][lane] = pos;
             const float4 *src = PS_REC(t, id, 0);
             cp_async16(&q.a[st][lane], src);
             cp_async16(&q.b[st][lane], src + 1);
@@ -400,16 +391,14 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         }
         cp_async_commit();
     };
-    auto fetch_pos = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
-    uint32_t posn, posnn, idn;
+    auto fetch_id = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
+    uint32_t idn, idnn;
     {
-        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
-        posn = fetch_pos(2);
-        posnn = fetch_pos(3);
-        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
-        issue(0, p0, i0);
-        issue(1, p1, i1);
-        idn = __ldg(list + posn);
+        const uint32_t i0 = fetch_id(0), i1 = fetch_id(1);
+        idn = fetch_id(2);
+        idnn = fetch_id(3);
+        issue(0, i0);
+        issue(1, i1);
     }
     unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
@@ -419,10 +408,9 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     int cnt = 0;
     int blastpos = 0;
     for (int ci = 0; ci < nchunks; ++ci) {
-        issue(ci + 2, posn, idn);
-        posn = posnn;
-        idn = __ldg(list + posn);
-        posnn = fetch_pos(ci + 4);
+        issue(ci + 2, idn);
+        idn = idnn;
+        idnn = fetch_id(ci + 4);
         cp_async_wait_group<2>();
         __syncwarp();
         const int st = ci % NS;
@@ -434,7 +422,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         if (ci * CH + lane < len) {
             const float4 a0 = q0[lane], a1 = q1[lane];
             float hA = a1.x, B = a1.y, hC = a1.z;
-            if (MODE == PS_MODE_2D) conic2d(a1, hA, B, hC);
+            if (MODE == PS_MODE_2D) ps_conic2d(a1, hA, B, hC);
             em = span_mask(a0.x, a0.y, hA, B, hC, a0.z * 1.0001f + 2.0f * THR_SLACK, bxf, byf) & live;
         }
         // lane = pixel: my candidate entries of this chunk, ascending = list order
@@ -521,7 +509,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         if (alpha) alpha[p] = oa;
         if (rgba8) rgba8[p] = quantise_rgba8(o0, o1, o2, oa);
         if (n_contrib) n_contrib[p] = cnt;
-        if (last) last[p] = c.start + (blastpos ? (int)__ldg(c.bl + blastpos - 1) + 1 : 0);
+        if (last) last[p] = c.start + ((blastpos && c.bp) ? (int)__ldg(c.bp + blastpos - 1) + 1 : 0);
         if (blast) blast[p] = blastpos;
         if (t_pen) t_pen[p] = Tpen;
     }
@@ -539,182 +527,6 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             atomicAdd(stats + 3, st_staged * CH);
         }
     }
-}
-
-// Sum 9 per-lane values over the warp.  v[0..7] go through a halving butterfly (4+2+1+1+1 shuffles
-// instead of 8 x 5); afterwards lane L holds the total of value (L >> 2) in v[0].
-// v8 is reduced with the plain 5-step butterfly (every lane gets the total).
-__device__ __forceinline__ void warp_reduce9(float (&v)[8], float &v8, int lane)
-{
-    {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? v[i] : v[i + 4];
-            const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
-        }
-    }
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = hi ? v[i] : v[i + 2];
-            const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
-        }
-    }
-    {
-        const bool hi = lane & 4;
-        const float send = hi ? v[0] : v[1];
-        const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(FULL, send, 4);
-    }
-    v[0] += __shfl_xor_sync(FULL, v[0], 2);
-    v[0] += __shfl_xor_sync(FULL, v[0], 1);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v8 += __shfl_xor_sync(FULL, v8, d);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(RT_THREADS, 20)
-raster_bwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
-                  const int32_t *__restrict__ worklist, const float *__restrict__ background, const int32_t *__restrict__ last,
-                  const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
-                  const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount, float *__restrict__ acc)
-{
-    __shared__ float4 s_a[WPC][NS][CH], s_b[WPC][NS][CH], s_c[WPC][NS][CH];
-    __shared__ uint32_t s_id[WPC][NS][CH];
-    const BlockCtx c = block_ctx<WPC>(g, offsets, worklist, blist, bcount);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int my_last = 0; // 1 + index in the block list of this pixel's last contributor (saved by the forward)
-    float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
-    if (c.inside) {
-        const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
-        my_last = last[p];
-        if (my_last > 0) {
-            Tcur = t_pen[p];
-            w0 = d_rgb[3 * p]; w1 = d_rgb[3 * p + 1]; w2 = d_rgb[3 * p + 2];
-            S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
-        }
-    }
-    int wmax = my_last;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
-    if (wmax <= 0) return; // no pixel of this block has a contributor
-    const Ring q = { s_a[wid], s_b[wid], s_c[wid], nullptr };
-    uint32_t (*qid)[CH] = s_id[wid];
-    const int len = wmax;
-    const int nchunks = (len + CH - 1) / CH;
-    const uint32_t *list = vals + c.start;
-    // reverse step r handles chunk nchunks - 1 - r; its ring stage is r % NS
-    auto issue = [&](int r, uint32_t id) {
-        const int cj = nchunks - 1 - r;
-        if (cj >= 0 && cj * CH + lane < len) {
-            const int st = r % NS;
-            qid[st][lane] = id;
-            const float4 *src = PS_REC(t, id, 0);
-            cp_async16(&q.a[st][lane], src);
-            cp_async16(&q.b[st][lane], src + 1);
-            cp_async16(&q.c[st][lane], src + 2);
-        }
-        cp_async_commit();
-    };
-    auto fetch_pos = [&](int r) -> uint32_t {
-        const int cj = nchunks - 1 - r;
-        return (cj >= 0 && cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u;
-    };
-    uint32_t posn, posnn, idn;
-    {
-        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
-        posn = fetch_pos(2);
-        posnn = fetch_pos(3);
-        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
-        issue(0, i0);
-        issue(1, i1);
-        idn = __ldg(list + posn);
-    }
-    const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
-    const float pyf = (MODE == PS_MODE_3D) ? (float)c.py + 0.5f : (float)c.py;
-    for (int r = 0; r < nchunks; ++r) {
-        issue(r + 2, idn);
-        posn = posnn;
-        idn = __ldg(list + posn);
-        posnn = fetch_pos(r + 4);
-        cp_async_wait_group<2>();
-        __syncwarp();
-        const int st = r % NS;
-        const int ci = nchunks - 1 - r;
-        const int first = ci * CH;
-        // lanes whose last contributor lies at or after this chunk's first entry (never empty: first < wmax)
-        const uint32_t live = __ballot_sync(FULL, my_last > first);
-        uint32_t mask = cull_chunk<MODE>(q, st, lane, ci * CH + lane < len, c, live);
-        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
-        while (mask) {
-            const int e = 31 - __clz(mask);
-            mask &= ~(1u << e);
-            const int pos = first + e;
-            const bool active = pos < my_last;
-            const float4 r0 = q0[e], r1 = q1[e];
-            // gradient terms are computed by every lane and gated with selects (no divergent branches);
-            // lanes that do not contribute carry zeros into the warp reduction
-            float v[8], v8;
-            if (MODE == PS_MODE_3D) {
-                float dx, dy;
-                const float4 r2 = q2[e];
-                const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
-                const bool cand = active && sg >= 0.0f && sg <= r0.z + THR_SLACK;
-                if (!__any_sync(FULL, cand)) continue;
-                const float ex = psm_exp2_inrange(psm_mul(-sg, 0x1.715476p+0f));
-                const float oe = psm_mul(r0.w, ex);
-                const float a = fminf(PS_ALPHA_MAX, oe);
-                const bool contrib = cand && a >= PS_ALPHA_MIN;
-                if (!__any_sync(FULL, contrib)) continue;
-                const float Tb = (pos == my_last - 1) ? Tcur : __fdividef(Tcur, 1.0f - a);
-                const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-                const float v_alpha = Tb * (cw - S);
-                const float vis = contrib ? a * Tb : 0.0f;
-                const float v_sigma = (contrib && oe <= PS_ALPHA_MAX) ? -oe * v_alpha : 0.0f;
-                Tcur = contrib ? Tb : Tcur;
-                S = contrib ? S + a * (cw - S) : S;
-                v[0] = vis * w0; v[1] = vis * w1; v[2] = vis * w2;
-                const float sx = v_sigma * dx, sy = v_sigma * dy;
-                v[3] = 0.5f * sx * dx;
-                v[4] = sx * dy;
-                v[5] = 0.5f * sy * dy;
-                v[6] = 2.0f * r1.x * sx + r1.y * sy;
-                v[7] = r1.y * sx + 2.0f * r1.z * sy;
-                v8 = (contrib && oe <= PS_ALPHA_MAX) ? ex * v_alpha : 0.0f;
-            } else {
-                float dxr, dyr;
-                const float4 r2 = q2[e];
-                const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
-                const bool contrib = active && qv <= r0.z;
-                if (!__any_sync(FULL, contrib)) continue;
-                const float gv = psm_mul(r0.w, psm_exp2_inrange(psm_mul(-qv, 0x1.715476p+0f)));
-                const float Tb = (pos == my_last - 1) ? Tcur : __fdividef(Tcur, 1.0f - gv);
-                const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-                const float dLdg = Tb * (cw - S);
-                const float cn = contrib ? gv * Tb : 0.0f;
-                const float Gq = contrib ? -gv * dLdg : 0.0f;
-                Tcur = contrib ? Tb : Tcur;
-                S = contrib ? S + gv * (cw - S) : S;
-                v[0] = cn * w0; v[1] = cn * w1; v[2] = cn * w2;
-                const float ddxr = 2.0f * dxr * r1.z * Gq, ddyr = 2.0f * dyr * r1.w * Gq;
-                v[3] = ddxr; v[4] = ddyr;
-                v[5] = ddxr * dyr - ddyr * dxr;
-                v[6] = dxr * dxr * Gq;
-                v[7] = dyr * dyr * Gq;
-                v8 = Gq;
-            }
-            warp_reduce9(v, v8, lane);
-            float *row = acc + (size_t)qid[st][e] * PS_ACC_STRIDE;
-            if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), v[0]);
-            if (lane == 1) atomicAdd(row + 8, v8);
-        }
-        __syncwarp(); // every lane is finished with stage st before step r + 3 is copied into it
-    }
-    cp_async_wait_group<0>();
 }
 
 // ---- backward v5: two phases per group of SL contributing entries --------------------------------------------------
@@ -745,13 +557,13 @@ __device__ __forceinline__ float rcp_approx(float x)
     return y;
 }
 
-template <int MODE, int BW> // BW = warps (independent pixel blocks) per CTA
+template <int MODE, int BW, bool STATS> // BW = warps (independent pixel blocks) per CTA
 __global__ void __launch_bounds__(BW * 32, 20 / BW)
 raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                    const int32_t *__restrict__ worklist, const float *__restrict__ background, const int32_t *__restrict__ last,
                    const float *__restrict__ t_pen, const float *__restrict__ d_rgb, const float *__restrict__ d_alpha,
                    const uint32_t *__restrict__ blist, const int32_t *__restrict__ bcount, float *__restrict__ acc,
-                   unsigned n_tasks, unsigned *__restrict__ next_task)
+                   const int32_t *__restrict__ n_lists, unsigned *__restrict__ next_task, unsigned long long *__restrict__ stats)
 {
     __shared__ float4 s_a[BW][NS][CH], s_b[BW][NS][CH], s_c[BW][NS][CH];
     __shared__ uint32_t s_id[BW][NS][CH];
@@ -760,6 +572,8 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     __shared__ float4 s_sr0[BW][SL], s_sr1[BW][SL]; // rec0 / rec1 of every slot's entry
     __shared__ uint32_t s_sid[BW][SL];              // accumulator row (view * N + Gaussian) of every slot
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long st_eval = 0, st_contrib = 0, st_walk = 0, st_staged = 0; // STATS: this kernel's own pair counters
+    const unsigned n_tasks = 8u * (unsigned)__ldg(n_lists);
     // persistent warps: every warp pulls (tile, block) tasks off one counter, in work-list order (longest size class
     // first), so a warp slot is never idle while work remains (no CTA pairing, no launch gaps)
     for (;;) {
@@ -767,7 +581,7 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     if (lane == 0) task = atomicAdd(next_task, 1u);
     task = __shfl_sync(FULL, task, 0);
     if (task >= n_tasks) break;
-    const BlockCtx c = block_ctx_task(g, offsets, worklist, blist, bcount, task);
+    const BlockCtx c = block_ctx_task(g, offsets, worklist, blist, nullptr, bcount, task);
     int my_last = 0;
     float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
     if (c.inside) {
@@ -783,7 +597,7 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
     if (wmax <= 0) continue;
-    const Ring q = { s_a[wid], s_b[wid], s_c[wid], nullptr };
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
     uint32_t (*qid)[CH] = s_id[wid];
     float2 *pairs = s_pair[wid].pair;
     float *outt = s_pair[wid].out;
@@ -792,7 +606,6 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     s_w[wid][lane] = make_float4(w0, w1, w2, 0.0f);
     const int len = wmax;
     const int nchunks = (len + CH - 1) / CH;
-    const uint32_t *list = vals + c.start;
     auto issue = [&](int r, uint32_t id) {
         const int cj = nchunks - 1 - r;
         if (cj >= 0 && cj * CH + lane < len) {
@@ -805,19 +618,17 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         }
         cp_async_commit();
     };
-    auto fetch_pos = [&](int r) -> uint32_t {
+    auto fetch_id = [&](int r) -> uint32_t {
         const int cj = nchunks - 1 - r;
         return (cj >= 0 && cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u;
     };
-    uint32_t posn, posnn, idn;
+    uint32_t idn, idnn;
     {
-        const uint32_t p0 = fetch_pos(0), p1 = fetch_pos(1);
-        posn = fetch_pos(2);
-        posnn = fetch_pos(3);
-        const uint32_t i0 = __ldg(list + p0), i1 = __ldg(list + p1);
+        const uint32_t i0 = fetch_id(0), i1 = fetch_id(1);
+        idn = fetch_id(2);
+        idnn = fetch_id(3);
         issue(0, i0);
         issue(1, i1);
-        idn = __ldg(list + posn);
     }
     const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
     const float pxf = (float)c.px + half, pyf = (float)c.py + half;
@@ -895,9 +706,8 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 
     for (int r = 0; r < nchunks; ++r) {
         issue(r + 2, idn);
-        posn = posnn;
-        idn = __ldg(list + posn);
-        posnn = fetch_pos(r + 4);
+        idn = idnn;
+        idnn = fetch_id(r + 4);
         cp_async_wait_group<2>();
         __syncwarp();
         const int st = r % NS;
@@ -905,6 +715,7 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         const int first = ci * CH;
         const uint32_t live = __ballot_sync(FULL, my_last > first);
         uint32_t mask = cull_chunk<MODE>(q, st, lane, ci * CH + lane < len, c, live);
+        if (STATS) { st_staged += CH; if (lane == 0) st_walk += __popc(mask); }
         const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
         while (mask) {
             if (nslots > SL - 2) flush(); // room for both survivors of this iteration
@@ -915,6 +726,7 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             const int eb = two ? 31 - __clz(mask) : ea;
             mask &= ~(1u << eb);
             const int posa = first + ea, posb = first + eb;
+            if (STATS) st_eval += (posa < my_last) + (two && posb < my_last); // pairs whose sigma / q is evaluated
             const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
             float ga, gb; // alpha (3D) / g (2D) of the two pairs
             bool ca, cb;  // contributes
@@ -943,6 +755,7 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                 gb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-qb, 0x1.715476p+0f)));
             }
             const uint32_t cma = __ballot_sync(FULL, ca), cmb = __ballot_sync(FULL, cb);
+            if (STATS) st_contrib += ca + cb;
             if (!(cma | cmb)) continue;
             const float4 r2a = q2[ea], r2b = q2[eb];
             const float cwa = r2a.x * w0 + r2a.y * w1 + r2a.z * w2;
@@ -971,57 +784,27 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     if (nslots) flush();
     __syncwarp();
     } // task loop
-}
-
-// Which of the eight 8x4 blocks of tile (tx, ty) can the splat contribute to?  `half` = 0.5 (3D pixel centres) or
-// 0 (2D: integer pixel centres).  Same test as
-// ellipse_hits_box for every block, with the per-column / per-row terms shared: the blocks' pixel-centre
-// boxes are bounded by 4 vertical and 8 horizontal lines.
-__device__ __forceinline__ uint32_t block_mask8(float gx, float gy, float hA, float B, float hC, float thr, float half, int tx, int ty)
-{
-    const float lim = thr * 1.0001f + 2.0f * THR_SLACK;
-    const float kx = __fdividef(-B, 2.0f * hC), ky = __fdividef(-B, 2.0f * hA);
-    const float X0 = ((float)(tx * PS_TILE) + half) - gx, Y0 = ((float)(ty * PS_TILE) + half) - gy;
-    float ux0[2], ux1[2], cx[2], tx_[2], ax[2], bx_[2];
+    if (STATS) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        ux0[i] = X0 + 8.0f * i;
-        ux1[i] = X0 + (8.0f * i + 7.0f);
-        cx[i] = fminf(fmaxf(0.0f, ux0[i]), ux1[i]);
-        tx_[i] = kx * cx[i];          // unconstrained minimiser along the vertical line ux = cx
-        ax[i] = hA * cx[i] * cx[i];
-        bx_[i] = B * cx[i];
+        for (int d = 16; d >= 1; d >>= 1) {
+            st_eval += __shfl_xor_sync(FULL, st_eval, d);
+            st_contrib += __shfl_xor_sync(FULL, st_contrib, d);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + 4, st_eval);
+            atomicAdd(stats + 5, st_contrib);
+            atomicAdd(stats + 6, st_walk);
+            atomicAdd(stats + 7, st_staged);
+        }
     }
-    float uy0[4], uy1[4], cy[4], ty_[4], ay[4], by_[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uy0[j] = Y0 + 4.0f * j;
-        uy1[j] = Y0 + (4.0f * j + 3.0f);
-        cy[j] = fminf(fmaxf(0.0f, uy0[j]), uy1[j]);
-        ty_[j] = ky * cy[j];
-        ay[j] = hC * cy[j] * cy[j];
-        by_[j] = B * cy[j];
-    }
-    uint32_t m8 = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i = k & 1, j = k >> 1;
-        const float t1 = fminf(fmaxf(tx_[i], uy0[j]), uy1[j]);
-        const float s1 = ax[i] + (hC * t1 + bx_[i]) * t1;
-        const float t2 = fminf(fmaxf(ty_[j], ux0[i]), ux1[i]);
-        const float s2 = ay[j] + (hA * t2 + by_[j]) * t2;
-        const bool inx = cx[i] == 0.0f, iny = cy[j] == 0.0f;
-        const bool hit = (inx && iny) || (!inx && !(s1 > lim)) || (!iny && !(s2 > lim));
-        m8 |= hit ? (1u << k) : 0u;
-    }
-    return m8;
 }
 
 // Split every non-empty tile list, in order, into the lists of its eight 8x4 pixel blocks.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
-                   const int32_t *__restrict__ worklist, uint32_t *__restrict__ blist, int32_t *__restrict__ bcount)
+                   const int32_t *__restrict__ worklist, uint32_t *__restrict__ blist, uint32_t *__restrict__ bpos,
+                   int32_t *__restrict__ bcount)
 {
     __shared__ int s_cnt[8][8]; // [warp][block]
     __shared__ int s_pre[8][8]; // [warp][block] output cursor of the round
@@ -1033,6 +816,7 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     const int start = offsets[lin], len = offsets[lin + 1] - start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *out = blist + 8 * (size_t)start;
+    uint32_t *outp = bpos ? bpos + 8 * (size_t)start : nullptr;
     const uint32_t *list = vals + start;
     uint32_t inside8 = 0; // blocks that have at least one pixel inside the image
 #pragma unroll
@@ -1049,8 +833,10 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     for (int first = 0; first < len; first += 256) {
         const int j = first + tid;
         const float4 r0 = r0_n, r1 = r1_n;
+        const uint32_t id_cur = id_n;
         {
             const uint32_t id_next = id_nn;
+            id_n = id_next;
             id_nn = (first + 512 + tid < len) ? __ldg(list + first + 512 + tid) : 0u;
             r0_n = __ldg(PS_REC(t, id_next, 0));
             r1_n = __ldg(PS_REC(t, id_next, 1));
@@ -1058,8 +844,8 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         uint32_t m8 = 0;
         if (j < len) {
             float hA = r1.x, B = r1.y, hC = r1.z;
-            if (MODE == PS_MODE_2D) conic2d(r1, hA, B, hC);
-            m8 = block_mask8(r0.x, r0.y, hA, B, hC, r0.z, (MODE == PS_MODE_3D) ? 0.5f : 0.0f, tx, ty);
+            if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
+            m8 = ps_block_mask8(r0.x, r0.y, hA, B, hC, r0.z, (MODE == PS_MODE_3D) ? 0.5f : 0.0f, tx, ty);
             m8 &= inside8;
         }
         uint32_t bal[8];
@@ -1080,7 +866,11 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if ((m8 >> k) & 1u) out[(size_t)k * len + s_pre[wid][k] + __popc(bal[k] & ((1u << lane) - 1u))] = (uint32_t)j;
+            if ((m8 >> k) & 1u) {
+                const size_t o = (size_t)k * len + s_pre[wid][k] + __popc(bal[k] & ((1u << lane) - 1u));
+                out[o] = id_cur;
+                if (outp) outp[o] = (uint32_t)j;
+            }
         }
         if (threadIdx.x < 8) s_run[threadIdx.x] = s_tot[threadIdx.x];
         // s_cnt is rewritten by the next round only after every thread has passed the second barrier above, and
@@ -1095,8 +885,8 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    if (g.mode == PS_MODE_3D) block_lists_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bcount);
-    else block_lists_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bcount);
+    if (g.mode == PS_MODE_3D) block_lists_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount);
+    else block_lists_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1107,13 +897,14 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
     if (n_work <= 0) return 0;
     const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
     // 3D: v6 (candidate masks + per-pixel walk; 3.22 -> 3.04 ms at c2).  2D footprints cover half a block, where the
-    // all-lanes walk of v4 is faster (5.25 vs 5.44 ms at c3).  The pair statistics (bench only) are defined on v4's walk.
+    // all-lanes walk of v4 is faster (5.25 vs 5.44 ms at c3).  With `stats` the SAME kernel runs with its pair
+    // counters compiled in (bench.py's roofline numerator comes from the kernel it times).
     static const bool force_v4 = getenv("PS_FWD_V4") != nullptr; // A/B switch for measurements
-#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bcount, rgba8, stats)
-    if (g.mode == PS_MODE_3D) {
-        if (stats) PS_FWD(raster_fwd_kernel, PS_MODE_3D, true);
-        else if (force_v4) PS_FWD(raster_fwd_kernel, PS_MODE_3D, false);
-        else PS_FWD(raster_fwd6_kernel, PS_MODE_3D, false);
+#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bpos, l.bcount, rgba8, stats, l.n_lists)
+    if (g.mode == PS_MODE_3D && !force_v4) {
+        if (stats) PS_FWD(raster_fwd6_kernel, PS_MODE_3D, true); else PS_FWD(raster_fwd6_kernel, PS_MODE_3D, false);
+    } else if (g.mode == PS_MODE_3D) {
+        if (stats) PS_FWD(raster_fwd_kernel, PS_MODE_3D, true); else PS_FWD(raster_fwd_kernel, PS_MODE_3D, false);
     } else {
         if (stats) PS_FWD(raster_fwd_kernel, PS_MODE_2D, true); else PS_FWD(raster_fwd_kernel, PS_MODE_2D, false);
     }
@@ -1151,46 +942,39 @@ int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s)
 
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
-                         unsigned *next_task, cudaStream_t s)
+                         unsigned *next_task, unsigned long long *stats, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const unsigned grid = (unsigned)n_work * TASKS_PER_TILE;
-    static const bool use_v4 = getenv("PS_BWD_V4") != nullptr; // A/B switch for measurements: the warp-reduction backward
-    if (!use_v4) {
-        // per device (a process may drive several): full shared-memory carve-out (10 CTAs x 21.6 KB per SM) and the
-        // persistent grid = resident CTAs per SM x SMs
-        constexpr int MAX_DEV = 64;
-        static int ctas_per_sm[MAX_DEV][2] = {}, sm_count[MAX_DEV] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const int di = dev < MAX_DEV ? dev : MAX_DEV - 1;
-        const int mi = g.mode == PS_MODE_3D ? 0 : 1;
-        if (!ctas_per_sm[di][mi]) {
-            int per = 0;
-            cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev);
-            if (mi == 0) {
-                cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_3D, WPC>, RT_THREADS, 0);
-            } else {
-                cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_2D, WPC>, RT_THREADS, 0);
-            }
-            ctas_per_sm[di][mi] = per > 0 ? per : 1;
+    // per device (a process may drive several): full shared-memory carve-out (10 CTAs x 21.6 KB per SM) and the
+    // persistent grid = resident CTAs per SM x SMs
+    constexpr int MAX_DEV = 64;
+    static int ctas_per_sm[MAX_DEV][2] = {}, sm_count[MAX_DEV] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev < MAX_DEV ? dev : MAX_DEV - 1;
+    const int mi = g.mode == PS_MODE_3D ? 0 : 1;
+    if (!ctas_per_sm[di][mi]) {
+        int per = 0;
+        cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev);
+        if (mi == 0) {
+            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_3D, WPC, false>, RT_THREADS, 0);
+        } else {
+            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_2D, WPC, false>, RT_THREADS, 0);
         }
-        const int n_sm = sm_count[di];
-        const unsigned n_tasks = (unsigned)n_work * 8u;
-        const unsigned want = (n_tasks + WPC - 1) / WPC, cap = (unsigned)(n_sm * ctas_per_sm[di][mi]);
-        const unsigned pgrid = want < cap ? want : cap;
-        if (g.mode == PS_MODE_3D)
-            raster_bwd2_kernel<PS_MODE_3D, WPC><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, n_tasks, next_task);
-        else
-            raster_bwd2_kernel<PS_MODE_2D, WPC><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, n_tasks, next_task);
-        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        ctas_per_sm[di][mi] = per > 0 ? per : 1;
     }
-    if (g.mode == PS_MODE_3D)
-        raster_bwd_kernel<PS_MODE_3D><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc);
-    else
-        raster_bwd_kernel<PS_MODE_2D><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc);
+    const int n_sm = sm_count[di];
+    const unsigned n_tasks = (unsigned)n_work * 8u; // n_work may be an upper bound: the kernel reads the exact count
+    const unsigned want = (n_tasks + WPC - 1) / WPC, cap = (unsigned)(n_sm * ctas_per_sm[di][mi]);
+    const unsigned pgrid = want < cap ? want : cap;
+#define PS_BWD(MODE, ST) raster_bwd2_kernel<MODE, WPC, ST><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, l.n_lists, next_task, stats)
+    if (g.mode == PS_MODE_3D) { if (stats) PS_BWD(PS_MODE_3D, true); else PS_BWD(PS_MODE_3D, false); }
+    else { if (stats) PS_BWD(PS_MODE_2D, true); else PS_BWD(PS_MODE_2D, false); }
+#undef PS_BWD
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -43,13 +43,13 @@ def save_gaussian_npz(filename, means, quats, scales, opacities, colors, center=
 
 def load_gaussian_npz(filename) -> torch.Tensor:
     """NPZ -> [N,14] activated rows: means + center | scales | quats | colours | opacity."""
-    with np.load(filename, allow_pickle=True) as z:
+    # allow_pickle stays off: every array this loader needs is plain float data.  The reference's `metadata` entry is a
+    # pickled dict (export_gaussian_full.py:176); unpickling an archive someone else wrote can run arbitrary code, so it
+    # is not read -- the required keys identify the format.
+    with np.load(filename, allow_pickle=False) as z:
         missing = [k for k in NPZ_KEYS if k not in z.files]
         if missing:
             raise ValueError(f"{filename}: not a gaussian_splatting_full archive (missing {missing})")
-        meta = z["metadata"].item() if "metadata" in z.files else {}
-        if meta and meta.get("format") != "gaussian_splatting_full":
-            raise ValueError(f"{filename}: unknown format {meta.get('format')!r}")
         means = z["means"].astype(np.float32) + z["center"].astype(np.float32).reshape(1, 3)
         n = len(means)
         cols = [means, z["scales"].astype(np.float32).reshape(n, 3), z["quaternions"].astype(np.float32).reshape(n, 4),

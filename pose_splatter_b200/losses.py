@@ -66,16 +66,36 @@ def view_loss(rgb, alpha, target_img, target_mask, ssim_lambda: float, img_lambd
     return _ViewLoss.apply(rgb, alpha, target_img, target_mask, ssim_lambda, img_lambda)
 
 
+class _IouLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, mask):
+        dev = alpha.device
+        V, H, W = alpha.shape
+        a = alpha.detach().float().contiguous()
+        m = mask.detach().to(dtype=torch.float32, device=dev).contiguous()
+        losses = torch.empty(V, dtype=torch.float32, device=dev)
+        d_alpha = torch.empty_like(a) if alpha.requires_grad else None
+        _capi.check(_capi.load().ps_iou_loss(_capi.context(dev), V, H, W, _capi.ptr(a), _capi.ptr(m), _capi.ptr(losses),
+                                             _capi.ptr(d_alpha), _capi.stream_ptr(dev)), "ps_iou_loss")
+        if d_alpha is not None:
+            ctx.save_for_backward(d_alpha)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_alpha,) = ctx.saved_tensors
+        return d_alpha * g.to(d_alpha.dtype)[:, None, None], None
+
+
 def get_iou_loss(predicted_mask, target_mask, eps=1e-6):
-    """Name and meaning of scripts/training/train_script.py:30-36 for one [H,W] (or [V,H,W]) pair of masks."""
+    """Name and meaning of scripts/training/train_script.py:30-36 for one [H,W] (or [V,H,W]) pair of masks: its own
+    two-launch path (ps_iou_loss), any image size, finite for an empty target mask like the reference."""
     if predicted_mask.shape != target_mask.shape:
         raise ValueError("Predicted and target masks must have the same shape.")
     if eps != 1e-6:
         raise ValueError("the fused kernel implements the reference's eps = 1e-6")
+    if predicted_mask.device.type != "cuda":
+        raise RuntimeError(f"pose_splatter_b200.losses runs on CUDA tensors only (got {predicted_mask.device}); there is no CPU path")
     a = predicted_mask if predicted_mask.dim() == 3 else predicted_mask[None]
     m = target_mask if target_mask.dim() == 3 else target_mask[None]
-    V, H, W = a.shape
-    zeros = torch.zeros((V, H, W, 3), dtype=torch.float32, device=a.device)
-    total, parts = view_loss(zeros, a, zeros.permute(0, 3, 1, 2), m, 0.0, 0.0)
-    iou = total - parts[:, 1] - parts[:, 2]  # keeps the autograd edge of total; the other two terms are constants here
-    return iou.mean()
+    return _IouLoss.apply(a, m).mean()

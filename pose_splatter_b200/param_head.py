@@ -38,7 +38,8 @@ def _call_forward(mode, net_out, probs_sel, grid_sel, scale, voxel_size, pt, cli
     _capi.check(_capi.load().ps_param_head_forward(
         _capi.context(dev), _capi.MODE_3D if mode == "3d" else _capi.MODE_2D, n, _capi.ptr(net_out), _capi.ptr(probs_sel),
         _capi.ptr(grid_sel), _capi.ptr(scale), float(voxel_size), float(pt), float(clip[0]), float(clip[1]), pose,
-        angle, p_host, _capi.ptr(poses), _capi.ptr(row_frame), _capi.ptr(rows), _capi.stream_ptr(dev)), "ps_param_head_forward")
+        angle, p_host, _capi.ptr(poses), _capi.ptr(row_frame), 0 if poses is None else int(poses.shape[0]), _capi.ptr(rows),
+        _capi.stream_ptr(dev)), "ps_param_head_forward")
     return rows
 
 
@@ -66,7 +67,7 @@ class _Head(torch.autograd.Function):
         _capi.check(_capi.load().ps_param_head_backward(
             _capi.context(dev), _capi.MODE_3D if mode == "3d" else _capi.MODE_2D, n, _capi.ptr(net_c), _capi.ptr(probs_c),
             float(voxel_size), float(pt), float(clip[0]), float(clip[1]), pose, angle, _capi.ptr(poses), _capi.ptr(row_frame),
-            _capi.ptr(d_rows), _capi.ptr(d_net), _capi.ptr(d_probs), _capi.ptr(d_scale), _capi.stream_ptr(dev)),
+            0 if poses is None else int(poses.shape[0]), _capi.ptr(d_rows), _capi.ptr(d_net), _capi.ptr(d_probs), _capi.ptr(d_scale), _capi.stream_ptr(dev)),
             "ps_param_head_backward")
         return d_net, d_probs, d_scale.reshape(scale_shape), None, None, None, None, None, None, None, None
 

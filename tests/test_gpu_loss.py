@@ -121,3 +121,28 @@ def test_empty_batch_and_degenerate_masks():
     rgb, alpha, timg, mask = _inputs(1, 1, 16, 16)
     total, parts = losses.view_loss(rgb.to(DEV), alpha.to(DEV), timg.to(DEV), torch.zeros_like(mask).to(DEV), 1.0, 1.0)
     assert not torch.isfinite(parts[0, 2]) and torch.isfinite(parts[0, :2]).all()
+
+
+def test_iou_loss_own_path_any_size_and_empty_mask():
+    """get_iou_loss has its own two-launch path (ps_iou_loss): images smaller than the SSIM window, an all-zero
+    target mask gives the reference's finite value (its eps), gradient = autograd of the reference formula."""
+    from pose_splatter_b200 import losses
+    g = torch.Generator().manual_seed(3)
+    for H, W, empty in ((7, 5, False), (40, 33, True), (64, 48, False)):
+        a = torch.rand(3, H, W, generator=g)
+        m = torch.zeros(3, H, W) if empty else (torch.rand(3, H, W, generator=g) > 0.6).float()
+        ar = a.double().requires_grad_(True)
+        inter = (ar * m).sum(dim=(-2, -1))
+        union = (ar + m - ar * m).sum(dim=(-2, -1))
+        want = (1 - (inter + 1e-6) / (union + 1e-6)).mean()  # scripts/training/train_script.py:30-36
+        want.backward()
+        ad = a.to(DEV).requires_grad_(True)
+        got = losses.get_iou_loss(ad, m.to(DEV))
+        got.backward()
+        assert torch.isfinite(got) and abs(float(got) - float(want)) < 2e-6
+        assert float((ad.grad.cpu().double() - ar.grad).abs().max()) <= 1e-3 * float(ar.grad.abs().max()) + 1e-12
+    # a zero-weight term of the fused loss is exactly zero, also for an empty mask
+    rgb = torch.rand(1, 16, 16, 3, generator=g).to(DEV)
+    total, parts = losses.view_loss(rgb, torch.rand(1, 16, 16, generator=g).to(DEV), torch.rand(1, 3, 16, 16, generator=g).to(DEV),
+                                    torch.zeros(1, 16, 16, device=DEV), 0.0, 0.0)
+    assert torch.isfinite(parts).all() and float(parts[0, 1]) == 0.0 and float(parts[0, 2]) == 0.0

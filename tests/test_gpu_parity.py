@@ -374,3 +374,25 @@ def test_render_views_vjp_equals_autograd():
     # atomics make the accumulation order free: equal up to fp32 re-association
     rel = (p.grad - g2).abs().max() / p.grad.abs().max()
     assert rel.item() < 1e-5
+
+
+def test_bad_inputs_are_rejected_or_guarded():
+    """short viewmats / Ks raise on the host; a frame id outside [0, F) held on the device never reads out of
+    bounds -- that view renders nothing and gets no gradient."""
+    _, _capi, batched, synth = _mods()
+    d = synth.make_views("c2", 1, 3, seed=2, n=500)
+    W, H = d["width"], d["height"]
+    p, bg = d["params"].to(DEV), torch.ones(3, device=DEV)
+    with pytest.raises(ValueError, match="viewmats"):
+        batched.render_views("3d", p, d["view_frame"].to(DEV), W, H, bg, d["viewmats"][:2].to(DEV), d["Ks"].to(DEV))
+    with pytest.raises(ValueError, match="view_frame entries"):
+        batched.render_views("3d", p, torch.tensor([0, 0, 5], dtype=torch.int32), W, H, bg, d["viewmats"].to(DEV), d["Ks"].to(DEV))
+    vf = torch.tensor([0, 7, -3], dtype=torch.int32, device=DEV)  # device-side map: guarded inside the kernels
+    pr = p.clone().requires_grad_(True)
+    rgb, alpha = batched.render_views("3d", pr, vf, W, H, bg, d["viewmats"].to(DEV), d["Ks"].to(DEV))
+    (rgb.sum() + alpha.sum()).backward()
+    torch.cuda.synchronize()
+    assert float(alpha[1:].abs().max()) == 0.0 and float(alpha[0].max()) > 0.0
+    assert torch.isfinite(pr.grad).all()
+    rgb0, alpha0 = batched.render_views("3d", p, vf[:1], W, H, bg, d["viewmats"][:1].to(DEV), d["Ks"][:1].to(DEV))
+    assert torch.equal(rgb0[0], rgb[0]) and torch.equal(alpha0[0], alpha[0])
