@@ -121,8 +121,9 @@ int ps_forward_rgba8(ps_ctx *ctx, const ps_render_desc *desc, const float *param
 /*
  * Backward of ps_forward: d_params [F,N,P] = dL/d gaussian_params given d_rgb [V,H,W,3] and
  * d_alpha [V,H,W].  Replaces autograd through :183-211 / :314-427 (gsplat's
- * rasterize_to_pixels_bwd + fully_fused_projection_bwd in 3D).  The input pointers must be
- * the ones given to the forward.  d_params is overwritten (not accumulated into).
+ * rasterize_to_pixels_bwd + fully_fused_projection_bwd in 3D).  params / viewmats / Ks must hold what the forward
+ * was given; `background` is ignored (the forward kept its own copy; may be NULL).  d_params is overwritten (not
+ * accumulated into).
  */
 int ps_backward(ps_ctx *ctx, ps_saved *saved, const float *params, const int32_t *view_frame, const float *viewmats,
                 const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,

@@ -168,7 +168,7 @@ class _RenderViews(torch.autograd.Function):
         rgb, alpha, _, saved = forward_raw(mode, p, view_frame, viewmats, Ks, background, width, height,
                                            _capi.FLAG_SAVE_FOR_BACKWARD if need else 0, False, opts)
         ctx.saved_fwd = saved
-        ctx.aux = (p, view_frame, viewmats, Ks, background.clone())
+        ctx.aux = (p, view_frame, viewmats, Ks, background)  # the library keeps its own copy of the colour for the backward
         ctx.in_dtype = params.dtype
         return rgb, alpha
 

@@ -21,6 +21,7 @@
 #include "ps_contract.cuh"
 #include "ps_cull.cuh"
 #include "ps_internal.h"
+#include <cstdlib>
 
 namespace {
 
@@ -321,9 +322,10 @@ build_worklist_kernel(const int32_t *__restrict__ offsets, int T, int32_t *__res
 
 // Every listed Gaussian drops one slot word into the list of every tile it touches: its depth rank (3D) / row index
 // (2D) in the low 24 bits and, above them, the 8-bit mask of the tile's 8x4 pixel blocks its footprint can reach
-// (ps_block_mask8 on the record the thread already holds: the block lists are later built from these masks without
-// touching the records again).
-template <int MODE>
+// (from the record the thread already holds: the block lists are later built from these masks without touching the
+// records again).  EXACT = false: the blocks met by the footprint's bounding box (a few per cent more block-list entries
+// than the exact ellipse-vs-block test, at a tenth of the instructions; the rasterizers' per-pixel tests decide anyway).
+template <int MODE, bool EXACT>
 __global__ void __launch_bounds__(PS_PROJ_BLOCK)
 partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, int32_t *__restrict__ fill,
                  uint32_t *__restrict__ slots, int use_smem)
@@ -337,6 +339,8 @@ partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, i
     int tx0 = 0, ty0 = 0, tx1 = 0, ty1 = 0;
     uint32_t val = 0;
     float gx = 0.0f, gy = 0.0f, thr = 0.0f, hA = 0.0f, B = 0.0f, hC = 0.0f;
+    const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
+    PsBlockRect brect = { 1, 0, 1, 0 };
     if (touched) {
         const uint2 tr = t.tile_rect[idx];
         tx0 = tr.x & 0xffff; ty0 = tr.x >> 16; tx1 = tr.y & 0xffff; ty1 = tr.y >> 16;
@@ -345,10 +349,13 @@ partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, i
         gx = r0.x; gy = r0.y; thr = r0.z;
         hA = r1.x; B = r1.y; hC = r1.z;
         if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
+        float ex, ey;
+        ps_footprint_box(hA, B, hC, thr, ex, ey);
+        brect = ps_block_rect(gx, gy, ex, ey, half, g.W, g.H);
     }
-    const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
     auto slot_word = [&](int tx, int ty) -> uint32_t {
-        const uint32_t m8 = ps_block_mask8(gx, gy, hA, B, hC, thr, half, tx, ty) & ps_blocks_inside8(tx, ty, g.W, g.H);
+        const uint32_t m8 = EXACT ? (ps_block_mask8(gx, gy, hA, B, hC, thr, half, tx, ty) & ps_blocks_inside8(tx, ty, g.W, g.H))
+                                  : ps_block_mask8_rect(brect, tx, ty);
         return val | (m8 << PS_SLOT_MASK_SHIFT);
     };
     const int32_t *off_v = offsets + (size_t)v * g.n_tiles;
@@ -440,25 +447,29 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
 
 // One CTA per non-empty list: sorts it AND splits it into the lists of the tile's eight 8x4 pixel blocks, without
 // reading a single splat record.  The keys of a list are unique integers < N, so nine bitmaps in shared memory (the
-// whole list + one per block, filled from the slot words' block masks) and their popcount prefixes give every entry
-// its position in the sorted tile list and in every block list it belongs to; the entry is then scattered there.
-//   vals  [start + pos]              = view * N + Gaussian           (the sorted tile list: gsplat's flatten_ids;
-//                                                                     NULL = not materialised, only the taps read it)
-//   blist [8 start + k len + pos_k]  = view * N + Gaussian           (block k's list, same order)
-//   bpos  [8 start + k len + pos_k]  = pos                           (only for the last-id tap, may be NULL)
-// Shared memory: 18 words per 32 keys (9 bitmaps + 9 prefix arrays).
+// whole list + one per block, filled from the slot words' block masks) hold the sorted lists implicitly.
+//   phase 1  (thread = list entry, four in flight): set the entry's bit in the bitmaps of its blocks; 3D: look up the
+//            Gaussian of this depth rank once and park it in a shared-memory table indexed by rank
+//   phase 2  (warp k = block k): enumerate bitmap k 32 words at a time (popcount + warp scan), every lane writes the
+//            ids of its word's set bits as one contiguous run: ordered output, neighbouring lanes write neighbouring runs
+//   blist [8 start + k len + j]  = view * N + Gaussian   of the j-th entry (in depth / row order) of block k
+//   KEEP (parity taps): vals [start + pos] = the sorted tile list itself (gsplat's flatten_ids) and
+//   bpos [8 start + k len + j] = pos, the entry's position in it (for the last-id tap)
+// Shared memory: 9 words per 32 keys (+ 4 N bytes for the rank -> id table in 3D when it fits, + 1 word per 32 keys KEEP).
 constexpr int SPLIT_THREADS = 256;
 constexpr int SPLIT_MAPS = 9;
+constexpr int SPLIT_MLP = 4; // list entries in flight per thread in phase 1
+constexpr int SPLIT_WPL = 4; // bitmap words per lane and step in phase 2
 
-template <int MODE>
+template <int MODE, bool KEEP>
 __global__ void __launch_bounds__(SPLIT_THREADS)
 sort_split_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const uint32_t *__restrict__ slots, uint32_t *__restrict__ vals,
                   uint32_t *__restrict__ blist, uint32_t *__restrict__ bpos, int32_t *__restrict__ bcount,
-                  const int32_t *__restrict__ n_lists)
+                  const int32_t *__restrict__ n_lists, int use_table)
 {
-    extern __shared__ uint32_t s_dyn32[]; // bm [9][words] | pre [9][words]
-    __shared__ int s_wsum[SPLIT_THREADS / 32][SPLIT_MAPS];
+    extern __shared__ uint32_t s_dyn32[]; // bm [9][words] | pre [words] (KEEP) | ids [N] (3D, use_table)
+    __shared__ int s_wsum[SPLIT_THREADS / 32];
     const int item = blockIdx.x;
     if (item >= __ldg(n_lists)) return; // the grid may be an upper bound (sync-free small calls)
     const int lin = worklist[item];
@@ -466,79 +477,107 @@ sort_split_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
     const int view = lin / g.n_tiles;
     const int words = (g.N + 31) >> 5;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t *bm = s_dyn32, *pre = s_dyn32 + SPLIT_MAPS * words;
+    uint32_t *bm = s_dyn32;
+    uint32_t *pre = bm + SPLIT_MAPS * words;
+    uint32_t *ids = (MODE == PS_MODE_3D && use_table) ? pre + (KEEP ? words : 0) : nullptr;
+    const uint32_t vbase = (uint32_t)view * (uint32_t)g.N;
     for (int w = tid; w < SPLIT_MAPS * words; w += SPLIT_THREADS) bm[w] = 0u;
     __syncthreads();
-    for (int i = start + tid; i < end; i += SPLIT_THREADS) {
-        const uint32_t sw = __ldg(slots + i);
-        const uint32_t r = sw & PS_SLOT_KEY_MASK;
-        uint32_t m8 = sw >> PS_SLOT_MASK_SHIFT;
-        const uint32_t bit = 1u << (r & 31u);
-        atomicOr(&bm[r >> 5], bit);
-        while (m8) {
-            const int k = __ffs(m8) - 1;
-            m8 &= m8 - 1;
-            atomicOr(&bm[(1 + k) * words + (r >> 5)], bit);
+    for (int i0 = start + tid; i0 < end; i0 += SPLIT_MLP * SPLIT_THREADS) {
+        uint32_t sw[SPLIT_MLP], gid[SPLIT_MLP];
+#pragma unroll
+        for (int u = 0; u < SPLIT_MLP; ++u) {
+            const int i = i0 + u * SPLIT_THREADS;
+            sw[u] = i < end ? __ldg(slots + i) : 0xffffffffu;
+        }
+        if (ids) {
+#pragma unroll
+            for (int u = 0; u < SPLIT_MLP; ++u)
+                gid[u] = sw[u] != 0xffffffffu ? __ldg(order + vbase + (sw[u] & PS_SLOT_KEY_MASK)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < SPLIT_MLP; ++u) {
+            if (i0 + u * SPLIT_THREADS >= end) continue;
+            const uint32_t r = sw[u] & PS_SLOT_KEY_MASK;
+            uint32_t m8 = sw[u] >> PS_SLOT_MASK_SHIFT;
+            const uint32_t bit = 1u << (r & 31u);
+            atomicOr(&bm[r >> 5], bit);
+            if (ids) ids[r] = vbase + gid[u];
+            while (m8) {
+                const int k = __ffs(m8) - 1;
+                m8 &= m8 - 1;
+                atomicOr(&bm[(1 + k) * words + (r >> 5)], bit);
+            }
         }
     }
     __syncthreads();
-    // exclusive popcount prefix of every bitmap: thread t owns a contiguous run of words
-    const int wpt = (words + SPLIT_THREADS - 1) / SPLIT_THREADS;
-    const int w0 = min(words, tid * wpt), w1 = min(words, w0 + wpt);
-    int cnt[SPLIT_MAPS], incl[SPLIT_MAPS];
-#pragma unroll
-    for (int j = 0; j < SPLIT_MAPS; ++j) {
+    if (KEEP) { // the sorted tile list itself + the word prefixes that give every entry its position in it
+        const int wpt = (words + SPLIT_THREADS - 1) / SPLIT_THREADS;
+        const int w0 = min(words, tid * wpt), w1 = min(words, w0 + wpt);
         int c = 0;
-        for (int w = w0; w < w1; ++w) c += __popc(bm[j * words + w]);
-        cnt[j] = c;
+        for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
         int x = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int n = __shfl_up_sync(FULL, x, d);
             if (lane >= d) x += n;
         }
-        incl[j] = x;
-        if (lane == 31) s_wsum[wid][j] = x;
-    }
-    __syncthreads();
+        if (lane == 31) s_wsum[wid] = x;
+        __syncthreads();
+        int run = x - c;
 #pragma unroll
-    for (int j = 0; j < SPLIT_MAPS; ++j) {
-        int base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < SPLIT_THREADS / 32; ++w) {
-            const int sgm = s_wsum[w][j];
-            base += (w < wid) ? sgm : 0;
-            total += sgm;
-        }
-        int run = base + incl[j] - cnt[j];
+        for (int w = 0; w < SPLIT_THREADS / 32; ++w) run += (w < wid) ? s_wsum[w] : 0;
         for (int w = w0; w < w1; ++w) {
-            pre[j * words + w] = (uint32_t)run;
-            run += __popc(bm[j * words + w]);
+            pre[w] = (uint32_t)run;
+            uint32_t bits = bm[w];
+            while (bits) {
+                const uint32_t r = (uint32_t)(w << 5) + (uint32_t)(__ffs(bits) - 1);
+                bits &= bits - 1;
+                vals[start + run++] = (MODE == PS_MODE_3D) ? (ids ? ids[r] : vbase + __ldg(order + vbase + r)) : vbase + r;
+            }
         }
-        if (j > 0 && tid == 0) bcount[item * 8 + (j - 1)] = total;
+        __syncthreads();
     }
-    __syncthreads();
-    const uint32_t vbase = (uint32_t)view * (uint32_t)g.N;
-    uint32_t *bl = blist + 8 * (size_t)start;
-    uint32_t *bp = bpos ? bpos + 8 * (size_t)start : nullptr;
-    for (int i = start + tid; i < end; i += SPLIT_THREADS) {
-        const uint32_t sw = __ldg(slots + i);
-        const uint32_t r = sw & PS_SLOT_KEY_MASK;
-        uint32_t m8 = sw >> PS_SLOT_MASK_SHIFT;
-        const uint32_t word = r >> 5, below = (1u << (r & 31u)) - 1u;
-        const uint32_t id = (MODE == PS_MODE_3D) ? vbase + __ldg(order + vbase + r) : vbase + r;
-        uint32_t pos = 0;
-        if (vals) { // the sorted tile list itself is only materialised for the parity taps
-            pos = pre[word] + __popc(bm[word] & below);
-            vals[start + pos] = id;
+    // phase 2: warp k enumerates block k's bitmap, 128 keys per lane and step
+    {
+        const int k = wid; // SPLIT_THREADS / 32 == 8 blocks
+        const uint32_t *map = bm + (1 + k) * words;
+        uint32_t *out = blist + 8 * (size_t)start + (size_t)k * len;
+        uint32_t *outp = (KEEP && bpos) ? bpos + 8 * (size_t)start + (size_t)k * len : nullptr;
+        int run = 0;
+        for (int wb = 0; wb < words; wb += 32 * SPLIT_WPL) {
+            const int w0 = wb + lane * SPLIT_WPL;
+            uint32_t bits[SPLIT_WPL];
+            int c = 0;
+#pragma unroll
+            for (int q = 0; q < SPLIT_WPL; ++q) {
+                bits[q] = w0 + q < words ? map[w0 + q] : 0u;
+                c += __popc(bits[q]);
+            }
+            int x = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int n = __shfl_up_sync(FULL, x, d);
+                if (lane >= d) x += n;
+            }
+            const int total = __shfl_sync(FULL, x, 31);
+            if (total == 0) continue;
+            int pos = run + x - c;
+#pragma unroll
+            for (int q = 0; q < SPLIT_WPL; ++q) {
+                uint32_t bq = bits[q];
+                while (bq) {
+                    const uint32_t b = (uint32_t)(__ffs(bq) - 1);
+                    bq &= bq - 1;
+                    const uint32_t r = (uint32_t)((w0 + q) << 5) + b;
+                    out[pos] = (MODE == PS_MODE_3D) ? (ids ? ids[r] : vbase + __ldg(order + vbase + r)) : vbase + r;
+                    if (KEEP && outp) outp[pos] = pre[w0 + q] + __popc(bm[w0 + q] & ((1u << b) - 1u));
+                    ++pos;
+                }
+            }
+            run += total;
         }
-        while (m8) {
-            const int k = __ffs(m8) - 1;
-            m8 &= m8 - 1;
-            const uint32_t pk = pre[(1 + k) * words + word] + __popc(bm[(1 + k) * words + word] & below);
-            bl[(size_t)k * len + pk] = id;
-            if (bp) bp[(size_t)k * len + pk] = pos;
-        }
+        if (lane == 0) bcount[item * 8 + k] = run;
     }
 }
 
@@ -608,13 +647,15 @@ int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l,
     dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
     const int use_smem = g.n_tiles <= PS_HIST_SMEM_TILES;
     const size_t dyn = use_smem ? (size_t)2 * g.n_tiles * sizeof(int) : 0;
-    if (g.mode == PS_MODE_3D) {
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        partition_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);
-    } else {
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        partition_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);
-    }
+    static const bool exact = getenv("PS_EXACT_BLOCK_MASKS") != nullptr; // A/B switch for measurements
+#define PS_PART(MODE, EX)                                                                                                     \
+    do {                                                                                                                      \
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<MODE, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1; \
+        partition_kernel<MODE, EX><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);                  \
+    } while (0)
+    if (g.mode == PS_MODE_3D) { if (exact) PS_PART(PS_MODE_3D, true); else PS_PART(PS_MODE_3D, false); }
+    else { if (exact) PS_PART(PS_MODE_2D, true); else PS_PART(PS_MODE_2D, false); }
+#undef PS_PART
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -640,23 +681,27 @@ int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-// the fused sort + block split needs 18 shared-memory words per 32 Gaussians (72 KB at N = 128 K)
-bool ps_split_fits_smem(const PsGeometry &g)
-{
-    return (size_t)((g.N + 31) / 32) * 2 * SPLIT_MAPS * sizeof(uint32_t) <= 160 * 1024;
-}
+// the fused sort + block split needs 9 (+1) shared-memory words per 32 Gaussians for its bitmaps
+static size_t split_map_bytes(const PsGeometry &g, bool keep) { return (size_t)((g.N + 31) / 32) * (SPLIT_MAPS + (keep ? 1 : 0)) * sizeof(uint32_t); }
+bool ps_split_fits_smem(const PsGeometry &g) { return split_map_bytes(g, true) <= 160 * 1024; }
 
 int ps_launch_sort_split(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const size_t dyn = (size_t)((g.N + 31) / 32) * 2 * SPLIT_MAPS * sizeof(uint32_t);
-    if (g.mode == PS_MODE_3D) {
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_split_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        sort_split_kernel<PS_MODE_3D><<<n_work, SPLIT_THREADS, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, l.blist, l.bpos, l.bcount, l.n_lists);
-    } else {
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_split_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        sort_split_kernel<PS_MODE_2D><<<n_work, SPLIT_THREADS, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, l.blist, l.bpos, l.bcount, l.n_lists);
-    }
+    const bool keep = l.vals != nullptr;
+    size_t dyn = split_map_bytes(g, keep);
+    // 3D: rank -> Gaussian table in shared memory when it leaves room for two CTAs per SM, else gathers in phase 2
+    static const bool table_ok = getenv("PS_SPLIT_TABLE") != nullptr; // A/B switch for measurements
+    const int use_table = table_ok && g.mode == PS_MODE_3D && dyn + (size_t)g.N * sizeof(uint32_t) <= 100 * 1024;
+    if (use_table) dyn += (size_t)g.N * sizeof(uint32_t);
+#define PS_SPLIT(MODE, KP)                                                                                                    \
+    do {                                                                                                                      \
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_split_kernel<MODE, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1; \
+        sort_split_kernel<MODE, KP><<<n_work, SPLIT_THREADS, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, l.blist, l.bpos, l.bcount, l.n_lists, use_table); \
+    } while (0)
+    if (g.mode == PS_MODE_3D) { if (keep) PS_SPLIT(PS_MODE_3D, true); else PS_SPLIT(PS_MODE_3D, false); }
+    else { if (keep) PS_SPLIT(PS_MODE_2D, true); else PS_SPLIT(PS_MODE_2D, false); }
+#undef PS_SPLIT
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -243,6 +243,7 @@ struct ps_saved {
     int32_t *last;  // [V,H,W] tile-list position + 1 of the last contributor (PS_FLAG_KEEP_BINNING: tap only)
     int32_t *blast; // [V,H,W] block-list index + 1 of the last contributor (what the backward starts from)
     int32_t *frame_off, *frame_views; // CSR: the views of every frame (projection backward sums them per row)
+    float *bg;      // [3] background colour of the forward (lives in the offsets allocation)
     float *t_pen;   // [V,H,W]
 };
 
@@ -317,6 +318,7 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
     dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bpos, s); dev_free(sv->l.bcount, s);
     dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->blast, s); dev_free(sv->t_pen, s);
     sv->frame_off = sv->frame_views = nullptr; // live inside the offsets allocation
+    sv->bg = nullptr;
     sv->l.n_lists = nullptr;                   // lives inside cls
     if (sv->ctx) mail_give(sv->ctx, sv->mail);
     sv->mail.h = nullptr;
@@ -372,7 +374,8 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
         const size_t npix = (size_t)g.V * g.H * g.W;
         if (T > 0x7ffffff0ULL) { rc = fail(1, "ps_forward: %zu (view, tile) lists exceed 2^31", T); goto out; }
         if (g.N > (1 << 20)) { rc = fail(1, "ps_forward: at most 2^20 Gaussians per frame (got %d)", g.N); goto out; }
-        const bool split = ps_split_fits_smem(g); // sort + block split in one kernel (else: list sort, then record gathers)
+        static const bool no_split = getenv("PS_NO_SPLIT") != nullptr; // A/B switch for measurements
+        const bool split = !no_split && ps_split_fits_smem(g); // sort + block split in one kernel (else: list sort, then record gathers)
         // Small calls (the reference's own call shape: one view per render()) never wait for the host: the list arrays
         // are sized for the worst case M = V * N * n_tiles and the per-list kernels are launched over all V * n_tiles
         // lists, reading the exact counts on the device.  Large batches size everything exactly from the mailbox
@@ -385,10 +388,11 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
         sv->resolved = true;
         // offsets [T+1] | frame_off [F+1] | frame_views [V] | csr cursor [F] share one allocation: tiny pool
         // allocations split the large free blocks the next call wants to reuse
-        PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1 + (size_t)g.F + 1 + (size_t)g.V + (size_t)g.F, s));
+        PS_TRY_CUDA(dev_alloc(&sv->l.offsets, T + 1 + (size_t)g.F + 1 + (size_t)g.V + (size_t)g.F + 4, s));
         sv->frame_off = sv->l.offsets + T + 1;
         sv->frame_views = sv->frame_off + g.F + 1;
         csr_cursor = sv->frame_views + g.V;
+        sv->bg = reinterpret_cast<float *>(csr_cursor + g.F); // the forward's background colour, kept for the backward
         PS_TRY_CUDA(dev_alloc(&sv->l.cls, (size_t)PS_CLS_WORDS, s));
         sv->l.n_lists = sv->l.cls + 3 * PS_N_CLASSES;
         PS_TRY_CUDA(dev_alloc(&scan_scratch, ps_scan_scratch_elems(g), s));
@@ -448,7 +452,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
                 PS_TRY_LAUNCH(ps_launch_debug_keys(g, sv->t, sv->l, sv->n_work, sv->keys, s));
             }
         }
-        if (save) PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, s));
+        if (save) PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, background, sv->bg, s));
         if (npix > 0) {
             if (save) {
                 PS_TRY_CUDA(dev_alloc(&sv->blast, npix, s));
@@ -518,7 +522,8 @@ static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const f
     }
     if (!nothing && (!sv->blast || !sv->t_pen)) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
     if (!sv->frame_off) return fail(1, "ps_backward: forward was not run with PS_FLAG_SAVE_FOR_BACKWARD");
-    if (!params || !background || (!nothing && (!d_rgb || !d_alpha))) return fail(1, "ps_backward: NULL buffer");
+    if (!params || (!nothing && (!d_rgb || !d_alpha))) return fail(1, "ps_backward: NULL buffer");
+    background = sv->bg; // the colour the forward composited against (the caller's buffer may have changed since)
     float *acc = nullptr;
     const size_t acc_rows = VN > 0 ? VN : 1;
     PS_CUDA(dev_alloc(&acc, acc_rows * PS_ACC_STRIDE + 4, s)); // + the rasterizer's task counter, zeroed with the rows

@@ -62,6 +62,51 @@ __device__ __forceinline__ uint32_t ps_block_mask8(float gx, float gy, float hA,
     return m8;
 }
 
+// Bounding box of the footprint {u : hA ux^2 + B ux uy + hC uy^2 <= lim} around the mean, half-widths in pixels
+// (slightly inflated).  A degenerate conic (not positive definite, NaN) gets an unbounded box.
+__device__ __forceinline__ void ps_footprint_box(float hA, float B, float hC, float thr, float &ex, float &ey)
+{
+    const float lim = thr * 1.0001f + 2.0f * PS_THR_SLACK;
+    const float det = hA * hC - 0.25f * B * B;
+    ex = ey = 3.0e38f;
+    if (det > 0.0f && lim >= 0.0f) {
+        const float k = __fdividef(lim, det);
+        ex = sqrtf(k * hC) * 1.0001f + 1e-3f;
+        ey = sqrtf(k * hA) * 1.0001f + 1e-3f;
+        if (!(ex == ex) || !(ey == ey)) ex = ey = 3.0e38f;
+    }
+}
+
+// Footprint bounding box -> inclusive rectangle of 8x4 pixel blocks (global block coordinates: column = x / 8,
+// row = y / 4) whose pixel centres it meets, clipped to the image; empty if c0 > c1 or r0 > r1.
+struct PsBlockRect { int c0, c1, r0, r1; };
+__device__ __forceinline__ PsBlockRect ps_block_rect(float gx, float gy, float ex, float ey, float half, int W, int H)
+{
+    // block column c holds the pixel centres [8c + half, 8c + 7 + half]; it meets [gx - ex, gx + ex] iff
+    // 8c + half <= gx + ex and 8c + 7 + half >= gx - ex
+    const float big = 1.0e9f;
+    const float xl = fmaxf(gx - ex, -big), xh = fminf(gx + ex, big), yl = fmaxf(gy - ey, -big), yh = fminf(gy + ey, big);
+    PsBlockRect r;
+    r.c0 = max(0, (int)ceilf((xl - half - 7.0f) * 0.125f));
+    r.c1 = min((W - 1) >> 3, (int)floorf((xh - half) * 0.125f));
+    r.r0 = max(0, (int)ceilf((yl - half - 3.0f) * 0.25f));
+    r.r1 = min((H - 1) >> 2, (int)floorf((yh - half) * 0.25f));
+    return r;
+}
+
+// the blocks of tile (tx, ty) inside the block rectangle: a superset of the blocks the exact test (ps_block_mask8)
+// keeps, for a handful of integer instructions
+__device__ __forceinline__ uint32_t ps_block_mask8_rect(const PsBlockRect &r, int tx, int ty)
+{
+    const int c = 2 * tx, q = 4 * ty;
+    const uint32_t cols = ((r.c0 <= c && c <= r.c1) ? 1u : 0u) | ((r.c0 <= c + 1 && c + 1 <= r.c1) ? 2u : 0u);
+    uint32_t m8 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (r.r0 <= q + j && q + j <= r.r1) m8 |= cols << (2 * j);
+    return m8;
+}
+
 // blocks of tile (tx, ty) that have at least one pixel inside the W x H image
 __device__ __forceinline__ uint32_t ps_blocks_inside8(int tx, int ty, int W, int H)
 {

@@ -53,8 +53,9 @@ struct PsLists {
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
                       const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s);
 // view_frame [V] -> CSR (frame_off [F+1], frame_views [V]); cursor [F] is scratch
+// also keeps a copy of the forward's background colour (bg_saved [3]) for the backward
 int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t *frame_off, int32_t *cursor,
-                        int32_t *frame_views, cudaStream_t s);
+                        int32_t *frame_views, const float *background, float *bg_saved, cudaStream_t s);
 // peers == nullptr: rows stored into d_params; else rows pushed into slot [my_rank][frame / world] of the staging
 // buffer of rank frame % world (peers = device array of the ranks' staging base pointers)
 int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_t *frame_off, const int32_t *frame_views,

@@ -315,11 +315,13 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(const float *__restrict__
 // view -> frame map to CSR (views of every frame): one CTA; order inside a frame is arbitrary
 __global__ void __launch_bounds__(1024)
 frame_csr_kernel(const int32_t *__restrict__ view_frame, int V, int F, int32_t *__restrict__ frame_off,
-                 int32_t *__restrict__ cursor, int32_t *__restrict__ frame_views)
+                 int32_t *__restrict__ cursor, int32_t *__restrict__ frame_views, const float *__restrict__ background,
+                 float *__restrict__ bg_saved)
 {
     __shared__ int s_carry;
     __shared__ int s_warp[33];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 3 && bg_saved) bg_saved[tid] = background[tid]; // the backward composites against the forward's background
     for (int f = tid; f <= F; f += 1024) frame_off[f] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -430,9 +432,9 @@ int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *v
 }
 
 int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t *frame_off, int32_t *cursor,
-                        int32_t *frame_views, cudaStream_t s)
+                        int32_t *frame_views, const float *background, float *bg_saved, cudaStream_t s)
 {
-    frame_csr_kernel<<<1, 1024, 0, s>>>(view_frame, g.V, g.F, frame_off, cursor, frame_views);
+    frame_csr_kernel<<<1, 1024, 0, s>>>(view_frame, g.V, g.F, frame_off, cursor, frame_views, background, bg_saved);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -34,6 +34,7 @@ class GaussianRenderer(ABC, nn.Module):
         self.height = height
         self.device = device
         self.register_buffer("background_color", torch.zeros(3, device=device))
+        self._frame0 = {}  # device -> the [0] view->frame map of a single-view call
 
     @abstractmethod
     def get_num_params(self) -> int:
@@ -59,7 +60,9 @@ class GaussianRenderer(ABC, nn.Module):
                 "pose_splatter_b200 renders on CUDA devices only (gaussian_params is on "
                 f"{gaussian_params.device}); there is no CPU fallback")
         dev = gaussian_params.device
-        frame0 = torch.zeros(1, dtype=torch.int32, device=dev)
+        frame0 = self._frame0.get(dev)  # non-persistent scratch like the reference's _cached_grids (not in state_dict)
+        if frame0 is None:
+            frame0 = self._frame0[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
         vm = None if viewmat is None else viewmat.reshape(1, 4, 4)
         Km = None if K is None else K.reshape(1, 3, 3)
         rgb, alpha = render_views(mode, gaussian_params.unsqueeze(0), frame0, self.width, self.height,

@@ -115,7 +115,7 @@ def test_raw_render_equals_reference_adapter_composed_with_activated_render():
         out[name] = (rgb.cpu().numpy(), alpha.cpu().numpy(), g[0].cpu().double().numpy())
     assert np.abs(out["raw"][0] - out["act"][0]).max() <= 2e-5
     assert np.abs(out["raw"][1] - out["act"][1]).max() <= 2e-5
-    assert (out["raw"][1] > 0.05).mean() > 0.01, "the case must actually render something"
+    assert (out["raw"][1] > 0.05).mean() > 0.005, "the case must actually render something"
     chained = np.einsum("iaj,ia->ij", jac.double().numpy(), out["act"][2])
     assert column_rel_err(out["raw"][2], chained).max() <= 1e-3
     del rows_np
