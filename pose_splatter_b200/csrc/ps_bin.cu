@@ -323,9 +323,10 @@ build_worklist_kernel(const int32_t *__restrict__ offsets, int T, int32_t *__res
 // Every listed Gaussian drops one slot word into the list of every tile it touches: its depth rank (3D) / row index
 // (2D) in the low 24 bits and, above them, the 8-bit mask of the tile's 8x4 pixel blocks its footprint can reach
 // (from the record the thread already holds: the block lists are later built from these masks without touching the
-// records again).  EXACT = false: the blocks met by the footprint's bounding box (a few per cent more block-list entries
-// than the exact ellipse-vs-block test, at a tenth of the instructions; the rasterizers' per-pixel tests decide anyway).
-template <int MODE, bool EXACT>
+// records again).  MASKS = 1: the blocks met by the footprint's bounding box (a few per cent more block-list entries
+// than the exact ellipse-vs-block test of MASKS = 2, at a tenth of the instructions; the rasterizers' per-pixel tests
+// decide anyway).  MASKS = 0: plain keys (the block split gathers the records itself).
+template <int MODE, int MASKS> // MASKS: 0 = plain keys, 1 = block rectangle of the footprint's bounding box, 2 = exact test
 __global__ void __launch_bounds__(PS_PROJ_BLOCK)
 partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, int32_t *__restrict__ fill,
                  uint32_t *__restrict__ slots, int use_smem)
@@ -345,17 +346,20 @@ partition_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, i
         const uint2 tr = t.tile_rect[idx];
         tx0 = tr.x & 0xffff; ty0 = tr.x >> 16; tx1 = tr.y & 0xffff; ty1 = tr.y >> 16;
         val = (MODE == PS_MODE_3D) ? t.rank[idx] : (uint32_t)gi;
-        const float4 r0 = __ldg(PS_REC(t, idx, 0)), r1 = __ldg(PS_REC(t, idx, 1));
-        gx = r0.x; gy = r0.y; thr = r0.z;
-        hA = r1.x; B = r1.y; hC = r1.z;
-        if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
-        float ex, ey;
-        ps_footprint_box(hA, B, hC, thr, ex, ey);
-        brect = ps_block_rect(gx, gy, ex, ey, half, g.W, g.H);
+        if (MASKS) {
+            const float4 r0 = __ldg(PS_REC(t, idx, 0)), r1 = __ldg(PS_REC(t, idx, 1));
+            gx = r0.x; gy = r0.y; thr = r0.z;
+            hA = r1.x; B = r1.y; hC = r1.z;
+            if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
+            float ex, ey;
+            ps_footprint_box(hA, B, hC, thr, ex, ey);
+            brect = ps_block_rect(gx, gy, ex, ey, half, g.W, g.H);
+        }
     }
     auto slot_word = [&](int tx, int ty) -> uint32_t {
-        const uint32_t m8 = EXACT ? (ps_block_mask8(gx, gy, hA, B, hC, thr, half, tx, ty) & ps_blocks_inside8(tx, ty, g.W, g.H))
-                                  : ps_block_mask8_rect(brect, tx, ty);
+        if (!MASKS) return val;
+        const uint32_t m8 = MASKS == 2 ? (ps_block_mask8(gx, gy, hA, B, hC, thr, half, tx, ty) & ps_blocks_inside8(tx, ty, g.W, g.H))
+                                       : ps_block_mask8_rect(brect, tx, ty);
         return val | (m8 << PS_SLOT_MASK_SHIFT);
     };
     const int32_t *off_v = offsets + (size_t)v * g.n_tiles;
@@ -406,23 +410,30 @@ __device__ __forceinline__ int block_exclusive_scan_256i(int v, int *s_warp)
     return pre + incl - v;
 }
 
-// One CTA per non-empty list: unique keys < N -> bitmap sort.
+// One CTA per non-empty list: unique keys < N -> bitmap sort.  With m8s != NULL the block masks packed into the slot
+// words travel along: a byte table indexed by key in shared memory, read back in sorted order -> m8s [M], so that the
+// block split streams (id, mask) pairs instead of gathering records.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_t *__restrict__ offsets,
-                  const int32_t *__restrict__ worklist, const uint32_t *__restrict__ slots, uint32_t *__restrict__ vals)
+                  const int32_t *__restrict__ worklist, const uint32_t *__restrict__ slots, uint32_t *__restrict__ vals,
+                  uint8_t *__restrict__ m8s, const int32_t *__restrict__ n_lists)
 {
-    extern __shared__ uint32_t s_bm[]; // [(N + 31) / 32]
+    extern __shared__ uint32_t s_bm[]; // [(N + 31) / 32] | bytes [N] (m8s)
     __shared__ int s_warp[8];
+    if ((int)blockIdx.x >= __ldg(n_lists)) return; // the grid may be an upper bound (sync-free small calls)
     const int lin = worklist[blockIdx.x];
     const int start = offsets[lin], end = offsets[lin + 1];
     const int view = lin / g.n_tiles;
     const int words = (g.N + 31) >> 5;
+    uint8_t *tab = reinterpret_cast<uint8_t *>(s_bm + words);
     for (int w = threadIdx.x; w < words; w += 256) s_bm[w] = 0u;
     __syncthreads();
     for (int i = start + threadIdx.x; i < end; i += 256) {
-        const uint32_t r = slots[i] & PS_SLOT_KEY_MASK;
+        const uint32_t sw = slots[i];
+        const uint32_t r = sw & PS_SLOT_KEY_MASK;
         atomicOr(&s_bm[r >> 5], 1u << (r & 31u));
+        if (m8s) tab[r] = (uint8_t)(sw >> PS_SLOT_MASK_SHIFT);
     }
     __syncthreads();
     const int wpt = (words + 255) / 256;
@@ -436,6 +447,7 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
         while (bits) {
             const uint32_t r = (uint32_t)(w << 5) + (uint32_t)(__ffs(bits) - 1);
             bits &= bits - 1;
+            if (m8s) m8s[out] = tab[r];
             vals[out++] = (MODE == PS_MODE_3D) ? r : vbase + r;
         }
     }
@@ -641,20 +653,19 @@ int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, long long *chunk
     return cudaGetLastError() == cudaSuccess ? (n_chunks > 0 ? 3 : 1) : -1;
 }
 
-int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s)
+int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, int masks, cudaStream_t s)
 {
     if (g.N == 0 || g.V == 0) return 0;
     dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
     const int use_smem = g.n_tiles <= PS_HIST_SMEM_TILES;
     const size_t dyn = use_smem ? (size_t)2 * g.n_tiles * sizeof(int) : 0;
-    static const bool exact = getenv("PS_EXACT_BLOCK_MASKS") != nullptr; // A/B switch for measurements
-#define PS_PART(MODE, EX)                                                                                                     \
+#define PS_PART(MODE, MK)                                                                                                     \
     do {                                                                                                                      \
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<MODE, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1; \
-        partition_kernel<MODE, EX><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);                  \
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(partition_kernel<MODE, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1; \
+        partition_kernel<MODE, MK><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, t, l.offsets, l.fill, l.slots, use_smem);                  \
     } while (0)
-    if (g.mode == PS_MODE_3D) { if (exact) PS_PART(PS_MODE_3D, true); else PS_PART(PS_MODE_3D, false); }
-    else { if (exact) PS_PART(PS_MODE_2D, true); else PS_PART(PS_MODE_2D, false); }
+    if (g.mode == PS_MODE_3D) { if (masks == 2) PS_PART(PS_MODE_3D, 2); else if (masks == 1) PS_PART(PS_MODE_3D, 1); else PS_PART(PS_MODE_3D, 0); }
+    else { if (masks == 2) PS_PART(PS_MODE_2D, 2); else if (masks == 1) PS_PART(PS_MODE_2D, 1); else PS_PART(PS_MODE_2D, 0); }
 #undef PS_PART
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -667,19 +678,22 @@ int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
+int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint8_t *m8s, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const size_t dyn = (size_t)((g.N + 31) / 32) * sizeof(uint32_t);
+    const size_t dyn = (size_t)((g.N + 31) / 32) * sizeof(uint32_t) + (m8s ? (size_t)g.N : 0);
     if (g.mode == PS_MODE_3D) {
         if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        sort_lists_kernel<PS_MODE_3D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals);
+        sort_lists_kernel<PS_MODE_3D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, m8s, l.n_lists);
     } else {
         if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        sort_lists_kernel<PS_MODE_2D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals);
+        sort_lists_kernel<PS_MODE_2D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, m8s, l.n_lists);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
+
+// the mask-byte table of sort_lists needs N bytes of shared memory beside the bitmap
+bool ps_mask_bytes_fit_smem(const PsGeometry &g) { return (size_t)((g.N + 31) / 32) * 4 + (size_t)g.N <= 200 * 1024; }
 
 // the fused sort + block split needs 9 (+1) shared-memory words per 32 Gaussians for its bitmaps
 static size_t split_map_bytes(const PsGeometry &g, bool keep) { return (size_t)((g.N + 31) / 32) * (SPLIT_MAPS + (keep ? 1 : 0)) * sizeof(uint32_t); }

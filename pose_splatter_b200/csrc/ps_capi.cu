@@ -365,6 +365,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
     uint32_t *rank_scratch = nullptr;
     long long *scan_scratch = nullptr;
     int32_t *csr_cursor = nullptr;
+    uint8_t *mask_bytes = nullptr;
     // everything below jumps to `out` on error so scratch is always returned to the pool
 #define PS_TRY_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); goto out; } } while (0)
 #define PS_TRY_LAUNCH(call) do { int n_ = (call); if (n_ < 0) { rc = fail(3, "kernel launch failed in %s: %s", #call, cudaGetErrorString(cudaGetLastError())); goto out; } ctx->launches += n_; } while (0)
@@ -374,15 +375,28 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
         const size_t npix = (size_t)g.V * g.H * g.W;
         if (T > 0x7ffffff0ULL) { rc = fail(1, "ps_forward: %zu (view, tile) lists exceed 2^31", T); goto out; }
         if (g.N > (1 << 20)) { rc = fail(1, "ps_forward: at most 2^20 Gaussians per frame (got %d)", g.N); goto out; }
-        static const bool no_split = getenv("PS_NO_SPLIT") != nullptr; // A/B switch for measurements
-        const bool split = !no_split && ps_split_fits_smem(g); // sort + block split in one kernel (else: list sort, then record gathers)
+        // How the eight block lists of a tile are built (A/B switch PS_BIN_MODE for measurements):
+        //   "bytes"  partition computes block-rectangle masks, the list sort carries them along as bytes, the split streams
+        //   "split"  partition computes masks, one kernel sorts and splits from shared-memory bitmaps
+        //   "gather" plain keys; the split gathers every record and tests it exactly
+        // Measured at c2 / c3 (partition + sort + split + both rasterizers, ms): gather 10.69 / 17.29, bytes 10.80 / 17.64,
+        // split 10.94 / 18.72 -- the mask variants build the lists faster (2.22 vs 2.44 ms at c2) but their cheap masks are a
+        // superset of the exact test and the extra block-list entries cost the rasterizers more than that; exact masks in the
+        // partition kernel cost 1.1 ms there.
+        static const char *bin_env = getenv("PS_BIN_MODE");
+        static const int mask_env = getenv("PS_EXACT_BLOCK_MASKS") ? 2 : 1;
+        int bin_mode = 0; // 0 gather (default: fastest end to end, measured), 1 bytes, 2 split
+        if (bin_env) bin_mode = !strcmp(bin_env, "gather") ? 0 : !strcmp(bin_env, "split") ? 2 : 1;
+        if (bin_mode == 2 && !ps_split_fits_smem(g)) bin_mode = 1;
+        if (bin_mode == 1 && !ps_mask_bytes_fit_smem(g)) bin_mode = 0;
+        const bool split = bin_mode == 2;
         // Small calls (the reference's own call shape: one view per render()) never wait for the host: the list arrays
         // are sized for the worst case M = V * N * n_tiles and the per-list kernels are launched over all V * n_tiles
         // lists, reading the exact counts on the device.  Large batches size everything exactly from the mailbox
         // (one stream synchronisation): the worst case would not fit, and empty CTAs would cost more than the wait.
         static const bool force_sync = getenv("PS_FORCE_SYNC") != nullptr; // A/B switch for measurements
         const size_t worst = VN * (size_t)g.n_tiles;
-        const bool sync_free = !keep && !force_sync && split && VN > 0 && T <= 16384 && worst <= ((size_t)1 << 31) / 40;
+        const bool sync_free = !keep && !force_sync && VN > 0 && T <= 16384 && worst <= ((size_t)1 << 31) / 40;
         sv->M = 0;
         sv->n_work = 0;
         sv->resolved = true;
@@ -436,16 +450,17 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             PS_TRY_CUDA(dev_alloc(&sv->l.bcount, 8 * capW, s));
             if (keep) PS_TRY_CUDA(dev_alloc(&sv->l.bpos, 8 * capM, s));
             PS_TRY_CUDA(cudaMemsetAsync(sv->l.fill, 0, T * sizeof(int32_t), s));
-            { StageTimer tm(ctx, PS_STAGE_PARTITION, s); PS_TRY_LAUNCH(ps_launch_partition(g, sv->t, sv->l, s)); }
+            { StageTimer tm(ctx, PS_STAGE_PARTITION, s); PS_TRY_LAUNCH(ps_launch_partition(g, sv->t, sv->l, bin_mode ? mask_env : 0, s)); }
             if (split) {
                 StageTimer tm(ctx, PS_STAGE_SORT, s);
                 PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
                 PS_TRY_LAUNCH(ps_launch_sort_split(g, sv->t, sv->l, sv->cap_work, s));
             } else {
+                if (bin_mode == 1) PS_TRY_CUDA(dev_alloc(&mask_bytes, capM, s));
                 { StageTimer tm(ctx, PS_STAGE_SORT, s);
                   PS_TRY_LAUNCH(ps_launch_build_worklist(g, sv->l, s));
-                  PS_TRY_LAUNCH(ps_launch_sort_lists(g, sv->t, sv->l, sv->n_work, s)); }
-                { StageTimer tm(ctx, PS_STAGE_BLOCKS, s); PS_TRY_LAUNCH(ps_launch_block_lists(g, sv->t, sv->l, sv->n_work, s)); }
+                  PS_TRY_LAUNCH(ps_launch_sort_lists(g, sv->t, sv->l, sv->cap_work, mask_bytes, s)); }
+                { StageTimer tm(ctx, PS_STAGE_BLOCKS, s); PS_TRY_LAUNCH(ps_launch_block_lists(g, sv->t, sv->l, sv->cap_work, mask_bytes, s)); }
             }
             if (keep) {
                 PS_TRY_CUDA(dev_alloc(&sv->keys, capM, s));
@@ -468,6 +483,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
 out:
     dev_free(rank_scratch, s);
     dev_free(scan_scratch, s);
+    dev_free(mask_bytes, s);
     dev_free(sv->l.fill, s); dev_free(sv->l.slots, s);
     dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
     if (rc == 0 && !keep) { dev_free(sv->t.tile_rect, s); dev_free(sv->t.depth, s); dev_free(sv->l.vals, s); }

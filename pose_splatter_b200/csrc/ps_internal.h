@@ -69,9 +69,12 @@ int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratc
 // exclusive scan of the T counts in place (offsets[T] = M), size classes; mailbox[0] = M, mailbox[1] = non-empty lists
 size_t ps_scan_scratch_elems(const PsGeometry &g); // int64 elements of scratch the scan needs
 int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, long long *chunk_scratch, int64_t *mailbox, cudaStream_t s);
-int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, cudaStream_t s);
+// masks: 0 = plain keys, 1 = block-rectangle masks, 2 = exact block masks packed above the key (PS_SLOT_MASK_SHIFT)
+int ps_launch_partition(const PsGeometry &g, const PsTable &t, const PsLists &l, int masks, cudaStream_t s);
 int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t s);
-int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
+// m8s [M] or NULL: the slot words' block masks in sorted order (needs ps_mask_bytes_fit_smem)
+bool ps_mask_bytes_fit_smem(const PsGeometry &g);
+int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint8_t *m8s, cudaStream_t s);
 // sort + split into the eight block lists in one kernel (no record gathers); needs ps_split_fits_smem(g)
 bool ps_split_fits_smem(const PsGeometry &g);
 int ps_launch_sort_split(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
@@ -81,7 +84,8 @@ int ps_launch_debug_keys(const PsGeometry &g, const PsTable &t, const PsLists &l
 // rgb / alpha / rgba8 may each be NULL (rgba8: uint8 RGBA, one uint32 per pixel, quantised like the reference's writer)
 int ps_launch_fill_empty(const PsGeometry &g, const int32_t *offsets, const float *background, float *rgb, float *alpha,
                          int32_t *n_contrib, int32_t *last, uint32_t *rgba8, cudaStream_t s);
-int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s);
+// m8s != NULL: stream (id, mask byte) pairs instead of gathering records
+int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const uint8_t *m8s, cudaStream_t s);
 // last: tile-list position + 1 of the last contributor (tap); blast: the same as an index into the block list (backward)
 int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          float *rgb, float *alpha, int32_t *n_contrib, int32_t *last, int32_t *blast, float *t_pen,

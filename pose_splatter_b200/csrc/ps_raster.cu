@@ -800,12 +800,15 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 }
 
 // Split every non-empty tile list, in order, into the lists of its eight 8x4 pixel blocks.
+// m8s != NULL: the block masks were computed by the partition kernel and sorted along (one byte per list entry):
+// a pure streaming split of (id, mask) pairs, no record is touched.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                    const int32_t *__restrict__ worklist, uint32_t *__restrict__ blist, uint32_t *__restrict__ bpos,
-                   int32_t *__restrict__ bcount)
+                   int32_t *__restrict__ bcount, const uint8_t *__restrict__ m8s, const int32_t *__restrict__ n_lists)
 {
+    if ((int)blockIdx.x >= __ldg(n_lists)) return; // the grid may be an upper bound (sync-free small calls)
     __shared__ int s_cnt[8][8]; // [warp][block]
     __shared__ int s_pre[8][8]; // [warp][block] output cursor of the round
     __shared__ int s_run[8], s_tot[8];
@@ -825,28 +828,33 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
     // software pipeline: ids two rounds ahead, records one round ahead
     const int tid = threadIdx.x;
+    const uint8_t *mlist = m8s ? m8s + start : nullptr;
     uint32_t id_n = (tid < len) ? __ldg(list + tid) : 0u;
     uint32_t id_nn = (256 + tid < len) ? __ldg(list + 256 + tid) : 0u;
-    float4 r0_n = __ldg(PS_REC(t, id_n, 0));
-    float4 r1_n = __ldg(PS_REC(t, id_n, 1));
+    uint32_t mk_n = (mlist && tid < len) ? mlist[tid] : 0u;
+    float4 r0_n = make_float4(0.f, 0.f, 0.f, 0.f), r1_n = r0_n;
+    if (!mlist) { r0_n = __ldg(PS_REC(t, id_n, 0)); r1_n = __ldg(PS_REC(t, id_n, 1)); }
     __syncthreads();
     for (int first = 0; first < len; first += 256) {
         const int j = first + tid;
         const float4 r0 = r0_n, r1 = r1_n;
         const uint32_t id_cur = id_n;
+        uint32_t m8 = mk_n;
         {
             const uint32_t id_next = id_nn;
             id_n = id_next;
             id_nn = (first + 512 + tid < len) ? __ldg(list + first + 512 + tid) : 0u;
-            r0_n = __ldg(PS_REC(t, id_next, 0));
-            r1_n = __ldg(PS_REC(t, id_next, 1));
+            if (mlist) mk_n = (first + 256 + tid < len) ? mlist[first + 256 + tid] : 0u;
+            else { r0_n = __ldg(PS_REC(t, id_next, 0)); r1_n = __ldg(PS_REC(t, id_next, 1)); }
         }
-        uint32_t m8 = 0;
-        if (j < len) {
-            float hA = r1.x, B = r1.y, hC = r1.z;
-            if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
-            m8 = ps_block_mask8(r0.x, r0.y, hA, B, hC, r0.z, (MODE == PS_MODE_3D) ? 0.5f : 0.0f, tx, ty);
-            m8 &= inside8;
+        if (!mlist) {
+            m8 = 0;
+            if (j < len) {
+                float hA = r1.x, B = r1.y, hC = r1.z;
+                if (MODE == PS_MODE_2D) ps_conic2d(r1, hA, B, hC);
+                m8 = ps_block_mask8(r0.x, r0.y, hA, B, hC, r0.z, (MODE == PS_MODE_3D) ? 0.5f : 0.0f, tx, ty);
+                m8 &= inside8;
+            }
         }
         uint32_t bal[8];
 #pragma unroll
@@ -882,11 +890,11 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 
 } // namespace
 
-int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, cudaStream_t s)
+int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const uint8_t *m8s, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    if (g.mode == PS_MODE_3D) block_lists_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount);
-    else block_lists_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount);
+    if (g.mode == PS_MODE_3D) block_lists_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount, m8s, l.n_lists);
+    else block_lists_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount, m8s, l.n_lists);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
