@@ -164,7 +164,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const uint32_t *__restrict__ bpos,
                   const int32_t *__restrict__ bcount, uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats,
-                  const int32_t *__restrict__ n_lists)
+                  const int32_t *__restrict__ n_lists, uint32_t *__restrict__ cmask)
 {
     __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
     // the grid may be sized from an upper bound of the number of non-empty lists (sync-free small calls)
@@ -214,6 +214,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         uint32_t mask = cull_chunk<MODE>(q, st, lane, ci * CH + lane < len, c, __ballot_sync(FULL, !done));
         if (STATS) { st_staged += 1; if (lane == 0) st_walk += __popc(mask); st_eval += done ? 0 : __popc(mask); }
         const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        uint32_t cm_mine = 0; // lane e: the pixels entry e of this chunk contributes to (saved for the backward)
         // survivors two at a time: the two alpha evaluations are independent chains, the compositing is ordered
         while (mask) {
             const int ea = __ffs(mask) - 1;
@@ -222,6 +223,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
             const int eb = two ? __ffs(mask) - 1 : ea;
             mask &= mask - 1;
             const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
+            bool conta = false, contb = false;
             if (MODE == PS_MODE_3D) {
                 float dx, dy;
                 const float thra = r0a.z, thrb = r0b.z;
@@ -241,7 +243,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                         const float4 r2 = q2[ea];
                         const float vis = psm_mul(aa, T);
                         cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1;
+                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1; conta = true;
                     }
                 }
                 if (candb && !done && ab >= PS_ALPHA_MIN) {
@@ -252,7 +254,7 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                         const float4 r2 = q2[eb];
                         const float vis = psm_mul(ab, T);
                         cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1;
+                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1; contb = true;
                     }
                 }
             } else {
@@ -269,17 +271,23 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                 if (ina) {
                     const float contrib = psm_mul(gva, T);
                     cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
-                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1;
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1; conta = true;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
                 if (inb && !done) {
                     const float contrib = psm_mul(gvb, T);
                     cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
-                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1;
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1; contb = true;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
             }
+            if (cmask) { // the walk is warp-uniform here: both ballots are taken by all lanes
+                const uint32_t cma = __ballot_sync(FULL, conta), cmb = __ballot_sync(FULL, contb);
+                cm_mine = (lane == ea) ? cma : cm_mine;
+                cm_mine = (two && lane == eb) ? cmb : cm_mine;
+            }
         }
+        if (cmask && first + lane < len) cmask[(c.bl - blist) + first + lane] = cm_mine;
         if (__all_sync(FULL, done)) break;
         __syncwarp(); // every lane is finished with stage st before chunk ci + 3 is copied into it
     }
@@ -368,7 +376,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                    int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
                    float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const uint32_t *__restrict__ bpos,
                    const int32_t *__restrict__ bcount, uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats,
-                  const int32_t *__restrict__ n_lists)
+                  const int32_t *__restrict__ n_lists, uint32_t *__restrict__ cmask)
 {
     __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
     // the grid may be sized from an upper bound of the number of non-empty lists (sync-free small calls)
@@ -433,6 +441,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             if (lane == 0) st_walk += __popc(reach);
             st_eval += __popc(pm);
         }
+        uint32_t cmp = 0; // this pixel's contributing entries of the chunk (saved, transposed, for the backward)
         while (pm && !done) {
             // two candidates in flight: independent alpha chains, compositing in order
             const int ea = __ffs(pm) - 1;
@@ -458,7 +467,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                         const float4 r2 = q2[ea];
                         const float vis = psm_mul(aa, T);
                         cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1;
+                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1; cmp |= 1u << ea;
                     }
                 }
                 if (candb && !done && ab >= PS_ALPHA_MIN) {
@@ -469,7 +478,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                         const float4 r2 = q2[eb];
                         const float vis = psm_mul(ab, T);
                         cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
-                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1;
+                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1; cmp |= 1u << eb;
                     }
                 }
             } else {
@@ -485,19 +494,23 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                     const float4 r2a = q2[ea];
                     const float contrib = psm_mul(gva, T);
                     cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
-                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1;
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1; cmp |= 1u << ea;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
                 if (inb && !done) {
                     const float4 r2b = q2[eb];
                     const float contrib = psm_mul(gvb, T);
                     cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
-                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1;
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1; cmp |= 1u << eb;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
             }
         }
         __syncwarp(); // lanes reconverge; every lane is finished with stage st before chunk ci + 3 is copied into it
+        if (cmask) { // (pixel, entry) -> (entry, pixel): lane e stores the pixels its entry contributes to
+            const uint32_t cme = transpose32(cmp, lane);
+            if (first + lane < len) cmask[(c.bl - blist) + first + lane] = cme;
+        }
         if (__all_sync(FULL, done)) break;
     }
     cp_async_wait_group<0>();
@@ -799,6 +812,207 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     }
 }
 
+// ---- backward v6: contributor masks from the forward, per-pixel chain, per-entry moments ------------------------------
+// The forward leaves, per block-list entry, the 32-bit mask of the block's pixels it contributed to (cmask).  The replay
+// therefore touches contributing (pixel, entry) pairs only -- no culling, no candidate tests, no ballots:
+//   A (lane = pixel)  the chunk's 32 entry masks are transposed across the warp (five shuffles); every pixel lane walks
+//                     ITS OWN contributors in reverse list order, recomputes alpha with the arithmetic of the contract and
+//                     advances the two sequential per-pixel quantities (T by rcp.approx from the saved "T before the last
+//                     contributor", S = sum behind); it leaves (alpha T, dL/dsigma) [3D] / (g T, dL/dq) [2D] per pair in a
+//                     32 x 32 table in shared memory
+//   B (lane = entry)  every entry lane walks the set bits of its own mask: 3 colour FMAs + six moments per pair in
+//                     registers; the nine gradient sums are linear in them, formed once per entry, transposed through
+//                     shared memory so that one entry's nine floats leave with adjacent red.global.add
+// Persistent warps pulling (tile, block) tasks off one counter, records streamed through the cp.async ring as before.
+constexpr int TAB_STRIDE = 33; // float2 per table row (32 pixels + 1 pad)
+
+template <int MODE, int BW, bool STATS>
+__global__ void __launch_bounds__(BW * 32)
+raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, const int32_t *__restrict__ worklist,
+                   const float *__restrict__ background, const int32_t *__restrict__ last, const float *__restrict__ t_pen,
+                   const float *__restrict__ d_rgb, const float *__restrict__ d_alpha, const uint32_t *__restrict__ blist,
+                   const uint32_t *__restrict__ cmask, const int32_t *__restrict__ bcount, float *__restrict__ acc,
+                   const int32_t *__restrict__ n_lists, unsigned *__restrict__ next_task, unsigned long long *__restrict__ stats)
+{
+    __shared__ float4 s_a[BW][NS][CH], s_b[BW][NS][CH], s_c[BW][NS][CH];
+    __shared__ float2 s_tab[BW][32 * TAB_STRIDE];   // phase A -> B pair table [entry][pixel]; reused as the 32 x 9 output transpose
+    __shared__ float4 s_w[BW][32];                  // d_rgb of the block's pixels
+    __shared__ uint32_t s_id[BW][32];               // accumulator rows (view * N + Gaussian) of the chunk's entries
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long st_pairs = 0, st_walk = 0, st_staged = 0;
+    const unsigned n_tasks = 8u * (unsigned)__ldg(n_lists);
+    const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
+    float2 *tab = s_tab[wid];
+    float *outt = reinterpret_cast<float *>(s_tab[wid]);
+    for (;;) {
+    unsigned task = 0;
+    if (lane == 0) task = atomicAdd(next_task, 1u);
+    task = __shfl_sync(FULL, task, 0);
+    if (task >= n_tasks) break;
+    const BlockCtx c = block_ctx_task(g, offsets, worklist, blist, nullptr, bcount, task);
+    int my_last = 0;
+    float Tcur = 1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, S = 0.0f;
+    if (c.inside) {
+        const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
+        my_last = last[p];
+        if (my_last > 0) {
+            Tcur = t_pen[p];
+            w0 = d_rgb[3 * p]; w1 = d_rgb[3 * p + 1]; w2 = d_rgb[3 * p + 2];
+            S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
+        }
+    }
+    int wmax = my_last;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
+    if (wmax <= 0) continue;
+    __syncwarp();
+    s_w[wid][lane] = make_float4(w0, w1, w2, 0.0f);
+    const int len = wmax;
+    const int nchunks = (len + CH - 1) / CH;
+    const uint32_t *cml = cmask + (c.bl - blist);
+    // reverse step r handles chunk nchunks - 1 - r; its ring stage is r % NS; ids and masks run ahead in registers
+    auto issue = [&](int r, uint32_t id) {
+        const int cj = nchunks - 1 - r;
+        if (cj >= 0 && cj * CH + lane < len) {
+            const int st = r % NS;
+            const float4 *src = PS_REC(t, id, 0);
+            cp_async16(&q.a[st][lane], src);
+            cp_async16(&q.b[st][lane], src + 1);
+            cp_async16(&q.c[st][lane], src + 2);
+        }
+        cp_async_commit();
+    };
+    auto fetch = [&](int r, uint32_t &id, uint32_t &cm) {
+        const int cj = nchunks - 1 - r;
+        const bool ok = cj >= 0 && cj * CH + lane < len;
+        id = ok ? __ldg(c.bl + cj * CH + lane) : 0u;
+        cm = ok ? __ldg(cml + cj * CH + lane) : 0u;
+    };
+    uint32_t id0, cm0, id1, cm1, id2, cm2, id3, cm3; // steps r, r + 1, r + 2, r + 3
+    fetch(0, id0, cm0); fetch(1, id1, cm1); fetch(2, id2, cm2); fetch(3, id3, cm3);
+    issue(0, id0);
+    issue(1, id1);
+    const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
+    const float pxf = (float)c.px + half, pyf = (float)c.py + half;
+    const float bxf = (float)c.bx + half, byf = (float)c.by + half;
+    bool first_c = true; // the next contributor met is this pixel's last one: its T is the saved t_pen itself
+
+    for (int r = 0; r < nchunks; ++r) {
+        issue(r + 2, id2);
+        const uint32_t id_c = id0, cme = cm0;
+        id0 = id1; cm0 = cm1; id1 = id2; cm1 = cm2; id2 = id3; cm2 = cm3;
+        fetch(r + 4, id3, cm3);
+        cp_async_wait_group<2>();
+        __syncwarp();
+        const int st = r % NS;
+        if (STATS) st_staged += CH;
+        const uint32_t nz = __ballot_sync(FULL, cme != 0u);
+        if (nz == 0u) continue; // no pixel of the block composited any entry of this chunk
+        if (STATS && lane == 0) st_walk += __popc(nz);
+        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        s_id[wid][lane] = id_c;
+        // ---- phase A: lane = pixel
+        uint32_t pm = transpose32(cme, lane);
+        if (STATS) st_pairs += __popc(pm);
+        while (pm) {
+            const int e = 31 - __clz(pm);
+            pm &= ~(1u << e);
+            const float4 r0 = q0[e], r1 = q1[e], r2 = q2[e];
+            float gv, pb_scale; // alpha (3D) / g (2D); factor of -v in dL/dsigma resp. dL/dq
+            if (MODE == PS_MODE_3D) {
+                float dx, dy;
+                const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
+                const float oe = psm_mul(r0.w, psm_exp2_inrange(psm_mul(-sg, 0x1.715476p+0f)));
+                gv = fminf(PS_ALPHA_MAX, oe);
+                pb_scale = (oe <= PS_ALPHA_MAX) ? oe : 0.0f;
+            } else {
+                float dxr, dyr;
+                const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
+                gv = psm_mul(r0.w, psm_exp2_inrange(psm_mul(-qv, 0x1.715476p+0f)));
+                pb_scale = gv;
+            }
+            const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
+            const float Tb = first_c ? Tcur : Tcur * rcp_approx(1.0f - gv); // 1 - g >= 1e-3 (3D) / > 0 for contributors
+            first_c = false;
+            const float v = Tb * (cw - S); // dL/dalpha (3D) / dL/dg (2D)
+            tab[e * TAB_STRIDE + lane] = make_float2(gv * Tb, -pb_scale * v);
+            Tcur = Tb;
+            S = S + gv * (cw - S);
+        }
+        __syncwarp(); // the pair table is complete
+        // ---- phase B: lane = entry
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, ms = 0.0f, mx = 0.0f, my = 0.0f, mxx = 0.0f, mxy = 0.0f, myy = 0.0f;
+        const float4 e0 = q0[lane], e1 = q1[lane];
+        {
+            uint32_t m = cme;
+            const float sgx = e0.x - bxf, sgy = e0.y - byf; // mean relative to the block's first pixel centre
+            const float2 *prow = tab + lane * TAB_STRIDE;
+            const float4 *wrow = s_w[wid];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const float2 pr = prow[b];
+                const float4 w = wrow[b];
+                // small integers -> float through the 2^23 mantissa trick (FP32 pipe instead of the conversion unit)
+                const float fx = __uint_as_float(0x4b000000u | (uint32_t)(b & 7)) - 8388608.0f;
+                const float fy = __uint_as_float(0x4b000000u | (uint32_t)(b >> 3)) - 8388608.0f;
+                a0 = fmaf(pr.x, w.x, a0); a1 = fmaf(pr.x, w.y, a1); a2 = fmaf(pr.x, w.z, a2);
+                float ex, ey;
+                if (MODE == PS_MODE_3D) {
+                    ex = sgx - fx; ey = sgy - fy;                 // mean - pixel centre
+                } else {
+                    const float dx = -(sgx - fx), dy = -(sgy - fy); // pixel - mean, rotated into the splat's axes
+                    ex = fmaf(e1.y, dy, e1.x * dx);
+                    ey = fmaf(e1.x, dy, -e1.y * dx);
+                }
+                const float tx = pr.y * ex, ty = pr.y * ey;
+                ms += pr.y; mx += tx; my += ty;
+                mxx = fmaf(tx, ex, mxx); mxy = fmaf(tx, ey, mxy); myy = fmaf(ty, ey, myy);
+            }
+        }
+        float v3, v4, v5, v6, v7, v8;
+        if (MODE == PS_MODE_3D) {
+            v3 = 0.5f * mxx; v4 = mxy; v5 = 0.5f * myy;
+            v6 = 2.0f * e1.x * mx + e1.y * my;
+            v7 = e1.y * mx + 2.0f * e1.z * my;
+            v8 = -ms * rcp_approx(e0.w); // sum of exp(-sigma) * v_alpha over the unclamped pairs = -(sum v_sigma) / o
+        } else {
+            v3 = 2.0f * e1.z * mx; v4 = 2.0f * e1.w * my;
+            v5 = 2.0f * (e1.z - e1.w) * mxy;
+            v6 = mxx; v7 = myy; v8 = ms;
+        }
+        __syncwarp(); // every lane has read its pairs: the table becomes the output transpose
+        {
+            float *o = outt + lane * 9;
+            o[0] = a0; o[1] = a1; o[2] = a2; o[3] = v3; o[4] = v4; o[5] = v5; o[6] = v6; o[7] = v7; o[8] = v8;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int f = i * 32 + lane;
+            const int en = f / 9;
+            if ((nz >> en) & 1u) {
+                const float val = outt[f];
+                if (val != 0.0f) atomicAdd(acc + (size_t)s_id[wid][en] * PS_ACC_STRIDE + (f - en * 9), val);
+            }
+        }
+        __syncwarp(); // before the next chunk's phase A writes the table / s_id again; ring stage st is free as well
+    }
+    cp_async_wait_group<0>();
+    __syncwarp();
+    } // task loop
+    if (STATS) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) st_pairs += __shfl_xor_sync(FULL, st_pairs, d);
+        if (lane == 0) {
+            atomicAdd(stats + 4, st_pairs); // every pair replayed is a contributing pair
+            atomicAdd(stats + 5, st_pairs);
+            atomicAdd(stats + 6, st_walk);
+            atomicAdd(stats + 7, st_staged);
+        }
+    }
+}
+
 // Split every non-empty tile list, in order, into the lists of its eight 8x4 pixel blocks.
 // m8s != NULL: the block masks were computed by the partition kernel and sorted along (one byte per list entry):
 // a pure streaming split of (id, mask) pairs, no record is touched.
@@ -908,7 +1122,7 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
     // all-lanes walk of v4 is faster (5.25 vs 5.44 ms at c3).  With `stats` the SAME kernel runs with its pair
     // counters compiled in (bench.py's roofline numerator comes from the kernel it times).
     static const bool force_v4 = getenv("PS_FWD_V4") != nullptr; // A/B switch for measurements
-#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bpos, l.bcount, rgba8, stats, l.n_lists)
+#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bpos, l.bcount, rgba8, stats, l.n_lists, l.cmask)
     if (g.mode == PS_MODE_3D && !force_v4) {
         if (stats) PS_FWD(raster_fwd6_kernel, PS_MODE_3D, true); else PS_FWD(raster_fwd6_kernel, PS_MODE_3D, false);
     } else if (g.mode == PS_MODE_3D) {
@@ -948,40 +1162,54 @@ int ps_launch_fp32_probe(float *sink, int iters, cudaStream_t s)
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+namespace {
+// persistent grid of a backward kernel on the current device: resident CTAs per SM x SMs (full shared-memory carve-out)
+template <typename K>
+unsigned persistent_ctas(K kernel, int slot)
+{
+    constexpr int MAX_DEV = 64;
+    static int cached[MAX_DEV][8] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev < MAX_DEV ? dev : MAX_DEV - 1;
+    if (!cached[di][slot]) {
+        int per = 0, n_sm = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, RT_THREADS, 0);
+        cached[di][slot] = n_sm * (per > 0 ? per : 1);
+    }
+    return (unsigned)cached[di][slot];
+}
+} // namespace
+
 int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const float *background,
                          const int32_t *last, const float *t_pen, const float *d_rgb, const float *d_alpha, float *acc,
                          unsigned *next_task, unsigned long long *stats, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    // per device (a process may drive several): full shared-memory carve-out (10 CTAs x 21.6 KB per SM) and the
-    // persistent grid = resident CTAs per SM x SMs
-    constexpr int MAX_DEV = 64;
-    static int ctas_per_sm[MAX_DEV][2] = {}, sm_count[MAX_DEV] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int di = dev < MAX_DEV ? dev : MAX_DEV - 1;
+    const unsigned n_tasks = (unsigned)n_work * 8u; // n_work may be an upper bound: the kernels read the exact count
+    const unsigned want = (n_tasks + WPC - 1) / WPC;
+    static const bool use_v5 = getenv("PS_BWD_V5") != nullptr; // A/B switch for measurements
     const int mi = g.mode == PS_MODE_3D ? 0 : 1;
-    if (!ctas_per_sm[di][mi]) {
-        int per = 0;
-        cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev);
-        if (mi == 0) {
-            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_3D, WPC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_3D, WPC, false>, RT_THREADS, 0);
-        } else {
-            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(raster_bwd2_kernel<PS_MODE_2D, WPC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, raster_bwd2_kernel<PS_MODE_2D, WPC, false>, RT_THREADS, 0);
-        }
-        ctas_per_sm[di][mi] = per > 0 ? per : 1;
+    if (l.cmask && !use_v5) { // v6: replay of the contributing pairs the forward recorded
+#define PS_BWD3(MODE, ST, SLOT)                                                                                              \
+        do {                                                                                                                 \
+            const unsigned cap = persistent_ctas(raster_bwd3_kernel<MODE, WPC, ST>, SLOT);                                   \
+            raster_bwd3_kernel<MODE, WPC, ST><<<want < cap ? want : cap, RT_THREADS, 0, s>>>(g, t, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.cmask, l.bcount, acc, l.n_lists, next_task, stats); \
+        } while (0)
+        if (mi == 0) { if (stats) PS_BWD3(PS_MODE_3D, true, 4); else PS_BWD3(PS_MODE_3D, false, 5); }
+        else { if (stats) PS_BWD3(PS_MODE_2D, true, 6); else PS_BWD3(PS_MODE_2D, false, 7); }
+#undef PS_BWD3
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    const int n_sm = sm_count[di];
-    const unsigned n_tasks = (unsigned)n_work * 8u; // n_work may be an upper bound: the kernel reads the exact count
-    const unsigned want = (n_tasks + WPC - 1) / WPC, cap = (unsigned)(n_sm * ctas_per_sm[di][mi]);
-    const unsigned pgrid = want < cap ? want : cap;
-#define PS_BWD(MODE, ST) raster_bwd2_kernel<MODE, WPC, ST><<<pgrid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, l.n_lists, next_task, stats)
-    if (g.mode == PS_MODE_3D) { if (stats) PS_BWD(PS_MODE_3D, true); else PS_BWD(PS_MODE_3D, false); }
-    else { if (stats) PS_BWD(PS_MODE_2D, true); else PS_BWD(PS_MODE_2D, false); }
+#define PS_BWD(MODE, ST, SLOT)                                                                                               \
+    do {                                                                                                                     \
+        const unsigned cap = persistent_ctas(raster_bwd2_kernel<MODE, WPC, ST>, SLOT);                                       \
+        raster_bwd2_kernel<MODE, WPC, ST><<<want < cap ? want : cap, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.bcount, acc, l.n_lists, next_task, stats); \
+    } while (0)
+    if (mi == 0) { if (stats) PS_BWD(PS_MODE_3D, true, 0); else PS_BWD(PS_MODE_3D, false, 1); }
+    else { if (stats) PS_BWD(PS_MODE_2D, true, 2); else PS_BWD(PS_MODE_2D, false, 3); }
 #undef PS_BWD
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
