@@ -54,7 +54,8 @@ def parse():
     return ap.parse_args()
 
 
-FRAMES_DEFAULT = {"c1": 64, "c2": 256, "c3": 32, "c5_3d": 16, "c5_2d": 4}
+FRAMES_DEFAULT = {"c1": 64, "c2": 256, "c3": 32, "c4": 256, "c5_3d": 16, "c5_2d": 4}
+C4_SEQUENCE_FRAMES = 3600  # BASELINE.json configs[3]: full-sequence inference render, 3600 frames x 6 cameras
 
 
 # ------------------------------------------------------------------------------------------
@@ -124,6 +125,91 @@ def cpu_views_per_second(workload, n_views, threads, n_override=0):
     return n_views / dt, dt
 
 
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def reference_2d_cpu(wl, reps=3):
+    """Baseline A of BASELINE.md section 3: the reference's OWN GaussianRenderer2D (baseline/_ref, byte-identical copy of
+    src/gaussian_renderer.py made by __graft_entry__.build) on the box's host cores, built like the a6000_2d template
+    (sigma_cutoff=3.0, kernel_size=5, batch_size=5), on camera 0 of the same synthetic workload.  Its autograd memory is
+    ~N*H*W*40 B, so fwd+bwd is timed at N = 1024 (= min_n, src/model.py:32) and forward-only (no_grad) at N = 4096; the
+    dense cost is exactly proportional to N (src/gaussian_renderer.py:379-425), which is what the labelled
+    extrapolation to the workload's N uses."""
+    import importlib.util
+    import torch
+    from pose_splatter_b200 import synth
+    path = ROOT / "baseline" / "_ref" / "reference_src" / "gaussian_renderer.py"
+    if not path.exists():
+        return {"unavailable": "baseline/_ref is missing: run __graft_entry__.build() where /root/reference exists"}
+    spec = importlib.util.spec_from_file_location("reference_gaussian_renderer", str(path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.WORKLOADS[wl]
+    W, H, N = cfg["width"], cfg["height"], cfg["n"]
+    d = synth.make_views(wl, 1, 6, seed=99)
+    params = d["params"][0]
+    r = mod.create_renderer("2d", W, H, device="cpu", sigma_cutoff=3.0, kernel_size=5, batch_size=5)
+    r.set_background_color(torch.ones(3))
+    w_rgb, w_a = synth.cotangents(1, H, W, seed=5)
+
+    def fwd_bwd(n):
+        p = params[:n].clone().requires_grad_(True)
+        rgb, alpha = r.render(p, None, None)
+        ((rgb * w_rgb[0]).sum() + (alpha * w_a[0]).sum()).backward()
+
+    def fwd(n):
+        with torch.no_grad():
+            r.render(params[:n], None, None)
+
+    def median_seconds(fn, n):
+        fn(n)  # warm-up
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn(n)
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+
+    n_bwd, n_fwd = min(1024, N), min(4096, N)
+    t_bwd, t_fwd = median_seconds(fwd_bwd, n_bwd), median_seconds(fwd, n_fwd)
+    return {"kind": "reference", "what": "reference GaussianRenderer2D (pure PyTorch, device='cpu'), one view per call",
+            "cores": cores, "torch_threads": torch.get_num_threads(), "cpu": cpu_model_name(),
+            "workload": f"{wl}: {W}x{H}, camera 0 of the synthetic workload, 1 warm-up + {reps} repetitions, median",
+            "fwd_bwd": {"n": n_bwd, "seconds": t_bwd, "views_per_s": 1.0 / t_bwd,
+                        "extrapolated_views_per_s_at_workload_n": (1.0 / t_bwd) * n_bwd / N, "workload_n": N,
+                        "extrapolation": "linear in N (dense N*H*W cost); not a measurement"},
+            "fwd_only": {"n": n_fwd, "seconds": t_fwd, "views_per_s": 1.0 / t_fwd,
+                         "extrapolated_views_per_s_at_workload_n": (1.0 / t_fwd) * n_fwd / N, "workload_n": N,
+                         "extrapolation": "linear in N (dense N*H*W cost); not a measurement" if n_fwd != N else "none: measured at the workload's N"}}
+
+
+def gsplat_comparator():
+    """Extra comparator of north_star: the reference's gsplat path on one B200.  gsplat is not vendored in the reference
+    and not installed in this image (no network); the repo-root gsplat/ package is this repo's own shim, not gsplat."""
+    import importlib.util
+    saved_path, saved_mod = list(sys.path), {k: v for k, v in sys.modules.items() if k == "gsplat" or k.startswith("gsplat.")}
+    try:
+        sys.path[:] = [p for p in sys.path if p not in ("", ".", str(ROOT))]
+        for k in saved_mod:
+            del sys.modules[k]
+        found = importlib.util.find_spec("gsplat") is not None
+    except Exception:
+        found = False
+    finally:
+        sys.path[:] = saved_path
+        sys.modules.update(saved_mod)
+    return "installed but not benchmarked" if found else "unavailable (gsplat is not installed in this image and cannot be fetched: no network)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,20 +237,72 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "CPU oracle port (oracle/ps_oracle.c) of the reference algorithm on all host cores; the reference "
-                   "ships no native code and its 3D arithmetic (gsplat) is CUDA-only, so there is no reference CPU build"}
+                   "ships no native code and its 3D arithmetic (gsplat) is CUDA-only, so there is no reference CPU path for "
+                   "the 3D configuration the metric is quoted on; the reference's own 2D class is timed beside it "
+                   "(cpu_baseline_reference)",
+           "gsplat_b200": gsplat_comparator()}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline_reference"] = reference_2d_cpu("c3" if cfg["mode"] == "3d" else wl)
     print(json.dumps(out), flush=True)
 
 
 def workload_name(wl):
     from pose_splatter_b200 import synth
     c = synth.WORKLOADS[wl]
-    idx = {"c1": 0, "c2": 1, "c3": 2, "c5_3d": 4, "c5_2d": 4}[wl]
-    return f"BASELINE.json configs[{idx}] ({wl}): {c['mode'].upper()} GS fwd+bwd, 6 cameras at {c['width']}x{c['height']}, N={c['n']} synthetic Gaussians per frame"
+    idx = {"c1": 0, "c2": 1, "c3": 2, "c4": 3, "c5_3d": 4, "c5_2d": 4}[wl]
+    what = "GS full-sequence inference render (forward only, uint8 RGBA out), 3600 frames x" if wl == "c4" else "GS fwd+bwd,"
+    return f"BASELINE.json configs[{idx}] ({wl}): {c['mode'].upper()} {what} 6 cameras at {c['width']}x{c['height']}, N={c['n']} synthetic Gaussians per frame"
 
 
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def pin_rank_to_cores(local, local_world):
+    """One process per GPU: give every rank a disjoint set of host cores on its GPU's NUMA node (its pinned staging
+    buffers are allocated afterwards, first-touch on that node).  Eight un-pinned ranks sharing every core was the e2e
+    limiter of round 1.  Returns what was done, for the JSON line."""
+    import torch
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return {"pinned": False, "why": "sched_getaffinity unavailable"}
+
+    def node_of(dev_index):
+        try:
+            pr = torch.cuda.get_device_properties(dev_index)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            return int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        except Exception:
+            return -1
+
+    def cpus_of(node):
+        out = []
+        try:
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                out += list(range(int(a), int(b or a) + 1))
+        except Exception:
+            pass
+        return [c for c in out if c in avail]
+
+    nodes = [node_of(i) for i in range(local_world)]
+    mine = nodes[local] if local < len(nodes) else -1
+    pool = cpus_of(mine) if mine >= 0 else []
+    peers = [i for i in range(local_world) if nodes[i] == mine] if pool else list(range(local_world))
+    if not pool:
+        pool = avail
+    k = peers.index(local) if local in peers else 0
+    per = max(1, len(pool) // max(1, len(peers)))
+    cores = pool[k * per:(k + 1) * per] or pool
+    try:
+        os.sched_setaffinity(0, cores)
+        torch.set_num_threads(max(1, min(len(cores), 8)))
+    except Exception as e:
+        return {"pinned": False, "why": str(e)}
+    return {"pinned": True, "numa_node": mine, "cores": f"{cores[0]}-{cores[-1]}" if cores else "", "n_cores": len(cores),
+            "host_cores_total": len(avail)}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -176,6 +314,8 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: pose_splatter_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pin = pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    args._pin = pin
     # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner at
     # communicator creation) goes to stderr
     sys.stdout.flush()
@@ -195,8 +335,79 @@ def run_b200(args):
         print(json.dumps(out), flush=True)
 
 
+def split_frames_leg(args, world, rank, dev, steps=5):
+    """BASELINE.json configs[4] layout at c2 size, part of the default N > 1 line: one frame's six cameras land on
+    DIFFERENT ranks (view v -> rank v % world), so the per-Gaussian gradients of a frame must be summed across GPUs.
+    Two ways, same inputs: (a) local backward + NCCL all-reduce of d_params over NVLink, (b) the fused exchange (K8'):
+    the projection-backward kernel pushes finished rows into the owner rank's staging buffer over peer memory
+    (ps_backward_peer) and the owner sums its slots.  The two gradients are compared on every rank."""
+    import torch
+    import torch.distributed as dist
+    from pose_splatter_b200 import _capi, batched, synth
+    from pose_splatter_b200 import dist as psd
+    F, C = FRAMES_DEFAULT["c2"], 6
+    d = synth.make_views("c2", F, C, seed=4242, n=args.n or None)  # the same frames on every rank
+    W, H = d["width"], d["height"]
+    mine = torch.tensor(psd.shard_views(F, C, rank, world, "view"), dtype=torch.long)
+    p = d["params"].to(dev)
+    vf, vm, Ks = d["view_frame"][mine].to(dev), d["viewmats"][mine].to(dev), d["Ks"][mine].to(dev)
+    w_rgb, w_a = synth.cotangents(F * C, H, W, seed=9)
+    w_rgb, w_a = w_rgb[mine].to(dev).contiguous(), w_a[mine].to(dev).contiguous()
+    bg = torch.ones(3, device=dev)
+    peer = psd.PeerGradBuffers(tuple(p.shape), dev)
+
+    def step_nccl():
+        _, _, _, sv = batched.forward_raw("3d", p, vf, vm, Ks, bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD)
+        g = batched.backward_raw(sv, p, vf, vm, Ks, bg, w_rgb, w_a)
+        sv.release()
+        psd.reduce_frame_grads(g)
+        return g
+
+    def step_fused():
+        _, _, _, sv = batched.forward_raw("3d", p, vf, vm, Ks, bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD)
+        peer.begin()
+        batched.backward_peer_raw(sv, p, vm, Ks, bg, w_rgb, w_a, peer.rank_ptrs, peer.rank, peer.world)
+        g = peer.end()
+        sv.release()
+        return g
+
+    res = {}
+    grads = {}
+    for name, fn in (("nccl_allreduce", step_nccl), ("fused_peer_push", step_fused)):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g = fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = psd.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+        grads[name] = g.clone()
+        res[name] = {"value": F * C / (ms * 1e-3), "unit": "views/s", "ms_per_step": ms}
+    want = grads["nccl_allreduce"][peer.owned]              # complete gradient of the frames this rank owns
+    got = grads["fused_peer_push"]
+    scale = want.abs().amax(dim=(0, 1)).clamp_min(1e-20)
+    rel = float(((got - want).abs().amax(dim=(0, 1)) / scale).max()) if len(peer.owned) else 0.0
+    rel = psd.max_over_ranks(rel, dev)
+    res["max_rel_difference_of_the_two_gradients"] = rel
+    res["gradients_agree"] = bool(rel < 1e-4)
+    res["config"] = {"workload": workload_name("c2"), "frames_per_step_total": F, "views_per_step_total": F * C,
+                     "sharding": f"view v -> rank v % {world}: every frame's cameras are split across ranks",
+                     "exchange_bytes_per_step_per_rank": int(p.numel() * 4), "steps": steps}
+    return res
+
+
 def run_measurements(args, world, rank, local, dev):
     out = measure(args, args.workload, args.steps, world, rank, local, dev, primary=True)
+    if world > 1 and args.workload == "c2" and not args.split_frames and not args.forward_only:
+        # driver-visible evidence for the cross-GPU gradient exchange: part of every default N > 1 line
+        leg = split_frames_leg(args, world, rank, dev)
+        if rank == 0:
+            out.setdefault("also", {})["split_frames"] = leg
     if args.workload == "c2" and not args.no_secondary and not args.n and not args.split_frames and not args.forward_only:
         # the metric names two configurations; the 2D one (BASELINE.json configs[2]) rides along, briefly
         other = measure(args, "c3", max(2, min(3, args.steps)), world, rank, local, dev, primary=False)
@@ -304,6 +515,8 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     # (every copy of every timed step is inside the timed region; the region ends when all three streams are idle).
     out_host = [torch.empty_like(host[0]["params"]).pin_memory() for _ in range(2)]
     loss_host = torch.empty(2).pin_memory()
+    gnorm_host = [torch.empty(host[0]["params"].shape[0]).pin_memory() for _ in range(2)]
+    e2e_cfg = {"grad_to_host": False}
     h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     staged = {}
 
@@ -344,13 +557,20 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         if need_reduce:
             psd.reduce_frame_grads(g)
         lossd = loss.detach().reshape(1)
+        # the step's result goes back to the host: the loss and the per-frame gradient norms (what a training loop logs;
+        # the gradient itself stays on the device for the optimiser, as in the reference's training step).  With
+        # grad_to_host the whole d_params [F,N,P] is copied back as well (round-1 definition, kept as a secondary number).
+        gnorm = g.reshape(g.shape[0], -1).square().sum(1)
         done = torch.cuda.Event()
         done.record(main)
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(done)
-            out_host[k % 2].copy_(g, non_blocking=True)
+            if e2e_cfg["grad_to_host"]:
+                out_host[k % 2].copy_(g, non_blocking=True)
+            gnorm_host[k % 2].copy_(gnorm, non_blocking=True)
             loss_host[k % 2:k % 2 + 1].copy_(lossd, non_blocking=True)
         g.record_stream(d2h_stream)
+        gnorm.record_stream(d2h_stream)
         lossd.record_stream(d2h_stream)
 
     def drain_e2e():
@@ -397,6 +617,25 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         step_e2e(k, last=True)
     drain_e2e()
     ms_e2e, _, _ = timed(step_e2e, steps, e2e=True)
+    ms_e2e_grad = None
+    if not fwd_only:  # secondary: the round-1 definition (the whole gradient copied back every step)
+        e2e_cfg["grad_to_host"] = True
+        step_e2e(0, last=True)
+        drain_e2e()
+        ms_e2e_grad, _, _ = timed(step_e2e, max(2, steps // 2), e2e=True)
+        ms_e2e_grad /= max(2, steps // 2)
+        e2e_cfg["grad_to_host"] = False
+    # copies alone (no kernels), all ranks at once: what the host side can deliver per step
+    def copies_only(k, last=False):
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(h2d_stream):
+            t = {name: v.to(dev, non_blocking=True) for name, v in host[k % n_sets].items()}
+        for v in t.values():
+            v.record_stream(main)
+    for k in range(2):
+        copies_only(k)
+    drain_e2e()
+    ms_copy, _, _ = timed(copies_only, steps, e2e=True)
 
     # pair counts of one step (untimed): the SAME forward / backward kernels with their counters compiled in
     s0 = devs[0]
@@ -414,6 +653,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
 
     if rank != 0:
         return None
+    h2d_bytes = int(sum(t.numel() * t.element_size() for t in host[0].values()))
     views_total = V * world * steps
     value = views_total / (ms_total * 1e-3)
     e2e_value = views_total / (ms_e2e * 1e-3)
@@ -484,8 +724,17 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                                                                  else "whole frames per rank, no collective"),
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
            "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / steps,
-                   "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0].values())),
-                   "d2h_bytes_per_step": int(V * H * W * 4) if fwd_only else int(out_host[0].numel() * 4 + 4),
+                   "h2d_bytes_per_step": h2d_bytes,
+                   "d2h_bytes_per_step": int(V * H * W * 4) if fwd_only else int(gnorm_host[0].numel() * 4 + 4),
+                   "result_read_back": "uint8 RGBA images" if fwd_only else "loss + per-frame gradient norms (d_params stays on the device, as in a training step)",
+                   "with_gradient_readback": None if ms_e2e_grad is None else {
+                       "value": V * world / (ms_e2e_grad * 1e-3), "ms_per_step": ms_e2e_grad,
+                       "d2h_bytes_per_step": int(out_host[0].numel() * 4 + gnorm_host[0].numel() * 4 + 4),
+                       "what": "round-1 definition: the whole d_params [F,N,P] copied back to pinned host memory every step"},
+                   "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / steps * 1e-3) / 1e9,
+                   "copies_alone": {"ms_per_step": ms_copy / steps, "h2d_gbs_per_rank": h2d_bytes / (ms_copy / steps * 1e-3) / 1e9,
+                                    "what": "the same host->device copies with no kernels, all ranks at once (max over ranks): the host-side ceiling"},
+                   "host_pinning": getattr(args, "_pin", None),
                    "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm, "binning": binning,
            "stage_ms_per_step": per_step, "pairs": stats_all, "per_kernel": per_kernel, "fp32_peak_tflops": fp32_peak}
@@ -506,7 +755,17 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
             lat.append(1e3 * (time.perf_counter() - t0))
             p1.grad = None
         lat = sorted(lat[5:])
+        latf = []
+        with torch.no_grad():
+            for it in range(30):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r1.render(p1, vm1, K1)
+                torch.cuda.synchronize()
+                latf.append(1e3 * (time.perf_counter() - t0))
+        latf = sorted(latf[5:])
         out["single_view"] = {"latency_ms_median": lat[len(lat) // 2], "latency_ms_min": lat[0],
+                              "forward_only_latency_ms_median": latf[len(latf) // 2], "forward_only_latency_ms_min": latf[0],
                               "what": "one renderer.render(params[N,P], viewmat, K) + backward, host wall clock with a device "
                                       "synchronisation on both sides (launch / latency bound; the batched numbers are the headline)"}
     if world == 1 and primary and not fwd_only and min(H, W) >= 11:
@@ -520,6 +779,15 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         vps, dt = cpu_views_per_second(wl, sample_views, cores, args.n)
         out["cpu_baseline"] = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
                                "sample": f"{sample_views} views of the same workload (full N, full resolution, fwd+bwd), {dt:.1f} s on {cores} threads"}
+        # the reference's own pure-PyTorch CPU path (2D only: its 3D arithmetic is gsplat, CUDA-only) beside the port
+        out["cpu_baseline_reference"] = reference_2d_cpu("c3" if mode == "3d" else wl)
+    if primary:
+        out["gsplat_b200"] = gsplat_comparator()
+    if wl == "c4":
+        out["full_sequence"] = {"frames": C4_SEQUENCE_FRAMES, "views": C4_SEQUENCE_FRAMES * n_cams,
+                                "seconds_at_this_rate_resident": C4_SEQUENCE_FRAMES * n_cams / value,
+                                "seconds_at_this_rate_e2e": C4_SEQUENCE_FRAMES * n_cams / e2e_value,
+                                "sharding": f"frames round-robin over {world} GPU(s), {F} frames per step per GPU, no collective"}
     return out
 
 
@@ -650,6 +918,8 @@ def training_step(dev, devs, n_sets, mode, W, H, V, bg, steps):
 
 if __name__ == "__main__":
     a = parse()
+    if a.workload == "c4":
+        a.forward_only = True  # configs[3] is inference: frames of the sequence sharded across ranks, no backward
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -331,23 +331,32 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
 
 // pixels (bit = y * 8 + x of the 8x4 block whose first pixel centre is (bxf, byf)) where the quadratic form
 // hA ux^2 + B ux uy + hC uy^2 <= lim can hold, u = pixel centre - (gx, gy)
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t span_mask(float gx, float gy, float hA, float B, float hC, float lim, float bxf, float byf)
 {
     if (!(hA > 0.0f)) return 0xffffffffu; // not an ellipse in x: let the exact test decide everywhere
+    // per pixel row uy: hA ux^2 + (B uy) ux + (hC uy^2 - lim) <= 0  <=>  |ux - c| <= h with
+    // c = -B uy / (2 hA), h = sqrt(disc) / (2 hA), disc = (B^2 - 4 hA hC) uy^2 + 4 hA lim.  The root comes from
+    // sqrt.approx (2 ulp): the interval is widened by 2e-3 px + 1e-6 relative, a superset of the exact test's pixels
     const float inv2a = __fdividef(0.5f, hA);
     const float gxr = gx - bxf;
-    const float four_a = 4.0f * hA;
+    const float k2 = B * B - 4.0f * hA * hC, k0 = 4.0f * hA * lim;
+    const float cs = -B * inv2a;
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float uy = (byf + (float)j) - gy;
-        const float bq = B * uy;
-        const float cq = hC * uy * uy - lim;
-        const float disc = bq * bq - four_a * cq;
+        const float disc = fmaf(k2, uy * uy, k0);
         if (disc >= 0.0f) { // NaN (degenerate records) fails: such entries never pass the exact test either
-            const float sq = sqrtf(disc);
-            const float flo = fmaxf(gxr + (-bq - sq) * inv2a - 1e-3f, -1.0f);
-            const float fhi = fminf(gxr + (-bq + sq) * inv2a + 1e-3f, 8.0f);
+            const float h = sqrt_approx(disc) * inv2a * 1.000001f + 2e-3f;
+            const float ctr = fmaf(cs, uy, gxr);
+            const float flo = fmaxf(ctr - h, -1.0f), fhi = fminf(ctr + h, 8.0f);
             const int ilo = max(0, (int)ceilf(flo)), ihi = min(7, (int)floorf(fhi));
             if (ilo <= ihi) m |= (((2u << ihi) - 1u) & ~((1u << ilo) - 1u)) << (8 * j);
         }
@@ -827,7 +836,7 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 constexpr int TAB_STRIDE = 33; // float2 per table row (32 pixels + 1 pad)
 
 template <int MODE, int BW, bool STATS>
-__global__ void __launch_bounds__(BW * 32)
+__global__ void __launch_bounds__(BW * 32, 16 / BW)
 raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, const int32_t *__restrict__ worklist,
                    const float *__restrict__ background, const int32_t *__restrict__ last, const float *__restrict__ t_pen,
                    const float *__restrict__ d_rgb, const float *__restrict__ d_alpha, const uint32_t *__restrict__ blist,
@@ -915,29 +924,46 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
         uint32_t pm = transpose32(cme, lane);
         if (STATS) st_pairs += __popc(pm);
         while (pm) {
-            const int e = 31 - __clz(pm);
-            pm &= ~(1u << e);
-            const float4 r0 = q0[e], r1 = q1[e], r2 = q2[e];
-            float gv, pb_scale; // alpha (3D) / g (2D); factor of -v in dL/dsigma resp. dL/dq
+            // two contributors in flight (independent sigma / exp chains), applied in reverse list order: a, then b
+            const int ea = 31 - __clz(pm);
+            pm &= ~(1u << ea);
+            const bool two = pm != 0u;
+            const int eb = two ? 31 - __clz(pm) : ea;
+            pm &= ~(1u << eb);
+            const float4 r0a = q0[ea], r1a = q1[ea], r2a = q2[ea], r0b = q0[eb], r1b = q1[eb], r2b = q2[eb];
+            float ga, gb, sa, sb; // alpha (3D) / g (2D); factor of -v in dL/dsigma resp. dL/dq
             if (MODE == PS_MODE_3D) {
                 float dx, dy;
-                const float sg = ps_sigma3d(r0.x, r0.y, r1.x, r1.y, r1.z, pxf, pyf, &dx, &dy);
-                const float oe = psm_mul(r0.w, psm_exp2_inrange(psm_mul(-sg, 0x1.715476p+0f)));
-                gv = fminf(PS_ALPHA_MAX, oe);
-                pb_scale = (oe <= PS_ALPHA_MAX) ? oe : 0.0f;
+                const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
+                const float sgb = ps_sigma3d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, pxf, pyf, &dx, &dy);
+                const float oea = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-sga, 0x1.715476p+0f)));
+                const float oeb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-sgb, 0x1.715476p+0f)));
+                ga = fminf(PS_ALPHA_MAX, oea); gb = fminf(PS_ALPHA_MAX, oeb);
+                sa = (oea <= PS_ALPHA_MAX) ? oea : 0.0f; sb = (oeb <= PS_ALPHA_MAX) ? oeb : 0.0f;
             } else {
                 float dxr, dyr;
-                const float qv = ps_q2d(r0.x, r0.y, r1.x, r1.y, r1.z, r1.w, pxf, pyf, &dxr, &dyr);
-                gv = psm_mul(r0.w, psm_exp2_inrange(psm_mul(-qv, 0x1.715476p+0f)));
-                pb_scale = gv;
+                const float qa = ps_q2d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, r1a.w, pxf, pyf, &dxr, &dyr);
+                const float qb = ps_q2d(r0b.x, r0b.y, r1b.x, r1b.y, r1b.z, r1b.w, pxf, pyf, &dxr, &dyr);
+                ga = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-qa, 0x1.715476p+0f)));
+                gb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-qb, 0x1.715476p+0f)));
+                sa = ga; sb = gb;
             }
-            const float cw = r2.x * w0 + r2.y * w1 + r2.z * w2;
-            const float Tb = first_c ? Tcur : Tcur * rcp_approx(1.0f - gv); // 1 - g >= 1e-3 (3D) / > 0 for contributors
+            const float cwa = r2a.x * w0 + r2a.y * w1 + r2a.z * w2;
+            const float cwb = r2b.x * w0 + r2b.y * w1 + r2b.z * w2;
+            const float ia = rcp_approx(1.0f - ga), ib = rcp_approx(1.0f - gb); // 1 - g >= 1e-3 (3D) / > 0 for contributors
+            const float Tba = first_c ? Tcur : Tcur * ia;
             first_c = false;
-            const float v = Tb * (cw - S); // dL/dalpha (3D) / dL/dg (2D)
-            tab[e * TAB_STRIDE + lane] = make_float2(gv * Tb, -pb_scale * v);
-            Tcur = Tb;
-            S = S + gv * (cw - S);
+            const float va = Tba * (cwa - S); // dL/dalpha (3D) / dL/dg (2D)
+            tab[ea * TAB_STRIDE + lane] = make_float2(ga * Tba, -sa * va);
+            Tcur = Tba;
+            S = S + ga * (cwa - S);
+            if (two) {
+                const float Tbb = Tcur * ib;
+                const float vb = Tbb * (cwb - S);
+                tab[eb * TAB_STRIDE + lane] = make_float2(gb * Tbb, -sb * vb);
+                Tcur = Tbb;
+                S = S + gb * (cwb - S);
+            }
         }
         __syncwarp(); // the pair table is complete
         // ---- phase B: lane = entry

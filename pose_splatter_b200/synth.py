@@ -21,6 +21,7 @@ WORKLOADS = {
     "c1": dict(mode="2d", ds=6, width=192, height=171, n=4096),
     "c2": dict(mode="3d", ds=4, width=288, height=256, n=16000),
     "c3": dict(mode="2d", ds=2, width=576, height=512, n=16000),
+    "c4": dict(mode="3d", ds=4, width=288, height=256, n=16000),  # full-sequence inference: 3600 frames x 6 cameras, forward only
     "c5_3d": dict(mode="3d", ds=1, width=1152, height=1024, n=16000),
     "c5_2d": dict(mode="2d", ds=1, width=1152, height=1024, n=16000),
 }
