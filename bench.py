@@ -412,8 +412,8 @@ def run_measurements(args, world, rank, local, dev):
         # the metric names two configurations; the 2D one (BASELINE.json configs[2]) rides along, briefly
         other = measure(args, "c3", max(2, min(3, args.steps)), world, rank, local, dev, primary=False)
         if rank == 0:
-            out["also"] = {"c3": {k: other[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline",
-                                                        "stage_ms_per_step", "pairs", "per_kernel")}}
+            out.setdefault("also", {})["c3"] = {k: other[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline",
+                                                                      "stage_ms_per_step", "pairs", "per_kernel")}
     return out
 
 
@@ -636,6 +636,15 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         copies_only(k)
     drain_e2e()
     ms_copy, _, _ = timed(copies_only, steps, e2e=True)
+    ms_copy_out = None
+    if not fwd_only:  # device->host alone: the gradient-sized buffer into pinned host memory
+        g_dev = torch.zeros_like(devs[0]["params"])
+        def copy_out_only(k, last=False):
+            with torch.cuda.stream(d2h_stream):
+                out_host[k % 2].copy_(g_dev, non_blocking=True)
+        copy_out_only(0)
+        drain_e2e()
+        ms_copy_out, _, _ = timed(copy_out_only, steps, e2e=True)
 
     # pair counts of one step (untimed): the SAME forward / backward kernels with their counters compiled in
     s0 = devs[0]
@@ -732,8 +741,11 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                        "d2h_bytes_per_step": int(gnorm_host[0].numel() * 4 + 4),
                        "what": "d_params stays on the device (as in a training step, where the optimiser consumes it there); only the loss and the per-frame gradient norms are read back"},
                    "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / steps * 1e-3) / 1e9,
-                   "copies_alone": {"ms_per_step": ms_copy / steps, "h2d_gbs_per_rank": h2d_bytes / (ms_copy / steps * 1e-3) / 1e9,
-                                    "what": "the same host->device copies with no kernels, all ranks at once (max over ranks): the host-side ceiling"},
+                   "copies_alone": {"h2d_ms_per_step": ms_copy / steps, "h2d_gbs_per_rank": h2d_bytes / (ms_copy / steps * 1e-3) / 1e9,
+                                    "d2h_ms_per_step": None if ms_copy_out is None else ms_copy_out / steps,
+                                    "d2h_gbs_per_rank": None if ms_copy_out is None else out_host[0].numel() * 4 / (ms_copy_out / steps * 1e-3) / 1e9,
+                                    "what": "the same copies with no kernels, each direction alone, all ranks at once (max over ranks): what the "
+                                            "host side of this box delivers; the e2e step cannot be faster than the slower of these and the kernels"},
                    "host_pinning": getattr(args, "_pin", None),
                    "overlap": "host->device and device->host copies on side streams, overlapped with the neighbouring steps' kernels"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm, "binning": binning,

@@ -22,7 +22,11 @@ out_host = [torch.empty_like(host[0]["params"]).pin_memory() for _ in range(2)]
 h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
 
-def run(steps, copy_in, copy_out, kernels):
+loss_host = torch.empty(2).pin_memory()
+gnorm_host = [torch.empty(F).pin_memory() for _ in range(2)]
+
+
+def run(steps, copy_in, copy_out, kernels, extras=0):
     main = torch.cuda.current_stream(dev)
     resident = {k: v.to(dev) for k, v in host[0].items()}
     g_res = torch.zeros_like(resident["params"])
@@ -49,13 +53,26 @@ def run(steps, copy_in, copy_out, kernels):
             rgb, alpha, g = batched.render_views_vjp("3d", t["params"], t["view_frame"], W, H, bg, w_rgb, w_a, t["viewmats"], t["Ks"])
         else:
             g = g_res
+        if extras >= 1 and kernels:
+            loss = torch.dot(rgb.reshape(-1), w_rgb.reshape(-1)) + torch.dot(alpha.reshape(-1), w_a.reshape(-1))
+            lossd = loss.detach().reshape(1)
+        if extras >= 2 and kernels:
+            gnorm = torch.linalg.vector_norm(g.reshape(g.shape[0], -1), dim=1)
         if copy_out:
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
                 out_host[k % 2].copy_(g, non_blocking=True)
+                if extras >= 2 and kernels:
+                    gnorm_host[k % 2].copy_(gnorm, non_blocking=True)
+                if extras >= 1 and kernels:
+                    loss_host[k % 2:k % 2 + 1].copy_(lossd, non_blocking=True)
             g.record_stream(d2h)
+            if extras >= 2 and kernels:
+                gnorm.record_stream(d2h)
+            if extras >= 1 and kernels:
+                lossd.record_stream(d2h)
     main.wait_stream(d2h)
     main.wait_stream(h2d)
     e1.record()
@@ -68,3 +85,6 @@ for name, cfg in (("kernels only", (False, False, True)), ("h2d only", (True, Fa
                   ("h2d + kernels + d2h", (True, True, True))):
     run(3, *cfg)
     print(f"{name:24s} {run(10, *cfg):8.3f} ms/step", flush=True)
+for extras in (1, 2):
+    run(3, True, True, True, extras)
+    print(f"full + extras {extras}          {run(10, True, True, True, extras):8.3f} ms/step", flush=True)
