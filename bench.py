@@ -516,7 +516,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     out_host = [torch.empty_like(host[0]["params"]).pin_memory() for _ in range(2)]
     loss_host = torch.empty(2).pin_memory()
     gnorm_host = [torch.empty(host[0]["params"].shape[0]).pin_memory() for _ in range(2)]
-    e2e_cfg = {"grad_to_host": True}
+    e2e_cfg = {"grad_to_host": False}
     h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     staged = {}
 
@@ -617,14 +617,14 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         step_e2e(k, last=True)
     drain_e2e()
     ms_e2e, _, _ = timed(step_e2e, steps, e2e=True)
-    ms_e2e_light = None
-    if not fwd_only:  # secondary: only the loss and the per-frame gradient norms go back (d_params stays on the device)
-        e2e_cfg["grad_to_host"] = False
+    ms_e2e_grad = None
+    if not fwd_only:  # secondary (round-1 definition): the whole gradient d_params [F,N,P] is copied back as well
+        e2e_cfg["grad_to_host"] = True
         step_e2e(0, last=True)
         drain_e2e()
-        ms_e2e_light, _, _ = timed(step_e2e, steps, e2e=True)
-        ms_e2e_light /= steps
-        e2e_cfg["grad_to_host"] = True
+        ms_e2e_grad, _, _ = timed(step_e2e, steps, e2e=True)
+        ms_e2e_grad /= steps
+        e2e_cfg["grad_to_host"] = False
     # copies alone (no kernels), all ranks at once: what the host side can deliver per step
     def copies_only(k, last=False):
         main = torch.cuda.current_stream(dev)
@@ -734,12 +734,14 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                       "l2": f"{n_sets} rotating input batches ({input_mb:.0f} MB) + {V * cfg['n'] * 60 / 2**20:.0f} MB of per-step intermediates > 126 MB L2"},
            "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": h2d_bytes,
-                   "d2h_bytes_per_step": int(V * H * W * 4) if fwd_only else int(out_host[0].numel() * 4 + gnorm_host[0].numel() * 4 + 4),
-                   "result_read_back": "uint8 RGBA images" if fwd_only else "the whole gradient d_params [F,N,P] + loss + per-frame gradient norms, into pinned host memory",
-                   "loss_and_norms_only": None if ms_e2e_light is None else {
-                       "value": V * world / (ms_e2e_light * 1e-3), "ms_per_step": ms_e2e_light,
-                       "d2h_bytes_per_step": int(gnorm_host[0].numel() * 4 + 4),
-                       "what": "d_params stays on the device (as in a training step, where the optimiser consumes it there); only the loss and the per-frame gradient norms are read back"},
+                   "d2h_bytes_per_step": int(V * H * W * 4) if fwd_only else int(gnorm_host[0].numel() * 4 + 4),
+                   "result_read_back": "uint8 RGBA images" if fwd_only else
+                                       "the step's loss + per-frame gradient norms (d_params stays on the device, where a training step's optimiser consumes it)",
+                   "with_gradient_readback": None if ms_e2e_grad is None else {
+                       "value": V * world / (ms_e2e_grad * 1e-3), "ms_per_step": ms_e2e_grad,
+                       "d2h_bytes_per_step": int(out_host[0].numel() * 4 + gnorm_host[0].numel() * 4 + 4),
+                       "what": "round-1 definition: additionally the whole d_params [F,N,P] is copied to pinned host memory every step; "
+                               "bounded by the host's device->host rate with all ranks copying at once (copies_alone.d2h_*)"},
                    "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / steps * 1e-3) / 1e9,
                    "copies_alone": {"h2d_ms_per_step": ms_copy / steps, "h2d_gbs_per_rank": h2d_bytes / (ms_copy / steps * 1e-3) / 1e9,
                                     "d2h_ms_per_step": None if ms_copy_out is None else ms_copy_out / steps,

@@ -9,6 +9,7 @@
 // fully_fused_projection + isect_tiles (absent from the reference tree).
 #include "ps_contract.cuh"
 #include "ps_internal.h"
+#include <cstdlib>
 
 namespace {
 
@@ -230,8 +231,8 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
 //                      owner's staging buffer, slot [my_rank][f / world] (local memory, or a peer GPU's over
 //                      NVLink): the transfer of one block overlaps the arithmetic of the next, no atomics, no
 //                      collective launch.  After a barrier the owner adds its `world` slots (ps_peer_sum).
-template <int MODE>
-__global__ void __launch_bounds__(PS_PROJ_BLOCK, 3)
+template <int MODE, int MINB> // MINB = CTAs per SM the register allocation is bounded for (measured: see the launcher)
+__global__ void __launch_bounds__(PS_PROJ_BLOCK, MINB)
 project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ frame_off,
                    const int32_t *__restrict__ frame_views, const float *__restrict__ viewmats,
                    const float *__restrict__ Ks, PsTable t, const float *__restrict__ acc, float *__restrict__ d_params,
@@ -444,10 +445,15 @@ int ps_launch_project_bwd(const PsGeometry &g, const float *params, const int32_
 {
     if (g.N == 0 || g.F == 0) return 0;
     dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.F);
-    if (g.mode == PS_MODE_3D)
-        project_bwd_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, my_rank, world);
-    else
-        project_bwd_kernel<PS_MODE_2D><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, my_rank, world);
+    // registers bounded for 2 / 3 / 4 CTAs per SM (122 / 80 / 64 registers): measured 1.41 / 1.23 / 1.17 ms at c2
+    static const int minb = getenv("PS_PBWD_MINB") ? atoi(getenv("PS_PBWD_MINB")) : 4; // A/B switch for measurements
+#define PS_PBWD(MODE, MB) project_bwd_kernel<MODE, MB><<<grid, PS_PROJ_BLOCK, 0, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, acc, d_params, peers, my_rank, world)
+    if (g.mode == PS_MODE_3D) {
+        if (minb == 2) PS_PBWD(PS_MODE_3D, 2); else if (minb == 3) PS_PBWD(PS_MODE_3D, 3); else PS_PBWD(PS_MODE_3D, 4);
+    } else {
+        PS_PBWD(PS_MODE_2D, 3);
+    }
+#undef PS_PBWD
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
