@@ -15,6 +15,7 @@
 //                 with the L1 sign term -> d_rgb [V,H,W,3]; IoU quotient rule -> d_alpha [V,H,W]
 //   loss_finalize losses [V,3] = (iou, ssim, img)
 #include "ps_internal.h"
+#include <cstdlib>
 
 namespace {
 
@@ -65,123 +66,207 @@ loss_reduce_kernel(LossDims d, const float *__restrict__ rgb, const float *__res
     r = block_sum((double)sL, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 3, r);
 }
 
-// horizontal 11-tap pass over a LIN-wide row segment: 4 consecutive outputs per thread
-template <int NMAP, typename F>
-__device__ __forceinline__ void hpass4(F value_at /* (k, i) -> input i of map k, i in [0, 14) */, float (&out)[NMAP][4])
+// ---- packed fp32: Blackwell issues two FMAs per instruction (fma.rn.f32x2 -> FFMA2); a plain three-register FFMA
+// only reaches half of the FP32 pipe's rate.  The window passes below are written on pairs: the horizontal pass filters
+// two image rows at once (the tile is kept row-pair interleaved in shared memory), the vertical pass two columns.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+
+constexpr int LP = LIN / 2;      // row pairs of the 42-row input tile
+constexpr int HP_ITEMS = LP * (LT / 4); // horizontal-pass items: a row pair x four output columns
+static_assert(LIN % 2 == 0 && LT % 4 == 0 && LTHREADS == 256, "tile geometry");
+
+// 11-tap window over 14 consecutive pairs -> 4 consecutive output pairs
+__device__ __forceinline__ void window4(const float2 (&in)[14], float2 (&out)[4])
 {
 #pragma unroll
-    for (int k = 0; k < NMAP; ++k) {
-        float in[14];
+    for (int o = 0; o < 4; ++o) {
+        float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 14; ++i) in[i] = value_at(k, i);
+        for (int tp = 0; tp < 11; ++tp) s = fma2(make_float2(c_taps[tp], c_taps[tp]), in[o + tp], s);
+        out[o] = s;
+    }
+}
+// 11-tap window over 12 consecutive pairs -> 2 consecutive output pairs
+__device__ __forceinline__ void window2(const float2 (&in)[12], float2 (&out)[2])
+{
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            float s = 0.f;
+    for (int o = 0; o < 2; ++o) {
+        float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int tp = 0; tp < 11; ++tp) s = fmaf(c_taps[tp], in[o + tp], s);
-            out[k][o] = s;
-        }
+        for (int tp = 0; tp < 11; ++tp) s = fma2(make_float2(c_taps[tp], c_taps[tp]), in[o + tp], s);
+        out[o] = s;
     }
 }
 
-// SSIM forward of one view tile, all three channels.  p = target image (planar), q = render (interleaved).
-__global__ void __launch_bounds__(LTHREADS)
-ssim_fwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restrict__ timg, float coef_over_count,
-                float c1, float c2, float *__restrict__ adj /* [V,3,3,H,W]: A1 | A2 | A3 per channel */,
-                double *__restrict__ stats)
+// SSIM forward of one view tile, all three channels, fused with the per-view sums of the other two loss terms
+// (soft-IoU I and U, sum of the mask, L1 distance).  p = target image (planar), q = render (interleaved).
+template <int MINB>
+__global__ void __launch_bounds__(LTHREADS, MINB)
+ssim_fwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restrict__ alpha, const float *__restrict__ timg,
+                const float *__restrict__ mask, float coef_over_count, float c1, float c2,
+                float *__restrict__ adj /* [V,3,3,H,W]: A1 | A2 | A3 per channel */, double *__restrict__ stats)
 {
-    __shared__ float sp[LIN][LIN + 1], sq[LIN][LIN + 1];
-    __shared__ float sh[5][LIN][LT + 1]; // + 1: the four rows a warp writes per store fall into different banks
+    __shared__ float2 sp[LP][LIN + 1], sq[LP][LIN + 1]; // [row pair][column]: .x = even row, .y = odd row of the pair
+    __shared__ __align__(16) float sh[5][LIN][LT + 4];  // horizontally filtered maps, rows 16-byte aligned
     __shared__ double scratch[LTHREADS / 32];
     const int v = blockIdx.z;
     const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
     const size_t npix = (size_t)d.H * d.W;
     const int tid = threadIdx.x;
-    float ssum = 0.f;
-    for (int ch = 0; ch < 3; ++ch) {
-        const float *pch = timg + (3 * (size_t)v + ch) * npix;
-        const float *qv = rgb + 3 * (size_t)v * npix;
-        __syncthreads(); // the previous channel's vertical pass is done with sh / sp / sq
-        for (int i = tid; i < LIN * LIN; i += LTHREADS) {
-            const int r = i / LIN, c = i - r * LIN;
-            const int y = y0 + r - HALO, x = x0 + c - HALO;
-            const bool in = y >= 0 && y < d.H && x >= 0 && x < d.W;
-            const size_t pix = (size_t)y * d.W + x;
-            sp[r][c] = in ? pch[pix] : 0.f;
-            sq[r][c] = in ? qv[3 * pix + ch] : 0.f;
-        }
-        __syncthreads();
-        for (int item = tid; item < LIN * (LT / 4); item += LTHREADS) {
-            const int r = item / (LT / 4), cg = (item - r * (LT / 4)) * 4;
-            float pv[14], qv14[14];
+    float ssum = 0.f, sI = 0.f, sU = 0.f, sM = 0.f, sL = 0.f;
+    {   // soft-IoU sums over this tile's own pixels (one 4-pixel row segment per thread)
+        const int r = tid >> 3, cg = (tid & 7) * 4;
+        const int y = y0 + r;
 #pragma unroll
-            for (int i = 0; i < 14; ++i) { pv[i] = sp[r][cg + i]; qv14[i] = sq[r][cg + i]; }
-            float out[5][4];
-            hpass4<5>([&](int k, int i) -> float {
-                return k == 0 ? pv[i] : k == 1 ? qv14[i] : k == 2 ? pv[i] * pv[i] : k == 3 ? qv14[i] * qv14[i] : pv[i] * qv14[i];
-            }, out);
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-#pragma unroll
-                for (int o = 0; o < 4; ++o) sh[k][r][cg + o] = out[k][o];
-        }
-        __syncthreads();
-        {
-            const int c = tid & 31, r0 = (tid >> 5) * 4;
-            float res[5][4];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                float in[14];
-#pragma unroll
-                for (int i = 0; i < 14; ++i) in[i] = sh[k][r0 + i][c];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int tp = 0; tp < 11; ++tp) s = fmaf(c_taps[tp], in[o + tp], s);
-                    res[k][o] = s;
-                }
-            }
-            float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix, *a2 = a1 + npix, *a3 = a2 + npix;
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const int y = y0 + r0 + o, x = x0 + c;
-                if (y >= d.H || x >= d.W) continue;
-                const bool centre = y >= HALO && y < d.H - HALO && x >= HALO && x < d.W - HALO;
-                float g1 = 0.f, g2 = 0.f, g3 = 0.f;
-                if (centre) {
-                    const float mp = res[0][o], mq = res[1][o];
-                    const float vpp = res[2][o] - mp * mp, vqq = res[3][o] - mq * mq, vpq = res[4][o] - mp * mq;
-                    const bool qfree = vqq > 0.f; // clamp(., min = 0) passes the gradient only when not clamped
-                    const float N1 = 2.f * mp * mq + c1, N2 = 2.f * vpq + c2;
-                    const float D1 = mp * mp + mq * mq + c1, D2 = fmaxf(vpp, 0.f) + fmaxf(vqq, 0.f) + c2;
-                    // D1 >= c1, D2 >= c2 > 0: approximate reciprocals (2 ulp) are far inside the 1e-3 gradient tolerance
-                    const float i1 = __fdividef(1.0f, D1), i2 = __fdividef(1.0f, D2);
-                    const float inv = i1 * i2;
-                    const float S = N1 * N2 * inv;
-                    ssum += S;
-                    const float dD2 = qfree ? -2.f * mq : 0.f;
-                    const float dmu = (2.f * mp * N2 - 2.f * mp * N1) * inv - S * (2.f * mq * i1 + dD2 * i2);
-                    g1 = coef_over_count * dmu;
-                    g2 = qfree ? coef_over_count * (-S * i2) : 0.f;
-                    g3 = coef_over_count * 2.f * N1 * inv;
-                }
-                const size_t pix = (size_t)y * d.W + x;
-                a1[pix] = g1; a2[pix] = g2; a3[pix] = g3;
+        for (int o = 0; o < 4; ++o) {
+            const int x = x0 + cg + o;
+            if (y < d.H && x < d.W) {
+                const float av = alpha[v * npix + (size_t)y * d.W + x], mv = mask[v * npix + (size_t)y * d.W + x];
+                sI += av * mv;
+                sU += av + mv - av * mv;
+                sM += mv;
             }
         }
     }
-    const double r = block_sum((double)ssum, scratch);
-    if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 4, r);
+    // The (p, q) tile of a channel is fetched into registers while the previous channel is being filtered (the passes are
+    // separated by CTA barriers, so a plain load -> store -> barrier sequence would expose the whole DRAM latency per
+    // channel) and parked in shared memory once the horizontal pass, the only reader of sp / sq, is done.
+    constexpr int NLD = (LIN * LIN + LTHREADS - 1) / LTHREADS; // tile elements per thread
+    const float *qv = rgb + 3 * (size_t)v * npix;
+    float pre_p[NLD], pre_q[NLD];
+    auto fetch = [&](int ch) {
+        const float *pch = timg + (3 * (size_t)v + ch) * npix;
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            const int i = tid + j * LTHREADS;
+            const int r = i / LIN, c = i - r * LIN;
+            const int y = y0 + r - HALO, x = x0 + c - HALO;
+            const bool in = i < LIN * LIN && y >= 0 && y < d.H && x >= 0 && x < d.W;
+            const size_t pix = (size_t)y * d.W + x;
+            pre_p[j] = in ? __ldg(pch + pix) : 0.f;
+            pre_q[j] = in ? __ldg(qv + 3 * pix + ch) : 0.f;
+        }
+    };
+    auto park = [&]() {
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            const int i = tid + j * LTHREADS;
+            if (i >= LIN * LIN) continue;
+            const int r = i / LIN, c = i - r * LIN;
+            *(reinterpret_cast<float *>(&sp[r >> 1][c]) + (r & 1)) = pre_p[j];
+            *(reinterpret_cast<float *>(&sq[r >> 1][c]) + (r & 1)) = pre_q[j];
+            // L1 term on the tile's own pixels (the halo belongs to the neighbours; outside the image both are 0)
+            if (r >= HALO && r < HALO + LT && c >= HALO && c < HALO + LT) sL += fabsf(pre_p[j] - pre_q[j]);
+        }
+    };
+    fetch(0);
+    park();
+    for (int ch = 0; ch < 3; ++ch) {
+        __syncthreads(); // sp / sq hold channel ch; the previous channel's vertical pass is done with sh
+        if (ch + 1 < 3) fetch(ch + 1);
+        for (int item = tid; item < HP_ITEMS; item += LTHREADS) {
+            // consecutive lanes take consecutive row pairs (their shared-memory rows fall into different banks)
+            const int cgi = item / LP, rp = item - cgi * LP, cg = cgi * 4;
+            float2 in2[14], t2[14], out[4];
+            auto put = [&](int k, const float2 (&o)[4]) {
+                *reinterpret_cast<float4 *>(&sh[k][2 * rp][cg]) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+                *reinterpret_cast<float4 *>(&sh[k][2 * rp + 1][cg]) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+            };
+            // three short-lived register windows (p | q | p q) instead of p and q held together: fewer live registers
+#pragma unroll
+            for (int i = 0; i < 14; ++i) in2[i] = sp[rp][cg + i];
+            window4(in2, out); put(0, out);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) t2[i] = mul2(in2[i], in2[i]);
+            window4(t2, out); put(2, out);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) in2[i] = sq[rp][cg + i];
+            window4(in2, out); put(1, out);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) t2[i] = mul2(in2[i], in2[i]);
+            window4(t2, out); put(3, out);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) t2[i] = mul2(in2[i], sp[rp][cg + i]);
+            window4(t2, out); put(4, out);
+        }
+        __syncthreads();
+        if (ch + 1 < 3) park(); // nobody reads sp / sq any more: the next channel moves in under the vertical pass
+        {   // vertical pass: thread = (column pair, two output rows)
+            const int c = (tid & 15) * 2, r0 = (tid >> 4) * 2;
+            float2 res[5][2];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                float2 in[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) in[i] = *reinterpret_cast<const float2 *>(&sh[k][r0 + i][c]);
+                window2(in, res[k]);
+            }
+            float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix, *a2 = a1 + npix, *a3 = a2 + npix;
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int y = y0 + r0 + o, x = x0 + c + h;
+                    if (y >= d.H || x >= d.W) continue;
+                    const bool centre = y >= HALO && y < d.H - HALO && x >= HALO && x < d.W - HALO;
+                    float g1 = 0.f, g2 = 0.f, g3 = 0.f;
+                    if (centre) {
+                        const float mp = h ? res[0][o].y : res[0][o].x, mq = h ? res[1][o].y : res[1][o].x;
+                        const float epp = h ? res[2][o].y : res[2][o].x, eqq = h ? res[3][o].y : res[3][o].x;
+                        const float epq = h ? res[4][o].y : res[4][o].x;
+                        const float vpp = epp - mp * mp, vqq = eqq - mq * mq, vpq = epq - mp * mq;
+                        const bool qfree = vqq > 0.f; // clamp(., min = 0) passes the gradient only when not clamped
+                        const float N1 = 2.f * mp * mq + c1, N2 = 2.f * vpq + c2;
+                        const float D1 = mp * mp + mq * mq + c1, D2 = fmaxf(vpp, 0.f) + fmaxf(vqq, 0.f) + c2;
+                        // D1 >= c1, D2 >= c2 > 0: approximate reciprocals (2 ulp) are far inside the 1e-3 gradient tolerance
+                        const float i1 = __fdividef(1.0f, D1), i2 = __fdividef(1.0f, D2);
+                        const float inv = i1 * i2;
+                        const float S = N1 * N2 * inv;
+                        ssum += S;
+                        const float dD2 = qfree ? -2.f * mq : 0.f;
+                        const float dmu = (2.f * mp * N2 - 2.f * mp * N1) * inv - S * (2.f * mq * i1 + dD2 * i2);
+                        g1 = coef_over_count * dmu;
+                        g2 = qfree ? coef_over_count * (-S * i2) : 0.f;
+                        g3 = coef_over_count * 2.f * N1 * inv;
+                    }
+                    const size_t pix = (size_t)y * d.W + x;
+                    a1[pix] = g1; a2[pix] = g2; a3[pix] = g3;
+                }
+            }
+        }
+    }
+    double r;
+    r = block_sum((double)ssum, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 4, r);
+    r = block_sum((double)sI, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 0, r);
+    r = block_sum((double)sU, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 1, r);
+    r = block_sum((double)sM, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 2, r);
+    r = block_sum((double)sL, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 3, r);
 }
 
-__global__ void __launch_bounds__(LTHREADS)
+template <int MINB>
+__global__ void __launch_bounds__(LTHREADS, MINB)
 loss_bwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restrict__ alpha,
                 const float *__restrict__ timg, const float *__restrict__ mask, const float *__restrict__ adj,
                 const double *__restrict__ stats, float img_lambda, float *__restrict__ d_rgb, float *__restrict__ d_alpha)
 {
-    __shared__ float sa[3][LIN][LIN + 1];
-    __shared__ float sh[3][LIN][LT + 1];
+    __shared__ float2 sa[3][LP][LIN + 1];              // adjoint maps, row-pair interleaved
+    __shared__ __align__(16) float sh[3][LIN][LT + 4];
     const int v = blockIdx.z;
     const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
     const size_t npix = (size_t)d.H * d.W;
@@ -189,64 +274,87 @@ loss_bwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
     const double I = stats[v * NSTAT + 0] + 1e-6, U = stats[v * NSTAT + 1] + 1e-6, msum = stats[v * NSTAT + 2];
     const float l1 = img_lambda == 0.0f ? 0.0f : (float)((double)img_lambda / msum); // lambda 0: no 0 * 0 / 0 for an empty mask
     const float iou_m = (float)(-1.0 / U), iou_c = (float)(I / (U * U)); // d(1 - I/U)/da = -m/U + I (1 - m) / U^2
-    const int c = tid & 31, r0 = (tid >> 5) * 4;
-    float g[4][3];
-    for (int ch = 0; ch < 3; ++ch) {
+    const int c = (tid & 15) * 2, r0 = (tid >> 4) * 2; // this thread's 2 x 2 output pixels
+    float g[2][2][3];
+    constexpr int NLD = (LIN * LIN + LTHREADS - 1) / LTHREADS;
+    float pre[3][NLD]; // the next channel's adjoint tiles, in flight while this channel is filtered
+    auto fetch = [&](int ch) {
         const float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix;
-        __syncthreads();
-        for (int i = tid; i < LIN * LIN; i += LTHREADS) {
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            const int i = tid + j * LTHREADS;
             const int r = i / LIN, cc = i - r * LIN;
             const int y = y0 + r - HALO, x = x0 + cc - HALO;
-            const bool in = y >= 0 && y < d.H && x >= 0 && x < d.W;
+            const bool in = i < LIN * LIN && y >= 0 && y < d.H && x >= 0 && x < d.W;
             const size_t pix = (size_t)y * d.W + x;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) sa[k][r][cc] = in ? a1[k * npix + pix] : 0.f;
+            for (int k = 0; k < 3; ++k) pre[k][j] = in ? __ldg(a1 + k * npix + pix) : 0.f;
         }
-        __syncthreads();
-        for (int item = tid; item < LIN * (LT / 4); item += LTHREADS) {
-            const int r = item / (LT / 4), cg = (item - r * (LT / 4)) * 4;
-            float out[3][4];
-            hpass4<3>([&](int k, int i) -> float { return sa[k][r][cg + i]; }, out);
+    };
+    auto park = [&]() {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < NLD; ++j) {
+            const int i = tid + j * LTHREADS;
+            if (i >= LIN * LIN) continue;
+            const int r = i / LIN, cc = i - r * LIN;
 #pragma unroll
-                for (int o = 0; o < 4; ++o) sh[k][r][cg + o] = out[k][o];
+            for (int k = 0; k < 3; ++k) *(reinterpret_cast<float *>(&sa[k][r >> 1][cc]) + (r & 1)) = pre[k][j];
         }
+    };
+    fetch(0);
+    park();
+    for (int ch = 0; ch < 3; ++ch) {
         __syncthreads();
-        float res[3][4];
+        if (ch + 1 < 3) fetch(ch + 1);
+        for (int item = tid; item < HP_ITEMS; item += LTHREADS) {
+            const int cgi = item / LP, rp = item - cgi * LP, cg = cgi * 4;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float in[14];
+            for (int k = 0; k < 3; ++k) {
+                float2 in[14], out[4];
 #pragma unroll
-            for (int i = 0; i < 14; ++i) in[i] = sh[k][r0 + i][c];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                float s = 0.f;
-#pragma unroll
-                for (int tp = 0; tp < 11; ++tp) s = fmaf(c_taps[tp], in[o + tp], s);
-                res[k][o] = s;
+                for (int i = 0; i < 14; ++i) in[i] = sa[k][rp][cg + i];
+                window4(in, out);
+                *reinterpret_cast<float4 *>(&sh[k][2 * rp][cg]) = make_float4(out[0].x, out[1].x, out[2].x, out[3].x);
+                *reinterpret_cast<float4 *>(&sh[k][2 * rp + 1][cg]) = make_float4(out[0].y, out[1].y, out[2].y, out[3].y);
             }
         }
+        __syncthreads();
+        if (ch + 1 < 3) park();
+        float2 res[3][2];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int y = y0 + r0 + o, x = x0 + c;
-            g[o][ch] = 0.f;
-            if (y >= d.H || x >= d.W) continue;
-            const size_t pix = (size_t)y * d.W + x;
-            const float q = rgb[3 * ((size_t)v * npix + pix) + ch], p = timg[(3 * (size_t)v + ch) * npix + pix];
-            const float diff = p - q;
-            const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-            g[o][ch] = res[0][o] + 2.f * q * res[1][o] + p * res[2][o] - l1 * sgn;
+        for (int k = 0; k < 3; ++k) {
+            float2 in[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) in[i] = *reinterpret_cast<const float2 *>(&sh[k][r0 + i][c]);
+            window2(in, res[k]);
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = y0 + r0 + o, x = x0 + c + h;
+                g[o][h][ch] = 0.f;
+                if (y >= d.H || x >= d.W) continue;
+                const size_t pix = (size_t)y * d.W + x;
+                const float q = rgb[3 * ((size_t)v * npix + pix) + ch], p = timg[(3 * (size_t)v + ch) * npix + pix];
+                const float diff = p - q;
+                const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                const float w1 = h ? res[0][o].y : res[0][o].x, w2 = h ? res[1][o].y : res[1][o].x, w3 = h ? res[2][o].y : res[2][o].x;
+                g[o][h][ch] = w1 + 2.f * q * w2 + p * w3 - l1 * sgn;
+            }
         }
     }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        const int y = y0 + r0 + o, x = x0 + c;
-        if (y >= d.H || x >= d.W) continue;
-        const size_t pix = (size_t)v * npix + (size_t)y * d.W + x;
-        d_rgb[3 * pix] = g[o][0]; d_rgb[3 * pix + 1] = g[o][1]; d_rgb[3 * pix + 2] = g[o][2];
-        const float m = mask[pix];
-        d_alpha[pix] = iou_m * m + iou_c * (1.f - m);
+    for (int o = 0; o < 2; ++o) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int y = y0 + r0 + o, x = x0 + c + h;
+            if (y >= d.H || x >= d.W) continue;
+            const size_t pix = (size_t)v * npix + (size_t)y * d.W + x;
+            d_rgb[3 * pix] = g[o][h][0]; d_rgb[3 * pix + 1] = g[o][h][1]; d_rgb[3 * pix + 2] = g[o][h][2];
+            const float m = mask[pix];
+            d_alpha[pix] = iou_m * m + iou_c * (1.f - m);
+        }
     }
     (void)alpha;
 }
@@ -306,17 +414,19 @@ int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alph
     const size_t npix = (size_t)H * W;
     int bx = (int)((npix + LTHREADS * 8 - 1) / (LTHREADS * 8));
     bx = bx < 1 ? 1 : (bx > 64 ? 64 : bx);
-    loss_reduce_kernel<<<dim3(bx, V), LTHREADS, 0, s>>>(d, rgb, alpha, timg, mask, stats);
     const dim3 tiles((W + LT - 1) / LT, (H + LT - 1) / LT, V);
     const double count = 3.0 * (double)(H - 2 * HALO) * (double)(W - 2 * HALO);
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f; // (k * data_range)^2, data_range = 1.0
-    int n = 2;
+    int n = 1;
+    (void)bx;
+    static const int minb = getenv("PS_LOSS_MINB") ? atoi(getenv("PS_LOSS_MINB")) : 2; // A/B switch: registers bounded for 2 / 3 CTAs per SM
+    const float coef = d_rgb ? (float)(-(double)ssim_lambda / count) : 0.0f;
+    if (minb == 3) ssim_fwd_kernel<3><<<tiles, LTHREADS, 0, s>>>(d, rgb, alpha, timg, mask, coef, c1, c2, adj, stats);
+    else ssim_fwd_kernel<2><<<tiles, LTHREADS, 0, s>>>(d, rgb, alpha, timg, mask, coef, c1, c2, adj, stats);
+    n += 1;
     if (d_rgb) {
-        ssim_fwd_kernel<<<tiles, LTHREADS, 0, s>>>(d, rgb, timg, (float)(-(double)ssim_lambda / count), c1, c2, adj, stats);
-        loss_bwd_kernel<<<tiles, LTHREADS, 0, s>>>(d, rgb, alpha, timg, mask, adj, stats, img_lambda, d_rgb, d_alpha);
-        n += 2;
-    } else {
-        ssim_fwd_kernel<<<tiles, LTHREADS, 0, s>>>(d, rgb, timg, 0.0f, c1, c2, adj, stats);
+        if (minb == 3) loss_bwd_kernel<3><<<tiles, LTHREADS, 0, s>>>(d, rgb, alpha, timg, mask, adj, stats, img_lambda, d_rgb, d_alpha);
+        else loss_bwd_kernel<2><<<tiles, LTHREADS, 0, s>>>(d, rgb, alpha, timg, mask, adj, stats, img_lambda, d_rgb, d_alpha);
         n += 1;
     }
     loss_finalize_kernel<<<(V + 127) / 128, 128, 0, s>>>(d, stats, ssim_lambda, img_lambda, losses);

@@ -88,6 +88,33 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 1-D bulk copies (the TMA engine's non-tensor form, cp.async.bulk -> UBLKCP) completing on an mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // 3D: can the splat pass sigma <= thr anywhere on the pixel centres [x0, x1] x [y0, y1]?
 // sigma(u) = hA ux^2 + hC uy^2 + B ux uy (u = pixel - mean) is convex with its minimum at u = 0, so over a
 // box that does not contain 0 the minimum lies on an edge facing the mean; along such an edge it is a 1-D
@@ -835,7 +862,9 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 // Persistent warps pulling (tile, block) tasks off one counter, records streamed through the cp.async ring as before.
 constexpr int TAB_STRIDE = 33; // float2 per table row (32 pixels + 1 pad)
 
-template <int MODE, int BW, bool STATS>
+// BULK = true: the records are staged with one 48-byte cp.async.bulk per entry (TMA engine, 1-D form) completing on a
+// per-stage mbarrier instead of three 16-byte cp.async per lane (A/B experiment).
+template <int MODE, int BW, bool STATS, bool BULK>
 __global__ void __launch_bounds__(BW * 32, 16 / BW)
 raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, const int32_t *__restrict__ worklist,
                    const float *__restrict__ background, const int32_t *__restrict__ last, const float *__restrict__ t_pen,
@@ -843,14 +872,21 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
                    const uint32_t *__restrict__ cmask, const int32_t *__restrict__ bcount, float *__restrict__ acc,
                    const int32_t *__restrict__ n_lists, unsigned *__restrict__ next_task, unsigned long long *__restrict__ stats)
 {
-    __shared__ float4 s_a[BW][NS][CH], s_b[BW][NS][CH], s_c[BW][NS][CH];
+    // cp.async: three planes of float4 (rec0 | rec1 | rec2); bulk: 48 contiguous bytes per entry (s_a[w][st][3 e + k])
+    __shared__ __align__(16) float4 s_a[BW][NS][BULK ? 3 * CH : CH], s_b[BW][NS][BULK ? 1 : CH], s_c[BW][NS][BULK ? 1 : CH];
+    __shared__ __align__(8) uint64_t s_bar[BW][NS];
     __shared__ float2 s_tab[BW][32 * TAB_STRIDE];   // phase A -> B pair table [entry][pixel]; reused as the 32 x 9 output transpose
     __shared__ float4 s_w[BW][32];                  // d_rgb of the block's pixels
     __shared__ uint32_t s_id[BW][32];               // accumulator rows (view * N + Gaussian) of the chunk's entries
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long st_pairs = 0, st_walk = 0, st_staged = 0;
     const unsigned n_tasks = 8u * (unsigned)__ldg(n_lists);
-    const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
+    if (BULK) {
+        if (lane < NS) mbar_init(&s_bar[wid][lane], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+    unsigned bar_phase = 0; // bit st: parity the next wait on stage st must see
     float2 *tab = s_tab[wid];
     float *outt = reinterpret_cast<float *>(s_tab[wid]);
     for (;;) {
@@ -882,12 +918,21 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
     // reverse step r handles chunk nchunks - 1 - r; its ring stage is r % NS; ids and masks run ahead in registers
     auto issue = [&](int r, uint32_t id) {
         const int cj = nchunks - 1 - r;
+        const int st = r % NS;
+        if (BULK) {
+            if (cj < 0) return;
+            const int n_valid = min(CH, len - cj * CH);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the stage's last generic-proxy reads precede the async writes
+            if (lane == 0) mbar_expect_tx(&s_bar[wid][st], 48u * (unsigned)n_valid);
+            __syncwarp(); // the transaction count is armed before any copy can complete on the barrier
+            if (lane < n_valid) bulk_copy_g2s(&s_a[wid][st][3 * lane], PS_REC(t, id, 0), 48u, &s_bar[wid][st]);
+            return;
+        }
         if (cj >= 0 && cj * CH + lane < len) {
-            const int st = r % NS;
             const float4 *src = PS_REC(t, id, 0);
-            cp_async16(&q.a[st][lane], src);
-            cp_async16(&q.b[st][lane], src + 1);
-            cp_async16(&q.c[st][lane], src + 2);
+            cp_async16(&s_a[wid][st][lane], src);
+            cp_async16(&s_b[wid][st][lane], src + 1);
+            cp_async16(&s_c[wid][st][lane], src + 2);
         }
         cp_async_commit();
     };
@@ -911,14 +956,21 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
         const uint32_t id_c = id0, cme = cm0;
         id0 = id1; cm0 = cm1; id1 = id2; cm1 = cm2; id2 = id3; cm2 = cm3;
         fetch(r + 4, id3, cm3);
-        cp_async_wait_group<2>();
-        __syncwarp();
         const int st = r % NS;
+        if (BULK) {
+            mbar_wait(&s_bar[wid][st], (bar_phase >> st) & 1u);
+            bar_phase ^= 1u << st;
+        } else {
+            cp_async_wait_group<2>();
+        }
+        __syncwarp();
         if (STATS) st_staged += CH;
         const uint32_t nz = __ballot_sync(FULL, cme != 0u);
         if (nz == 0u) continue; // no pixel of the block composited any entry of this chunk
         if (STATS && lane == 0) st_walk += __popc(nz);
-        const float4 *q0 = q.a[st], *q1 = q.b[st], *q2 = q.c[st];
+        // record words of entry e: cp.async planes q0[e], q1[e], q2[e]; bulk rows q0[3 e], q0[3 e + 1], q0[3 e + 2]
+        const float4 *q0 = s_a[wid][st], *q1 = BULK ? s_a[wid][st] + 1 : s_b[wid][st], *q2 = BULK ? s_a[wid][st] + 2 : s_c[wid][st];
+        constexpr int RS = BULK ? 3 : 1; // float4 stride between consecutive entries
         s_id[wid][lane] = id_c;
         // ---- phase A: lane = pixel
         uint32_t pm = transpose32(cme, lane);
@@ -930,7 +982,7 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
             const bool two = pm != 0u;
             const int eb = two ? 31 - __clz(pm) : ea;
             pm &= ~(1u << eb);
-            const float4 r0a = q0[ea], r1a = q1[ea], r2a = q2[ea], r0b = q0[eb], r1b = q1[eb], r2b = q2[eb];
+            const float4 r0a = q0[RS * ea], r1a = q1[RS * ea], r2a = q2[RS * ea], r0b = q0[RS * eb], r1b = q1[RS * eb], r2b = q2[RS * eb];
             float ga, gb, sa, sb; // alpha (3D) / g (2D); factor of -v in dL/dsigma resp. dL/dq
             if (MODE == PS_MODE_3D) {
                 float dx, dy;
@@ -968,7 +1020,7 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
         __syncwarp(); // the pair table is complete
         // ---- phase B: lane = entry
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, ms = 0.0f, mx = 0.0f, my = 0.0f, mxx = 0.0f, mxy = 0.0f, myy = 0.0f;
-        const float4 e0 = q0[lane], e1 = q1[lane];
+        const float4 e0 = q0[RS * lane], e1 = q1[RS * lane];
         {
             uint32_t m = cme;
             const float sgx = e0.x - bxf, sgy = e0.y - byf; // mean relative to the block's first pixel centre
@@ -1024,7 +1076,7 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
         }
         __syncwarp(); // before the next chunk's phase A writes the table / s_id again; ring stage st is free as well
     }
-    cp_async_wait_group<0>();
+    if (!BULK) cp_async_wait_group<0>();
     __syncwarp();
     } // task loop
     if (STATS) {
@@ -1194,7 +1246,7 @@ template <typename K>
 unsigned persistent_ctas(K kernel, int slot)
 {
     constexpr int MAX_DEV = 64;
-    static int cached[MAX_DEV][8] = {};
+    static int cached[MAX_DEV][10] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const int di = dev < MAX_DEV ? dev : MAX_DEV - 1;
@@ -1219,13 +1271,15 @@ int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l
     static const bool use_v5 = getenv("PS_BWD_V5") != nullptr; // A/B switch for measurements
     const int mi = g.mode == PS_MODE_3D ? 0 : 1;
     if (l.cmask && !use_v5) { // v6: replay of the contributing pairs the forward recorded
-#define PS_BWD3(MODE, ST, SLOT)                                                                                              \
+#define PS_BWD3(MODE, ST, BK, SLOT)                                                                                          \
         do {                                                                                                                 \
-            const unsigned cap = persistent_ctas(raster_bwd3_kernel<MODE, WPC, ST>, SLOT);                                   \
-            raster_bwd3_kernel<MODE, WPC, ST><<<want < cap ? want : cap, RT_THREADS, 0, s>>>(g, t, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.cmask, l.bcount, acc, l.n_lists, next_task, stats); \
+            const unsigned cap = persistent_ctas(raster_bwd3_kernel<MODE, WPC, ST, BK>, SLOT);                               \
+            raster_bwd3_kernel<MODE, WPC, ST, BK><<<want < cap ? want : cap, RT_THREADS, 0, s>>>(g, t, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.cmask, l.bcount, acc, l.n_lists, next_task, stats); \
         } while (0)
-        if (mi == 0) { if (stats) PS_BWD3(PS_MODE_3D, true, 4); else PS_BWD3(PS_MODE_3D, false, 5); }
-        else { if (stats) PS_BWD3(PS_MODE_2D, true, 6); else PS_BWD3(PS_MODE_2D, false, 7); }
+        static const bool bulk = getenv("PS_BWD_BULK") != nullptr; // A/B switch: records staged by cp.async.bulk (TMA 1-D)
+        if (bulk && !stats) { if (mi == 0) PS_BWD3(PS_MODE_3D, false, true, 8); else PS_BWD3(PS_MODE_2D, false, true, 9); }
+        else if (mi == 0) { if (stats) PS_BWD3(PS_MODE_3D, true, false, 4); else PS_BWD3(PS_MODE_3D, false, false, 5); }
+        else { if (stats) PS_BWD3(PS_MODE_2D, true, false, 6); else PS_BWD3(PS_MODE_2D, false, false, 7); }
 #undef PS_BWD3
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
