@@ -417,7 +417,9 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             PS_TRY_CUDA(dev_alloc(&sv->t.tile_rect, VN, s));
             PS_TRY_CUDA(dev_alloc(&sv->t.tiles_touched, VN, s));
             if (g.mode == PS_MODE_3D) PS_TRY_CUDA(dev_alloc(&sv->t.depth, VN, s));
-            { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, sv->l.offsets, s)); }
+            // the views of every frame (CSR): the 3D projection and the projection backward loop over them per Gaussian
+            PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, background, sv->bg, s));
+            { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, sv->l.offsets, sv->frame_off, sv->frame_views, s)); }
             if (g.mode == PS_MODE_3D) {
                 PS_TRY_CUDA(dev_alloc(&sv->t.order, VN, s));
                 PS_TRY_CUDA(dev_alloc(&sv->t.rank, VN, s));
@@ -468,7 +470,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
                 PS_TRY_LAUNCH(ps_launch_debug_keys(g, sv->t, sv->l, sv->n_work, sv->keys, s));
             }
         }
-        if (save) PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, background, sv->bg, s));
+        if (save && VN == 0) PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, background, sv->bg, s));
         if (npix > 0) {
             if (save) {
                 PS_TRY_CUDA(dev_alloc(&sv->blast, npix, s));

@@ -198,11 +198,11 @@ PS_HD void ps_adapter3d_vjp(const float *row, const float *s, float qn_raw, floa
     out[13] = v_act[13] * o * (1.0f - o);
 }
 
-// Adapter activations + EWA projection of one Gaussian for one camera. Returns 1 if visible.
-// activated != 0: the row already holds scales / quaternion / colours / opacity as gsplat's rasterization() takes
-// them (the legacy PoseSplatter.splat call, src/model.py:342-361): no exp, no q/(|q|+1e-8), no clamp, no sigmoid.
-PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, int H, float near_plane,
-                       float far_plane, float radius_clip, float eps2d, PsRecord *rec, PsProj3dAux *t, int activated = 0)
+// The projection of one Gaussian for one camera = a camera-independent part (adapter activations, rotation, world
+// covariance: ps_gauss3d) followed by a camera-dependent part (ps_view3d).  A frame's six cameras share the first; the
+// kernels that loop over a frame's views compute it once per Gaussian.  Same operations in the same order as before the
+// split: every bit-exact output is unchanged.
+PS_HD void ps_gauss3d(const float *row, int activated, PsRecord *rec, PsProj3dAux *t, float *S /* [6] world covariance */)
 {
     ps_record_clear(rec);
     float o;
@@ -231,7 +231,6 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
     float *M = t->M;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) M[3 * i + j] = psm_mul(R[3 * i + j], t->s[j]);
-    float S[6];
     {
         int idx = 0;
         for (int i = 0; i < 3; ++i)
@@ -239,6 +238,20 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
                 S[idx++] = psm_fma(M[3 * i + 2], M[3 * j + 2],
                                    psm_fma(M[3 * i + 1], M[3 * j + 1], psm_mul(M[3 * i], M[3 * j])));
     }
+}
+
+// camera-dependent part: rec / t hold what ps_gauss3d left (colours, opacity, rotation ...).  Returns 1 if visible.
+PS_HD int ps_view3d(const float *row, const float *S, const float *V, const float *K, int W, int H, float near_plane,
+                    float far_plane, float radius_clip, float eps2d, PsRecord *rec, PsProj3dAux *t)
+{
+    const float o = rec->r1[3];
+    // the camera-dependent fields start from zero for every camera (a Gaussian culled by this camera keeps only its
+    // colours and opacity, whatever an earlier camera of the same frame left here)
+    for (int k = 0; k < 4; ++k) { rec->r0[k] = 0.0f; rec->tile[k] = 0; }
+    rec->r1[0] = rec->r1[1] = rec->r1[2] = 0.0f;
+    rec->r2[3] = 0.0f;
+    rec->low = 0;
+    rec->thr = 0.0f;
     for (int i = 0; i < 3; ++i)
         t->pc[i] = psm_fma(V[4 * i + 2], row[2], psm_fma(V[4 * i + 1], row[1], psm_fma(V[4 * i], row[0], V[4 * i + 3])));
     float zc = t->pc[2];
@@ -321,6 +334,17 @@ PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, 
         rec->tile[2] = rec->tile[0]; rec->tile[3] = rec->tile[1];
     }
     return 1;
+}
+
+// Adapter activations + EWA projection of one Gaussian for one camera. Returns 1 if visible.
+// activated != 0: the row already holds scales / quaternion / colours / opacity as gsplat's rasterization() takes
+// them (the legacy PoseSplatter.splat call, src/model.py:342-361): no exp, no q/(|q|+1e-8), no clamp, no sigmoid.
+PS_HD int ps_project3d(const float *row, const float *V, const float *K, int W, int H, float near_plane,
+                       float far_plane, float radius_clip, float eps2d, PsRecord *rec, PsProj3dAux *t, int activated = 0)
+{
+    float S[6];
+    ps_gauss3d(row, activated, rec, t, S);
+    return ps_view3d(row, S, V, K, W, H, near_plane, far_plane, radius_clip, eps2d, rec, t);
 }
 
 // 2D activations + binning extent. Returns 1 if listed anywhere.

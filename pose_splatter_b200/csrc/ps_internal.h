@@ -52,8 +52,11 @@ struct PsLists {
 };
 
 // every launcher returns the number of kernels it launched (for gpu_launches) or -1 on error
+// frame_off / frame_views (the CSR of ps_launch_frame_csr) != NULL in 3D: one thread per (frame, Gaussian), the
+// camera-independent part of the projection computed once per frame
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
-                      const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s);
+                      const float *Ks, const PsTable &t, int32_t *tile_counts, const int32_t *frame_off,
+                      const int32_t *frame_views, cudaStream_t s);
 // view_frame [V] -> CSR (frame_off [F+1], frame_views [V]); cursor [F] is scratch
 // also keeps a copy of the forward's background colour (bg_saved [3]) for the backward
 int ps_launch_frame_csr(const PsGeometry &g, const int32_t *view_frame, int32_t *frame_off, int32_t *cursor,

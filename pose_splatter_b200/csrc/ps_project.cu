@@ -93,16 +93,76 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
     }
 }
 
+// 3D projection with the camera-independent part hoisted: one thread per (frame, Gaussian) applies the adapter and builds
+// the world covariance ONCE (ps_gauss3d), then projects into every camera of the frame (ps_view3d; the frame's views
+// come from the CSR the forward builds first).  Same records, bit for bit, as one thread per (view, Gaussian).
+__global__ void __launch_bounds__(PS_PROJ_BLOCK)
+project3d_frames_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ frame_off,
+                        const int32_t *__restrict__ frame_views, const float *__restrict__ viewmats,
+                        const float *__restrict__ Ks, PsTable t, int32_t *__restrict__ tile_counts, int use_smem)
+{
+    constexpr int P = 14;
+    extern __shared__ int s_cnt[]; // [n_tiles] when use_smem
+    __shared__ __align__(16) float s_rows[PS_PROJ_BLOCK * P];
+    __shared__ float s_cam[25];
+    const int frame = blockIdx.y;
+    const int g0 = blockIdx.x * PS_PROJ_BLOCK;
+    const int n_rows = min(PS_PROJ_BLOCK, g.N - g0);
+    stage_rows<P>(params + ((size_t)frame * g.N + g0) * P, n_rows, s_rows);
+    __syncthreads();
+    const bool live = (int)threadIdx.x < n_rows;
+    const float *row = s_rows + threadIdx.x * P;
+    PsRecord rec;
+    PsProj3dAux aux;
+    float S[6];
+    if (live) ps_gauss3d(row, g.activated, &rec, &aux, S);
+    const int j0 = frame_off[frame], j1 = frame_off[frame + 1];
+    for (int j = j0; j < j1; ++j) {
+        const int v = frame_views[j];
+        __syncthreads(); // the previous camera's histogram has been flushed, s_cam is free
+        if (threadIdx.x < 25)
+            s_cam[threadIdx.x] = threadIdx.x < 16 ? viewmats[(size_t)v * 16 + threadIdx.x] : Ks[(size_t)v * 9 + threadIdx.x - 16];
+        if (use_smem)
+            for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) s_cnt[i] = 0;
+        __syncthreads();
+        int32_t *cnt_v = tile_counts + (size_t)v * g.n_tiles;
+        if (live) {
+            ps_view3d(row, S, s_cam, s_cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &aux);
+            const size_t idx = (size_t)v * g.N + g0 + threadIdx.x;
+            float4 *dst = PS_REC(t, idx, 0);
+            dst[0] = make_float4(rec.r0[0], rec.r0[1], rec.thr, rec.r1[3]);
+            dst[1] = make_float4(psm_mul(0.5f, rec.r1[0]), rec.r1[1], psm_mul(0.5f, rec.r1[2]), 0.0f);
+            dst[2] = make_float4(rec.r2[0], rec.r2[1], rec.r2[2], 0.0f);
+            dst[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            t.depth[idx] = rec.low;
+            t.tile_rect[idx] = make_uint2((uint32_t)rec.tile[0] | ((uint32_t)rec.tile[1] << 16),
+                                          (uint32_t)rec.tile[2] | ((uint32_t)rec.tile[3] << 16));
+            t.tiles_touched[idx] = (rec.tile[2] - rec.tile[0]) * (rec.tile[3] - rec.tile[1]);
+            for (int ty = rec.tile[1]; ty < rec.tile[3]; ++ty)
+                for (int tx = rec.tile[0]; tx < rec.tile[2]; ++tx)
+                    atomicAdd(use_smem ? &s_cnt[ty * g.tiles_x + tx] : &cnt_v[ty * g.tiles_x + tx], 1);
+        }
+        if (use_smem) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < g.n_tiles; i += PS_PROJ_BLOCK) {
+                const int c = s_cnt[i];
+                if (c) atomicAdd(&cnt_v[i], c);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Backward of the projection / activations. acc row = 9 sums from the rasterizer backward:
 //   3D: v_rgb(3), v_A, v_B, v_C, v_x, v_y, v_opacity        2D: v_rgb(3), sum d_dxr, sum d_dyr, d_theta, d_iax, d_iay, sum G_q
 // ------------------------------------------------------------------------------------------
 // Gradient of one (view, Gaussian) pair w.r.t. its raw parameter row, added into out[P].
 //   r   the raw row, cam  viewmat[16] | K[9] of the view (3D), a  the nine sums of the rasterizer backward
+//   3D: rec / x / S hold the camera-independent part of the projection (ps_gauss3d), computed once per Gaussian by the caller
 template <int MODE>
 __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTable &t, size_t idx, const float *r,
-                                                const float *cam, const float (&a)[9],
-                                                float (&out)[(MODE == PS_MODE_3D) ? 14 : 9])
+                                                const float *cam, const float (&a)[9], PsRecord &rec, PsProj3dAux &x,
+                                                const float *S, float (&out)[(MODE == PS_MODE_3D) ? 14 : 9])
 {
     constexpr int P = (MODE == PS_MODE_3D) ? 14 : 9;
     float o[P];
@@ -122,10 +182,7 @@ __device__ __forceinline__ void project_bwd_row(const PsGeometry &g, const PsTab
         for (int k = 0; k < 3; ++k) o[5 + k] = (r[5 + k] >= 0.0f && r[5 + k] <= 1.0f) ? a[k] : 0.0f;
         o[8] = -a[8] * (1.0f - op);
     } else {
-        PsRecord rec;
-        PsProj3dAux x;
-        const int ok = ps_project3d(r, cam, cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x,
-                                    g.activated);
+        const int ok = ps_view3d(r, S, cam, cam + 16, g.W, g.H, g.near_plane, g.far_plane, g.radius_clip, g.eps2d, &rec, &x);
         // v[14]: gradient w.r.t. the activated values (means | scales | quats | colours | opacity), i.e. what gsplat's
         // backward hands to autograd; the adapter's own vector-Jacobian product maps it to the raw row below
         float v[14];
@@ -252,6 +309,10 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
 #pragma unroll
         for (int k = 0; k < P; ++k) r[k] = __ldg(row + k);
     }
+    PsRecord rec;
+    PsProj3dAux aux;
+    float S[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    if (MODE == PS_MODE_3D && live) ps_gauss3d(r, g.activated, &rec, &aux, S); // once per Gaussian, shared by the frame's cameras
     const int j0 = frame_off[frame], j1 = frame_off[frame + 1];
     for (int j = j0; j < j1; ++j) {
         const int v = frame_views[j];
@@ -271,7 +332,7 @@ project_bwd_kernel(PsGeometry g, const float *__restrict__ params, const int32_t
 #pragma unroll
         for (int k = 0; k < 9; ++k) any = any || (a[k] != 0.0f);
         if (!any) continue;
-        project_bwd_row<MODE>(g, t, idx, r, s_cam, a, out);
+        project_bwd_row<MODE>(g, t, idx, r, s_cam, a, rec, aux, S, out);
     }
     if (peers == nullptr) {
         if (!live) return;
@@ -419,12 +480,21 @@ int ps_launch_adapter3d_probe(const float *rows, int n, const float *v_act, floa
 }
 
 int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *view_frame, const float *viewmats,
-                      const float *Ks, const PsTable &t, int32_t *tile_counts, cudaStream_t s)
+                      const float *Ks, const PsTable &t, int32_t *tile_counts, const int32_t *frame_off,
+                      const int32_t *frame_views, cudaStream_t s)
 {
     if (g.N == 0 || g.V == 0) return 0;
     dim3 grid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.V);
     const int use_smem = g.n_tiles <= PS_HIST_SMEM_TILES;
     const size_t dyn = use_smem ? (size_t)g.n_tiles * sizeof(int) : 0;
+    static const bool per_view = getenv("PS_PROJECT_PER_VIEW") != nullptr; // A/B switch for measurements
+    if (g.mode == PS_MODE_3D && frame_off && !per_view && g.F > 0) {
+        // a view whose frame id is out of range is in no frame's list: it must still read as "nothing listed"
+        if (cudaMemsetAsync(t.tiles_touched, 0, (size_t)g.V * g.N * sizeof(int32_t), s) != cudaSuccess) return -1;
+        dim3 fgrid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.F);
+        project3d_frames_kernel<<<fgrid, PS_PROJ_BLOCK, dyn, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, tile_counts, use_smem);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     if (g.mode == PS_MODE_3D)
         project_kernel<PS_MODE_3D><<<grid, PS_PROJ_BLOCK, dyn, s>>>(g, params, view_frame, viewmats, Ks, t, tile_counts, use_smem);
     else
