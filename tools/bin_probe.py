@@ -1,5 +1,5 @@
 """Stage times of a few forward(+backward) passes at a reduced batch, for profiling runs (ncu) of single kernels.
-    python tools/bin_probe.py [workload] [frames] [reps] [fwd|fwdbwd]"""
+    python tools/bin_probe.py [workload] [frames] [reps] [fwd|fwdbwd] [cameras]"""
 import sys
 from pathlib import Path
 
@@ -12,8 +12,9 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 bwd = (sys.argv[4] if len(sys.argv) > 4 else "fwdbwd") == "fwdbwd"
+cams = int(sys.argv[5]) if len(sys.argv) > 5 else 6
 dev = torch.device("cuda", 0)
-d = synth.make_views(wl, frames, 6, seed=3)
+d = synth.make_views(wl, frames, cams, seed=3)
 W, H, mode = d["width"], d["height"], d["mode"]
 p, vf, vm, Ks = (d[k].to(dev) for k in ("params", "view_frame", "viewmats", "Ks"))
 V = len(vf)
