@@ -64,10 +64,12 @@ __device__ __forceinline__ uint32_t scan256_exclusive(uint32_t *s, uint32_t *s_t
 template <typename IdT>
 __global__ void __launch_bounds__(RT)
 depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__restrict__ touched,
-                  uint32_t *__restrict__ order, uint32_t *__restrict__ rank, uint32_t *gscratch)
+                  uint32_t *__restrict__ order, uint32_t *__restrict__ rank, uint32_t *gscratch,
+                  const int32_t *__restrict__ only_flagged)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ uint32_t s_hist[256], s_tmp[8], s_minmax[2];
+    if (only_flagged && only_flagged[blockIdx.x] == 0) return; // this view was ranked by the bucket kernel
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t base = (size_t)blockIdx.x * N;
     // per-(warp, digit) counts, then output cursors (< N: fits IdT); two matrices: this pass's and the next's
@@ -183,6 +185,111 @@ depth_rank_kernel(int N, const uint32_t *__restrict__ depth, const int32_t *__re
         order[base + r] = gid;
         rank[base + gid] = (uint32_t)r;
     }
+}
+
+// Depth ranking by one bucket pass (the common case).  The depth words of a view lie in a narrow range, so a
+// monotonic linear map onto NB >= N buckets leaves ~1 key per bucket: count (shared-memory atomics, which also give
+// every key a slot inside its bucket), scan, place, and repair the order inside the few buckets that hold more than
+// one key with an insertion sort on (depth word, Gaussian index) -- the order a stable sort of the depth words gives.
+// Four sweeps over the keys and five CTA barriers instead of three radix passes of scans and match-any scatters.
+// A view with a crowded bucket (> RANK_BUCKET_LIMIT equal or nearly equal depths) sets its flag and is ranked by
+// the radix kernel afterwards.
+constexpr int RANK_BUCKET_LIMIT = 32;
+
+__global__ void __launch_bounds__(RT)
+depth_rank_bucket_kernel(int N, int NB, const uint32_t *__restrict__ depth, const int32_t *__restrict__ touched,
+                         uint32_t *__restrict__ order, uint32_t *__restrict__ rank, int32_t *__restrict__ fallback)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ uint32_t s_minmax[2], s_wsum[RW], s_nunlisted, s_bad;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(dyn);             // [NB + 1] counts, then exclusive bases
+    uint32_t *tkey = cnt + NB + 1;                                 // [N] keys in bucket order
+    uint16_t *tgid = reinterpret_cast<uint16_t *>(tkey + N);       // [N] Gaussians in bucket order
+    uint16_t *slot = tgid + ((N + 1) & ~1);                        // [N] slot of every key inside its bucket
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t base = (size_t)blockIdx.x * N;
+    for (int i = tid; i <= NB; i += RT) cnt[i] = 0u;
+    if (tid == 0) { s_minmax[0] = 0xffffffffu; s_minmax[1] = 0u; s_nunlisted = 0u; s_bad = 0u; }
+    __syncthreads();
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int i = tid; i < N; i += RT) {
+        if (touched[base + i] > 0) { const uint32_t key = depth[base + i]; mn = min(mn, key); mx = max(mx, key); }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(FULL, mn, d));
+        mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+    }
+    if (lane == 0) { atomicMin(&s_minmax[0], mn); atomicMax(&s_minmax[1], mx); }
+    __syncthreads();
+    mn = s_minmax[0]; mx = s_minmax[1];
+    const unsigned long long range = (mx >= mn) ? (unsigned long long)(mx - mn) : 0ull;
+    const unsigned long long scale = ((unsigned long long)NB << 32) / (range + 1ull); // bucket = (key - mn) * scale >> 32 < NB
+    auto bucket_of = [&](uint32_t key) -> uint32_t { return (uint32_t)(((unsigned long long)(key - mn) * scale) >> 32); };
+    for (int i = tid; i < N; i += RT) {
+        uint32_t sl;
+        if (touched[base + i] > 0) sl = atomicAdd(&cnt[bucket_of(depth[base + i])], 1u);
+        else sl = atomicAdd(&s_nunlisted, 1u);
+        slot[i] = (uint16_t)sl;
+    }
+    __syncthreads();
+    {   // exclusive scan of the NB counts (NB is a multiple of RT): a contiguous run per thread
+        const int per = NB / RT;
+        uint32_t sum = 0, big = 0;
+        for (int k = 0; k < per; ++k) { const uint32_t c = cnt[tid * per + k]; sum += c; big = max(big, c); }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) s_wsum[wid] = incl;
+        if (big > (uint32_t)RANK_BUCKET_LIMIT) s_bad = 1u;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int w = 0; w < RW; ++w) run += (w < wid) ? s_wsum[w] : 0u;
+        for (int k = 0; k < per; ++k) { const uint32_t c = cnt[tid * per + k]; cnt[tid * per + k] = run; run += c; }
+        if (tid == RT - 1) cnt[NB] = run; // number of listed Gaussians
+    }
+    __syncthreads();
+    if (s_bad) { // crowded bucket: leave this view to the radix kernel
+        if (tid == 0) fallback[blockIdx.x] = 1;
+        return;
+    }
+    const uint32_t n_listed = cnt[NB];
+    for (int i = tid; i < N; i += RT) {
+        uint32_t pos, key = 0xffffffffu;
+        if (touched[base + i] > 0) { key = depth[base + i]; pos = cnt[bucket_of(key)] + slot[i]; }
+        else pos = n_listed + slot[i];
+        tkey[pos] = key;
+        tgid[pos] = (uint16_t)i;
+    }
+    __syncthreads();
+    {   // buckets holding several keys: order by (depth word, Gaussian index)
+        const int per = NB / RT;
+        for (int k = 0; k < per; ++k) {
+            const uint32_t b0 = cnt[tid * per + k], b1 = cnt[tid * per + k + 1];
+            for (uint32_t a = b0 + 1; a < b1; ++a) {
+                const uint32_t ka = tkey[a];
+                const uint16_t ga = tgid[a];
+                uint32_t j = a;
+                while (j > b0 && (tkey[j - 1] > ka || (tkey[j - 1] == ka && tgid[j - 1] > ga))) {
+                    tkey[j] = tkey[j - 1];
+                    tgid[j] = tgid[j - 1];
+                    --j;
+                }
+                tkey[j] = ka;
+                tgid[j] = ga;
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < N; r += RT) {
+        const uint32_t gid = (uint32_t)tgid[r];
+        order[base + r] = gid;
+        rank[base + gid] = (uint32_t)r;
+    }
+    if (tid == 0) fallback[blockIdx.x] = 0;
 }
 
 // Exclusive scan of the T list lengths in place + size-class histogram of the non-empty lists, three launches:
@@ -623,21 +730,42 @@ size_t ps_rank_scratch_elems(const PsGeometry &g)
     return (size_t)g.V * 4 * (size_t)g.N;
 }
 
-int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, cudaStream_t s)
+// buckets of the one-pass ranking: the power of two >= N, between RT and 16384; 0 = N too large for its shared memory
+static int rank_buckets(int N)
+{
+    if (N > 65535) return 0;
+    int nb = RT;
+    while (nb < N && nb < 16384) nb <<= 1;
+    const size_t dyn = (size_t)(nb + 1) * 4 + (size_t)N * 4 + (size_t)((N + 1) & ~1) * 2 + (size_t)N * 2;
+    return dyn + 1024 <= SMEM_LIMIT ? nb : 0;
+}
+
+int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, int32_t *flags, cudaStream_t s)
 {
     if (g.mode != PS_MODE_3D || g.N == 0 || g.V == 0) return 0;
+    int launches = 0;
+    static const bool radix_only = getenv("PS_RANK_RADIX") != nullptr; // A/B switch for measurements
+    const int nb = (flags && !radix_only) ? rank_buckets(g.N) : 0;
+    const int32_t *only_flagged = nullptr;
+    if (nb) {
+        const size_t dyn = (size_t)(nb + 1) * 4 + (size_t)g.N * 4 + (size_t)((g.N + 1) & ~1) * 2 + (size_t)g.N * 2;
+        if (cudaFuncSetAttribute(depth_rank_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
+        depth_rank_bucket_kernel<<<g.V, RT, dyn, s>>>(g.N, nb, t.depth, t.tiles_touched, t.order, t.rank, flags);
+        only_flagged = flags; // the radix kernel below only ranks the views the bucket pass gave up on
+        ++launches;
+    }
     if (ps_rank_scratch_elems(g) == 0) {
         const size_t dyn = rank_smem_bytes(g.N) + RANK_CNT_SMEM16;
         if (cudaFuncSetAttribute(depth_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
             return -1;
-        depth_rank_kernel<uint16_t><<<g.V, RT, dyn, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, nullptr);
+        depth_rank_kernel<uint16_t><<<g.V, RT, dyn, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, nullptr, only_flagged);
     } else {
         if (!scratch) return -1;
         if (cudaFuncSetAttribute(depth_rank_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_CNT_SMEM32) != cudaSuccess)
             return -1;
-        depth_rank_kernel<uint32_t><<<g.V, RT, RANK_CNT_SMEM32, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, scratch);
+        depth_rank_kernel<uint32_t><<<g.V, RT, RANK_CNT_SMEM32, s>>>(g.N, t.depth, t.tiles_touched, t.order, t.rank, scratch, only_flagged);
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    return cudaGetLastError() == cudaSuccess ? launches + 1 : -1;
 }
 
 size_t ps_scan_scratch_elems(const PsGeometry &g) { return (size_t)(g.V * g.n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }

@@ -363,6 +363,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
 
     int rc = 0;
     uint32_t *rank_scratch = nullptr;
+    int32_t *rank_flags = nullptr;
     long long *scan_scratch = nullptr;
     int32_t *csr_cursor = nullptr;
     uint8_t *mask_bytes = nullptr;
@@ -425,8 +426,9 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
                 PS_TRY_CUDA(dev_alloc(&sv->t.rank, VN, s));
                 const size_t ns = ps_rank_scratch_elems(g);
                 if (ns) PS_TRY_CUDA(dev_alloc(&rank_scratch, ns, s));
+                PS_TRY_CUDA(dev_alloc(&rank_flags, (size_t)g.V, s));
                 StageTimer tm(ctx, PS_STAGE_RANK, s);
-                PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, s));
+                PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, rank_flags, s));
             }
             { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, sv->mail.d, s)); }
             if (sync_free) {
@@ -485,6 +487,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
     }
 out:
     dev_free(rank_scratch, s);
+    dev_free(rank_flags, s);
     dev_free(scan_scratch, s);
     dev_free(mask_bytes, s);
     dev_free(sv->l.fill, s); dev_free(sv->l.slots, s);

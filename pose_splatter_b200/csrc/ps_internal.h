@@ -70,7 +70,8 @@ int ps_launch_peer_sum(const float *stage, int world, size_t n, float *out, cuda
 
 // binning (ps_bin.cu)
 size_t ps_rank_scratch_elems(const PsGeometry &g); // uint32 elements of global scratch the ranking needs (0 if it fits smem)
-int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, cudaStream_t s);
+// flags [V] int32 scratch (or NULL = radix ranking only): views the one-pass bucket ranking left to the radix kernel
+int ps_launch_depth_rank(const PsGeometry &g, const PsTable &t, uint32_t *scratch, int32_t *flags, cudaStream_t s);
 // exclusive scan of the T counts in place (offsets[T] = M), size classes; mailbox[0] = M, mailbox[1] = non-empty lists
 size_t ps_scan_scratch_elems(const PsGeometry &g); // int64 elements of scratch the scan needs
 int ps_launch_scan_lists(const PsGeometry &g, const PsLists &l, long long *chunk_scratch, int64_t *mailbox, cudaStream_t s);

@@ -486,6 +486,9 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             const int eb = two ? __ffs(pm) - 1 : ea;
             pm &= pm - 1;
             const float4 r0a = q0[ea], r1a = q1[ea], r0b = q0[eb], r1b = q1[eb];
+            // the colours are fetched with the rest (95 % of the candidates contribute): their latency hides behind the
+            // alpha evaluation instead of stalling the compositing
+            const float4 r2a = q2[ea], r2b = q2[eb];
             if (MODE == PS_MODE_3D) {
                 float dx, dy;
                 const float sga = ps_sigma3d(r0a.x, r0a.y, r1a.x, r1a.y, r1a.z, pxf, pyf, &dx, &dy);
@@ -500,9 +503,8 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                     if (nT <= PS_T_STOP_3D) {
                         done = true;
                     } else {
-                        const float4 r2 = q2[ea];
                         const float vis = psm_mul(aa, T);
-                        cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                        cr = psm_fma(vis, r2a.x, cr); cg = psm_fma(vis, r2a.y, cg); cb = psm_fma(vis, r2a.z, cb);
                         Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1; cmp |= 1u << ea;
                     }
                 }
@@ -511,9 +513,8 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                     if (nT <= PS_T_STOP_3D) {
                         done = true;
                     } else {
-                        const float4 r2 = q2[eb];
                         const float vis = psm_mul(ab, T);
-                        cr = psm_fma(vis, r2.x, cr); cg = psm_fma(vis, r2.y, cg); cb = psm_fma(vis, r2.z, cb);
+                        cr = psm_fma(vis, r2b.x, cr); cg = psm_fma(vis, r2b.y, cg); cb = psm_fma(vis, r2b.z, cb);
                         Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1; cmp |= 1u << eb;
                     }
                 }
@@ -527,14 +528,12 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                 const float gva = psm_mul(r0a.w, psm_exp2_inrange(psm_mul(-qa, 0x1.715476p+0f)));
                 const float gvb = psm_mul(r0b.w, psm_exp2_inrange(psm_mul(-qb, 0x1.715476p+0f)));
                 if (ina) {
-                    const float4 r2a = q2[ea];
                     const float contrib = psm_mul(gva, T);
                     cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
                     Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1; cmp |= 1u << ea;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
                 if (inb && !done) {
-                    const float4 r2b = q2[eb];
                     const float contrib = psm_mul(gvb, T);
                     cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
                     Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1; cmp |= 1u << eb;

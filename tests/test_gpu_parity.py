@@ -396,3 +396,18 @@ def test_bad_inputs_are_rejected_or_guarded():
     assert torch.isfinite(pr.grad).all()
     rgb0, alpha0 = batched.render_views("3d", p, vf[:1], W, H, bg, d["viewmats"][:1].to(DEV), d["Ks"][:1].to(DEV))
     assert torch.equal(rgb0[0], rgb[0]) and torch.equal(alpha0[0], alpha[0])
+
+
+def test_3d_equal_depths_crowded_buckets_and_ties():
+    """Depth ties: hundreds of Gaussians at exactly the same camera depth (identical means) and others spread out.  The
+    one-pass bucket ranking gives such a view to the radix kernel (crowded bucket); either way equal depth words must keep
+    Gaussian order -- the sorted keys / values are compared bit for bit with the oracle's stable sort."""
+    _, _, _, synth = _mods()
+    W, H = 144, 128
+    vm, Ks = synth.ring_cameras(6, ds=8.0)
+    p = synth.gaussians_3d(1200, 31)
+    p[100:500, 0:3] = p[100, 0:3]          # 400 identical means: identical depth words in every view
+    p[600:640, 0:3] = p[600, 0:3]          # a second, smaller tie group (stays below the bucket limit in most views)
+    p[:, 3:6] += 0.5
+    d = dict(params=p[None], view_frame=torch.zeros(3, dtype=torch.int32))
+    _compare("3d", d["params"], d["view_frame"], W, H, (0.1, 0.2, 0.3), vm[:3], Ks[:3])

@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = Path(__file__).resolve().parent.parent
-SLICE = "test_3d_single_view or test_3d_batched_views_two_frames or ref2d_random_96x80 or test_2d_projected_views_batched " \
+SLICE = "test_3d_single_view or test_3d_batched_views_two_frames or test_3d_equal_depths or ref2d_random_96x80 or test_2d_projected_views_batched " \
         "or test_3d_adversarial_randn_eye_viewmat or test_empty_input_is_background or test_autograd_function_matches_raw_backward"
 
 VARIANTS = {
@@ -22,6 +22,7 @@ VARIANTS = {
     "fwd_v4": {"PS_FWD_V4": "1"},                             # all-lanes walk in 3D as well
     "force_sync": {"PS_FORCE_SYNC": "1"},                     # small calls sized exactly from the mailbox
     "project_per_view": {"PS_PROJECT_PER_VIEW": "1"},         # one thread per (view, Gaussian) projection
+    "rank_radix": {"PS_RANK_RADIX": "1"},                     # depth ranking by the radix kernel only
 }
 
 
