@@ -177,6 +177,7 @@ ssim_fwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
     };
     fetch(0);
     park();
+#pragma unroll 1 // three unrolled channels would be 4 k instructions (64 KB of code): keep the body in the instruction cache
     for (int ch = 0; ch < 3; ++ch) {
         __syncthreads(); // sp / sq hold channel ch; the previous channel's vertical pass is done with sh
         if (ch + 1 < 3) fetch(ch + 1);
@@ -303,6 +304,7 @@ loss_bwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
     };
     fetch(0);
     park();
+#pragma unroll 1
     for (int ch = 0; ch < 3; ++ch) {
         __syncthreads();
         if (ch + 1 < 3) fetch(ch + 1);
