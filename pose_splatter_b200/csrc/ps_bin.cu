@@ -203,33 +203,49 @@ depth_rank_bucket_kernel(int N, int NB, const uint32_t *__restrict__ depth, cons
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ uint32_t s_minmax[2], s_wsum[RW], s_nunlisted, s_bad;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(dyn);             // [NB + 1] counts, then exclusive bases
-    uint32_t *tkey = cnt + NB + 1;                                 // [N] keys in bucket order
-    uint16_t *tgid = reinterpret_cast<uint16_t *>(tkey + N);       // [N] Gaussians in bucket order
+    uint32_t *keys = cnt + NB + 1;                                 // [N] depth words by Gaussian (0xffffffff = not listed)
+    uint16_t *tgid = reinterpret_cast<uint16_t *>(keys + N);       // [N] Gaussians in bucket order
     uint16_t *slot = tgid + ((N + 1) & ~1);                        // [N] slot of every key inside its bucket
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t base = (size_t)blockIdx.x * N;
     for (int i = tid; i <= NB; i += RT) cnt[i] = 0u;
     if (tid == 0) { s_minmax[0] = 0xffffffffu; s_minmax[1] = 0u; s_nunlisted = 0u; s_bad = 0u; }
-    __syncthreads();
+    // the only sweep over global memory: independent loads, four elements in flight per thread
     uint32_t mn = 0xffffffffu, mx = 0u;
-    for (int i = tid; i < N; i += RT) {
-        if (touched[base + i] > 0) { const uint32_t key = depth[base + i]; mn = min(mn, key); mx = max(mx, key); }
+    for (int i0 = tid; i0 < N; i0 += 4 * RT) {
+        uint32_t k4[4];
+        int t4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * RT;
+            k4[u] = i < N ? __ldg(depth + base + i) : 0u;
+            t4[u] = i < N ? __ldg(touched + base + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * RT;
+            if (i >= N) continue;
+            const bool listed = t4[u] > 0;
+            keys[i] = listed ? k4[u] : 0xffffffffu;
+            if (listed) { mn = min(mn, k4[u]); mx = max(mx, k4[u]); }
+        }
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         mn = min(mn, __shfl_xor_sync(FULL, mn, d));
         mx = max(mx, __shfl_xor_sync(FULL, mx, d));
     }
+    __syncthreads(); // s_minmax and cnt are initialised
     if (lane == 0) { atomicMin(&s_minmax[0], mn); atomicMax(&s_minmax[1], mx); }
     __syncthreads();
     mn = s_minmax[0]; mx = s_minmax[1];
+    // a listed depth word is never 0xffffffff (that is a NaN): the marker cannot collide with a key
     const unsigned long long range = (mx >= mn) ? (unsigned long long)(mx - mn) : 0ull;
     const unsigned long long scale = ((unsigned long long)NB << 32) / (range + 1ull); // bucket = (key - mn) * scale >> 32 < NB
     auto bucket_of = [&](uint32_t key) -> uint32_t { return (uint32_t)(((unsigned long long)(key - mn) * scale) >> 32); };
     for (int i = tid; i < N; i += RT) {
-        uint32_t sl;
-        if (touched[base + i] > 0) sl = atomicAdd(&cnt[bucket_of(depth[base + i])], 1u);
-        else sl = atomicAdd(&s_nunlisted, 1u);
+        const uint32_t key = keys[i];
+        const uint32_t sl = key != 0xffffffffu ? atomicAdd(&cnt[bucket_of(key)], 1u) : atomicAdd(&s_nunlisted, 1u);
         slot[i] = (uint16_t)sl;
     }
     __syncthreads();
@@ -258,10 +274,8 @@ depth_rank_bucket_kernel(int N, int NB, const uint32_t *__restrict__ depth, cons
     }
     const uint32_t n_listed = cnt[NB];
     for (int i = tid; i < N; i += RT) {
-        uint32_t pos, key = 0xffffffffu;
-        if (touched[base + i] > 0) { key = depth[base + i]; pos = cnt[bucket_of(key)] + slot[i]; }
-        else pos = n_listed + slot[i];
-        tkey[pos] = key;
+        const uint32_t key = keys[i];
+        const uint32_t pos = key != 0xffffffffu ? cnt[bucket_of(key)] + slot[i] : n_listed + slot[i];
         tgid[pos] = (uint16_t)i;
     }
     __syncthreads();
@@ -270,15 +284,16 @@ depth_rank_bucket_kernel(int N, int NB, const uint32_t *__restrict__ depth, cons
         for (int k = 0; k < per; ++k) {
             const uint32_t b0 = cnt[tid * per + k], b1 = cnt[tid * per + k + 1];
             for (uint32_t a = b0 + 1; a < b1; ++a) {
-                const uint32_t ka = tkey[a];
                 const uint16_t ga = tgid[a];
+                const uint32_t ka = keys[ga];
                 uint32_t j = a;
-                while (j > b0 && (tkey[j - 1] > ka || (tkey[j - 1] == ka && tgid[j - 1] > ga))) {
-                    tkey[j] = tkey[j - 1];
-                    tgid[j] = tgid[j - 1];
+                while (j > b0) {
+                    const uint16_t gp = tgid[j - 1];
+                    const uint32_t kp = keys[gp];
+                    if (!(kp > ka || (kp == ka && gp > ga))) break;
+                    tgid[j] = gp;
                     --j;
                 }
-                tkey[j] = ka;
                 tgid[j] = ga;
             }
         }
