@@ -410,7 +410,7 @@ def run_measurements(args, world, rank, local, dev):
             out.setdefault("also", {})["split_frames"] = leg
     if args.workload == "c2" and not args.no_secondary and not args.n and not args.split_frames and not args.forward_only:
         # the metric names two configurations; the 2D one (BASELINE.json configs[2]) rides along, briefly
-        other = measure(args, "c3", max(2, min(3, args.steps)), world, rank, local, dev, primary=False)
+        other = measure(args, "c3", max(3, min(6, args.steps)), world, rank, local, dev, primary=False)
         if rank == 0:
             out.setdefault("also", {})["c3"] = {k: other[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline",
                                                                       "stage_ms_per_step", "pairs", "per_kernel")}
