@@ -7,7 +7,8 @@ import json
 import subprocess
 import sys
 
-KEYS = {"project_kernel": "project", "depth_rank_kernel": "depth_rank", "partition_kernel": "partition",
+KEYS = {"project_kernel": "project", "project3d_frames_kernel": "project", "depth_rank_bucket_kernel": "depth_rank",
+        "depth_rank_kernel": "depth_rank_radix_fallback", "partition_kernel": "partition",
         "sort_lists_kernel": "sort_lists", "sort_split_kernel": "sort_split", "block_lists_kernel": "block_lists",
         "raster_fwd6_kernel": "raster_fwd", "raster_fwd_kernel": "raster_fwd", "raster_bwd3_kernel": "raster_bwd",
         "raster_bwd2_kernel": "raster_bwd_v5", "project_bwd_kernel": "project_bwd", "fill_empty_kernel": "fill_empty",
