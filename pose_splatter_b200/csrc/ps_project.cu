@@ -96,7 +96,8 @@ project_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__
 // 3D projection with the camera-independent part hoisted: one thread per (frame, Gaussian) applies the adapter and builds
 // the world covariance ONCE (ps_gauss3d), then projects into every camera of the frame (ps_view3d; the frame's views
 // come from the CSR the forward builds first).  Same records, bit for bit, as one thread per (view, Gaussian).
-__global__ void __launch_bounds__(PS_PROJ_BLOCK)
+template <int MINB> // CTAs per SM the register allocation is bounded for
+__global__ void __launch_bounds__(PS_PROJ_BLOCK, MINB)
 project3d_frames_kernel(PsGeometry g, const float *__restrict__ params, const int32_t *__restrict__ frame_off,
                         const int32_t *__restrict__ frame_views, const float *__restrict__ viewmats,
                         const float *__restrict__ Ks, PsTable t, int32_t *__restrict__ tile_counts, int use_smem)
@@ -492,7 +493,10 @@ int ps_launch_project(const PsGeometry &g, const float *params, const int32_t *v
         // a view whose frame id is out of range is in no frame's list: it must still read as "nothing listed"
         if (cudaMemsetAsync(t.tiles_touched, 0, (size_t)g.V * g.N * sizeof(int32_t), s) != cudaSuccess) return -1;
         dim3 fgrid((g.N + PS_PROJ_BLOCK - 1) / PS_PROJ_BLOCK, g.F);
-        project3d_frames_kernel<<<fgrid, PS_PROJ_BLOCK, dyn, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, tile_counts, use_smem);
+        static const int minb = getenv("PS_PROJ_MINB") ? atoi(getenv("PS_PROJ_MINB")) : 4; // A/B switch for measurements
+        if (minb == 3) project3d_frames_kernel<3><<<fgrid, PS_PROJ_BLOCK, dyn, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, tile_counts, use_smem);
+        else if (minb == 5) project3d_frames_kernel<5><<<fgrid, PS_PROJ_BLOCK, dyn, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, tile_counts, use_smem);
+        else project3d_frames_kernel<4><<<fgrid, PS_PROJ_BLOCK, dyn, s>>>(g, params, frame_off, frame_views, viewmats, Ks, t, tile_counts, use_smem);
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     if (g.mode == PS_MODE_3D)
