@@ -427,12 +427,13 @@ def per_kernel_traffic(wl, mode, V, N, M, n_lists, stats_all, stage_ms):
     alg = {
         "project": rows_in + VN * (64 + 8 + 4 + (4 if mode == "3d" else 0)),
         "partition": VN * (4 + 8 + 32 + (4 if mode == "3d" else 0)) + M * 4,
-        "sort_split": M * (8 if mode == "3d" else 4) + f["entries_staged"] * 4,
+        "sort_lists": M * (8 if mode == "3d" else 4) + M * 4,
+        "block_lists": M * 36 + f["entries_staged"] * 4,
         "raster_fwd": f["entries_staged"] * 52 + n_lists * 256 * 28,
         "raster_bwd": b["entries_staged"] * 52 + n_lists * 256 * 24 + b["entries_walked"] * 36,
         "project_bwd": VN * (4 + 36 + 64) + 2 * rows_in,
     }
-    stage_of = {"project": "project", "partition": "partition", "sort_split": "sort", "raster_fwd": "raster_fwd",
+    stage_of = {"project": "project", "partition": "partition", "sort_lists": "sort", "block_lists": "blocks", "raster_fwd": "raster_fwd",
                 "raster_bwd": "raster_bwd", "project_bwd": "project_bwd"}
     out = {}
     for k, a in alg.items():
@@ -520,21 +521,29 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
     h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     staged = {}
 
+    # three persistent device staging sets, reused round-robin: no allocator traffic inside the timed loop (a
+    # cudaMalloc issued by the caching allocator for a side stream synchronises the device and stalls the pipeline:
+    # measured as a step time that doubled on some runs)
+    n_stage = 3
+    stage_dev = [{name: torch.empty_like(v, device=dev) for name, v in host[0].items()} for _ in range(n_stage)]
+    stage_free = [None] * n_stage  # event recorded on the main stream after the step that consumed the set
+
     def stage_inputs(k):
-        main = torch.cuda.current_stream(dev)
+        j = k % n_stage
         with torch.cuda.stream(h2d_stream):
-            t = {name: v.to(dev, non_blocking=True) for name, v in host[k % n_sets].items()}
+            if stage_free[j] is not None:
+                h2d_stream.wait_event(stage_free[j])
+            for name, v in host[k % n_sets].items():
+                stage_dev[j][name].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(h2d_stream)
-        for v in t.values():
-            v.record_stream(main)
-        staged[k] = (t, ev)
+        staged[k] = (stage_dev[j], ev, j)
 
     def step_e2e(k, last=False):
         main = torch.cuda.current_stream(dev)
         if k not in staged:
             stage_inputs(k)
-        t, ev = staged.pop(k)
+        t, ev, slot_j = staged.pop(k)
         if not last:
             stage_inputs(k + 1)
         main.wait_event(ev)
@@ -549,6 +558,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                 d2h_stream.wait_event(done)
                 img_host[k % 2].copy_(img, non_blocking=True)
             img.record_stream(d2h_stream)
+            stage_free[slot_j] = done
             return
         # public API: forward + vector-Jacobian product with the metric's fixed cotangents (no autograd graph: the
         # cotangent of L = sum(w_rgb * rgb) + sum(w_a * alpha) is w itself), loss value from the rendered images
@@ -572,6 +582,7 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         g.record_stream(d2h_stream)
         gnorm.record_stream(d2h_stream)
         lossd.record_stream(d2h_stream)
+        stage_free[slot_j] = done
 
     def drain_e2e():
         torch.cuda.current_stream(dev).wait_stream(d2h_stream)
@@ -627,11 +638,9 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
         e2e_cfg["grad_to_host"] = False
     # copies alone (no kernels), all ranks at once: what the host side can deliver per step
     def copies_only(k, last=False):
-        main = torch.cuda.current_stream(dev)
         with torch.cuda.stream(h2d_stream):
-            t = {name: v.to(dev, non_blocking=True) for name, v in host[k % n_sets].items()}
-        for v in t.values():
-            v.record_stream(main)
+            for name, v in host[k % n_sets].items():
+                stage_dev[k % n_stage][name].copy_(v, non_blocking=True)
     for k in range(2):
         copies_only(k)
     drain_e2e()
@@ -710,17 +719,21 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                "work": f"M={M} list entries in {n_lists} non-empty (view,tile) lists, {VN} (view,Gaussian) records",
                "project": {"achieved": proj_bytes / (stage_ms['project'][0] * 1e-3) / 1e9 if stage_ms['project'][0] else None,
                            "unit": "GB/s", "avg_launch_ms": stage_ms["project"][0]}}
-    # the HBM-side kernel of the binning: sort + block split (sort_split_kernel).  Algorithmic bytes per tile-list entry:
-    # 4 (slot word in) + 4 (depth-order gather, 3D) + 4 per block-list entry written
-    blk_ms = stage_ms["sort"][0]
+    # the HBM-bound kernel of the path: block_lists (default binning mode "gather").  Algorithmic bytes per tile-list entry:
+    # 4 (list id) + 32 (the two cull words of the splat record) + 4 per block-list entry written
+    blk_ms = stage_ms["blocks"][0]
     blk_entries = stats_all["fwd"]["entries_staged"]
-    blk_bytes = M * (8 if mode == "3d" else 4) + blk_entries * 4
-    roof_hbm = {"bound": "hbm", "kernel": "sort_split", "achieved": blk_bytes / (blk_ms * 1e-3) / 1e9 if blk_ms else None,
+    blk_bytes = M * 36 + blk_entries * 4
+    blk_traffic = ncu_traffic(wl, "block_lists")
+    roof_hbm = {"bound": "hbm", "kernel": "block_lists", "achieved": blk_bytes / (blk_ms * 1e-3) / 1e9 if blk_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "frac": (blk_bytes / (blk_ms * 1e-3) / 1e9) / hbm_peak if blk_ms else None,
-                "traffic": ncu_traffic(wl, "sort_split"), "peak_source": hbm_src, "algorithmic_bytes": blk_bytes,
-                "work": f"{M} tile-list slot words in + ~{blk_entries} block-list entries x 4 B out (staged entries, rounded up to chunks of 32)",
+                "traffic": blk_traffic, "peak_source": hbm_src, "algorithmic_bytes": blk_bytes,
+                "frac_on_dram_traffic": (blk_traffic / (blk_ms * 1e-3) / 1e9) / hbm_peak if (blk_ms and blk_traffic) else None,
+                "work": f"{M} tile-list entries x 36 B in + ~{blk_entries} block-list entries x 4 B out",
                 "avg_launch_ms": blk_ms,
-                "note": "work list + sort + block split of every list in one kernel, no record gathers; latency bound (DESIGN.md section 7)"}
+                "note": "DRAM traffic is above the algorithmic bytes because a 32-byte gather costs a 64-byte DRAM access and records are "
+                        "shared by tiles that run far apart; the two binning modes that avoid the gathers (PS_BIN_MODE=bytes|split) remove "
+                        "that traffic but lose end to end (DESIGN.md section 7)"}
     per_kernel = per_kernel_traffic(wl, mode, V, args.n or cfg["n"], M, n_lists, stats_all, stage_ms)
     out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
