@@ -444,10 +444,10 @@ def per_kernel_traffic(wl, mode, V, N, M, n_lists, stats_all, stage_ms):
     return out
 
 
-def ncu_traffic(wl, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload, or None."""
+def ncu_traffic(wl, kernel, field="dram_bytes_per_launch"):
+    """DRAM bytes per launch (or another field) of `kernel` from the committed ncu --set full capture of this workload, or None."""
     try:
-        return json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())[wl][kernel]["dram_bytes_per_launch"]
+        return json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())[wl][kernel][field]
     except Exception:
         return None
 
@@ -698,7 +698,14 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                "MEASURED_PEAKS.json has no FP32 figure; no tensor cores on this path",
                 "work": f"counters of {kname} itself (same kernel, STATS template path): {stats['pairs_evaluated']} evaluated pairs x "
                         f"{FLOPS_EVAL[dom]:.0f} + {stats['pairs_contributing']} contributing pairs x {FLOPS_CONTRIB[dom]:.0f} FP32 ops per launch",
-                "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / steps)}
+                "avg_launch_ms": dom_ms, "share_of_step": per_step[dom] / (ms_total / steps),
+                # what actually bounds the kernel (committed ncu capture of the same kernel at this batch size): the share of
+                # cycles in which a scheduler issues an instruction, and the active lanes per issued instruction
+                "issue_bound": {"issue_active_frac": (ncu_traffic(wl, dom, "issue_active_pct") or 0.0) / 100.0 or None,
+                                "active_lanes_per_instruction": ncu_traffic(wl, dom, "threads_per_inst"),
+                                "warp_instructions_per_launch": ncu_traffic(wl, dom, "inst_executed"),
+                                "note": "the rasterizers are bound by instruction issue on divergent lanes (per-pixel / per-entry walks over "
+                                        "32-entry chunks), not by the FMA pipe or HBM: `frac` counts useful pair flops only"}}
     # the same kernel against the HBM roofline: per staged block-list entry 4 B id + 48 B record, per pixel OF A NON-EMPTY
     # TILE 24 B (saved state + cotangents; forward: 20 B written + 8 B saved), 36 B of atomics per contributing entry (backward)
     dom_bytes = stats["entries_staged"] * 52 + n_lists * 256 * (24 if dom == "raster_bwd" else 28) + \
