@@ -551,11 +551,17 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
     uint8_t *tab = reinterpret_cast<uint8_t *>(s_bm + words);
     for (int w = threadIdx.x; w < words; w += 256) s_bm[w] = 0u;
     __syncthreads();
-    for (int i = start + threadIdx.x; i < end; i += 256) {
-        const uint32_t sw = slots[i];
-        const uint32_t r = sw & PS_SLOT_KEY_MASK;
-        atomicOr(&s_bm[r >> 5], 1u << (r & 31u));
-        if (m8s) tab[r] = (uint8_t)(sw >> PS_SLOT_MASK_SHIFT);
+    for (int i0 = start + threadIdx.x; i0 < end; i0 += 4 * 256) { // four independent loads in flight per thread
+        uint32_t sw4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sw4[u] = i0 + u * 256 < end ? __ldg(slots + i0 + u * 256) : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * 256 >= end) continue;
+            const uint32_t r = sw4[u] & PS_SLOT_KEY_MASK;
+            atomicOr(&s_bm[r >> 5], 1u << (r & 31u));
+            if (m8s) tab[r] = (uint8_t)(sw4[u] >> PS_SLOT_MASK_SHIFT);
+        }
     }
     __syncthreads();
     const int wpt = (words + 255) / 256;
@@ -573,9 +579,18 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
             vals[out++] = (MODE == PS_MODE_3D) ? r : vbase + r;
         }
     }
-    if (MODE == PS_MODE_3D) { // rank -> Gaussian with every thread gathering independently
+    if (MODE == PS_MODE_3D) { // rank -> Gaussian with every thread gathering independently, four in flight
         __syncthreads();
-        for (int i = start + threadIdx.x; i < end; i += 256) vals[i] = vbase + __ldg(order + vbase + vals[i]);
+        for (int i0 = start + threadIdx.x; i0 < end; i0 += 4 * 256) {
+            uint32_t r4[4], g4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r4[u] = i0 + u * 256 < end ? vals[i0 + u * 256] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g4[u] = i0 + u * 256 < end ? __ldg(order + vbase + r4[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * 256 < end) vals[i0 + u * 256] = vbase + g4[u];
+        }
     }
 }
 
