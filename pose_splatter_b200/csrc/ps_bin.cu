@@ -532,23 +532,27 @@ __device__ __forceinline__ int block_exclusive_scan_256i(int v, int *s_warp)
     return pre + incl - v;
 }
 
-// One CTA per non-empty list: unique keys < N -> bitmap sort.  With m8s != NULL the block masks packed into the slot
-// words travel along: a byte table indexed by key in shared memory, read back in sorted order -> m8s [M], so that the
-// block split streams (id, mask) pairs instead of gathering records.
-template <int MODE>
+// One CTA per non-empty list: unique keys < N -> bitmap sort.  The sorted keys are enumerated into a shared-memory
+// staging array (every thread owns a run of bitmap words and writes its run), then leave in one coalesced sweep that
+// also maps depth rank -> Gaussian (3D), four gathers in flight: the list is written to HBM once, in order.
+// With m8s != NULL the block masks packed into the slot words travel along: a byte table indexed by key in shared
+// memory, read back in sorted order -> m8s [M], so that the block split streams (id, mask) pairs instead of gathering
+// records.  STAGED = false: lists longer than the staging capacity (N > 65535) write the sorted keys to vals first.
+template <int MODE, bool STAGED>
 __global__ void __launch_bounds__(256)
 sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_t *__restrict__ offsets,
                   const int32_t *__restrict__ worklist, const uint32_t *__restrict__ slots, uint32_t *__restrict__ vals,
                   uint8_t *__restrict__ m8s, const int32_t *__restrict__ n_lists)
 {
-    extern __shared__ uint32_t s_bm[]; // [(N + 31) / 32] | bytes [N] (m8s)
+    extern __shared__ uint32_t s_bm[]; // [(N + 31) / 32] | STAGED: sorted keys uint16 [N] | bytes [N] (m8s)
     __shared__ int s_warp[8];
     if ((int)blockIdx.x >= __ldg(n_lists)) return; // the grid may be an upper bound (sync-free small calls)
     const int lin = worklist[blockIdx.x];
     const int start = offsets[lin], end = offsets[lin + 1];
     const int view = lin / g.n_tiles;
     const int words = (g.N + 31) >> 5;
-    uint8_t *tab = reinterpret_cast<uint8_t *>(s_bm + words);
+    uint16_t *stage = reinterpret_cast<uint16_t *>(s_bm + words);
+    uint8_t *tab = reinterpret_cast<uint8_t *>(s_bm + words) + (STAGED ? 2 * (size_t)((g.N + 1) & ~1) : 0);
     for (int w = threadIdx.x; w < words; w += 256) s_bm[w] = 0u;
     __syncthreads();
     for (int i0 = start + threadIdx.x; i0 < end; i0 += 4 * 256) { // four independent loads in flight per thread
@@ -568,28 +572,39 @@ sort_lists_kernel(PsGeometry g, const uint32_t *__restrict__ order, const int32_
     const int w0 = min(words, (int)threadIdx.x * wpt), w1 = min(words, w0 + wpt);
     int cnt = 0;
     for (int w = w0; w < w1; ++w) cnt += __popc(s_bm[w]);
-    int out = start + block_exclusive_scan_256i(cnt, s_warp);
+    int out = block_exclusive_scan_256i(cnt, s_warp); // position inside the list
     const uint32_t vbase = (uint32_t)view * (uint32_t)g.N;
-    for (int w = w0; w < w1; ++w) { // sorted ranks (3D) / finished values (2D), in order
+    for (int w = w0; w < w1; ++w) { // sorted ranks (3D) / row indices (2D), in order
         uint32_t bits = s_bm[w];
         while (bits) {
             const uint32_t r = (uint32_t)(w << 5) + (uint32_t)(__ffs(bits) - 1);
             bits &= bits - 1;
-            if (m8s) m8s[out] = tab[r];
-            vals[out++] = (MODE == PS_MODE_3D) ? r : vbase + r;
+            if (STAGED) stage[out] = (uint16_t)r;
+            else {
+                if (m8s) m8s[start + out] = tab[r];
+                vals[start + out] = (MODE == PS_MODE_3D) ? r : vbase + r;
+            }
+            ++out;
         }
     }
-    if (MODE == PS_MODE_3D) { // rank -> Gaussian with every thread gathering independently, four in flight
-        __syncthreads();
-        for (int i0 = start + threadIdx.x; i0 < end; i0 += 4 * 256) {
-            uint32_t r4[4], g4[4];
+    if (!STAGED && MODE != PS_MODE_3D) return;
+    __syncthreads();
+    const int len = end - start;
+    for (int j0 = threadIdx.x; j0 < len; j0 += 4 * 256) { // rank -> Gaussian, four gathers in flight, coalesced stores
+        uint32_t r4[4], g4[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) r4[u] = i0 + u * 256 < end ? vals[i0 + u * 256] : 0u;
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 256;
+            r4[u] = j < len ? (STAGED ? (uint32_t)stage[j] : vals[start + j]) : 0u;
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) g4[u] = i0 + u * 256 < end ? __ldg(order + vbase + r4[u]) : 0u;
+        for (int u = 0; u < 4; ++u) g4[u] = (MODE == PS_MODE_3D && j0 + u * 256 < len) ? __ldg(order + vbase + r4[u]) : r4[u];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i0 + u * 256 < end) vals[i0 + u * 256] = vbase + g4[u];
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 256;
+            if (j >= len) continue;
+            vals[start + j] = vbase + g4[u];
+            if (STAGED && m8s) m8s[start + j] = tab[r4[u]];
         }
     }
 }
@@ -839,14 +854,19 @@ int ps_launch_build_worklist(const PsGeometry &g, const PsLists &l, cudaStream_t
 int ps_launch_sort_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, uint8_t *m8s, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    const size_t dyn = (size_t)((g.N + 31) / 32) * sizeof(uint32_t) + (m8s ? (size_t)g.N : 0);
-    if (g.mode == PS_MODE_3D) {
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        sort_lists_kernel<PS_MODE_3D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, m8s, l.n_lists);
-    } else {
-        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<PS_MODE_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1;
-        sort_lists_kernel<PS_MODE_2D><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, m8s, l.n_lists);
-    }
+    const size_t bm = (size_t)((g.N + 31) / 32) * sizeof(uint32_t);
+    const size_t stage = 2 * (size_t)((g.N + 1) & ~1);
+    static const bool no_stage = getenv("PS_SORT_UNSTAGED") != nullptr; // A/B switch for measurements
+    const bool staged = !no_stage && g.N <= 65535 && bm + stage + (m8s ? (size_t)g.N : 0) <= 100 * 1024;
+    const size_t dyn = bm + (staged ? stage : 0) + (m8s ? (size_t)g.N : 0);
+#define PS_SORT(MODE, ST)                                                                                                     \
+    do {                                                                                                                      \
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(sort_lists_kernel<MODE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return -1; \
+        sort_lists_kernel<MODE, ST><<<n_work, 256, dyn, s>>>(g, t.order, l.offsets, l.worklist, l.slots, l.vals, m8s, l.n_lists); \
+    } while (0)
+    if (g.mode == PS_MODE_3D) { if (staged) PS_SORT(PS_MODE_3D, true); else PS_SORT(PS_MODE_3D, false); }
+    else { if (staged) PS_SORT(PS_MODE_2D, true); else PS_SORT(PS_MODE_2D, false); }
+#undef PS_SORT
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
