@@ -429,8 +429,10 @@ def per_kernel_traffic(wl, mode, V, N, M, n_lists, stats_all, stage_ms):
         "partition": VN * (4 + 8 + 32 + (4 if mode == "3d" else 0)) + M * 4,
         "sort_lists": M * (8 if mode == "3d" else 4) + M * 4,
         "block_lists": M * 36 + f["entries_staged"] * 4,
-        "raster_fwd": f["entries_staged"] * 52 + n_lists * 256 * 28,
-        "raster_bwd": b["entries_staged"] * 52 + n_lists * 256 * 24 + b["entries_walked"] * 36,
+        # forward: id + record per staged block-list entry, (id, pixel mask) written per contributor-list entry (= what the
+        # backward stages); backward: id + mask + record per contributor-list entry
+        "raster_fwd": f["entries_staged"] * 52 + b["entries_staged"] * 8 + n_lists * 256 * 28,
+        "raster_bwd": b["entries_staged"] * 56 + n_lists * 256 * 24 + b["entries_walked"] * 36,
         "project_bwd": VN * (4 + 36 + 64) + 2 * rows_in,
     }
     stage_of = {"project": "project", "partition": "partition", "sort_lists": "sort", "block_lists": "blocks", "raster_fwd": "raster_fwd",
@@ -706,10 +708,11 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                 "warp_instructions_per_launch": ncu_traffic(wl, dom, "inst_executed"),
                                 "note": "the rasterizers are bound by instruction issue on divergent lanes (per-pixel / per-entry walks over "
                                         "32-entry chunks), not by the FMA pipe or HBM: `frac` counts useful pair flops only"}}
-    # the same kernel against the HBM roofline: per staged block-list entry 4 B id + 48 B record, per pixel OF A NON-EMPTY
-    # TILE 24 B (saved state + cotangents; forward: 20 B written + 8 B saved), 36 B of atomics per contributing entry (backward)
-    dom_bytes = stats["entries_staged"] * 52 + n_lists * 256 * (24 if dom == "raster_bwd" else 28) + \
-        (stats["entries_walked"] * 36 if dom == "raster_bwd" else 0)
+    # the same kernel against the HBM roofline: per staged entry 4 B id + 48 B record (+ 4 B pixel mask in the backward, which
+    # stages the forward's contributor list; the forward writes 8 B per entry of that list), per pixel OF A NON-EMPTY TILE
+    # 24 B (saved state + cotangents; forward: 20 B written + 8 B saved), 36 B of atomics per contributing entry (backward)
+    dom_bytes = stats["entries_staged"] * (56 if dom == "raster_bwd" else 52) + n_lists * 256 * (24 if dom == "raster_bwd" else 28) + \
+        (stats["entries_walked"] * 36 if dom == "raster_bwd" else stats_all["bwd"]["entries_staged"] * 8)
     roofline["as_hbm"] = {"bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                           "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes": dom_bytes,
                           "note": "the rasterizers are instruction-issue bound, not HBM bound: this is how far below the HBM roofline they sit"}

@@ -315,7 +315,7 @@ static void saved_free(ps_saved *sv, cudaStream_t s)
     dev_free(sv->t.tile_rect, s); dev_free(sv->t.tiles_touched, s); dev_free(sv->t.order, s); dev_free(sv->t.rank, s);
     dev_free(sv->t.depth, s);
     dev_free(sv->l.offsets, s); dev_free(sv->l.fill, s); dev_free(sv->l.worklist, s); dev_free(sv->l.cls, s);
-    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bpos, s); dev_free(sv->l.cmask, s); dev_free(sv->l.bcount, s);
+    dev_free(sv->l.slots, s); dev_free(sv->l.vals, s); dev_free(sv->l.blist, s); dev_free(sv->l.bpos, s); dev_free(sv->l.cmask, s); dev_free(sv->l.cids, s); dev_free(sv->l.ccount, s); dev_free(sv->l.bcount, s);
     dev_free(sv->keys, s); dev_free(sv->last, s); dev_free(sv->blast, s); dev_free(sv->t_pen, s);
     sv->frame_off = sv->frame_views = nullptr; // live inside the offsets allocation
     sv->bg = nullptr;
@@ -453,7 +453,11 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             PS_TRY_CUDA(dev_alloc(&sv->l.blist, 8 * capM, s));
             PS_TRY_CUDA(dev_alloc(&sv->l.bcount, 8 * capW, s));
             if (keep) PS_TRY_CUDA(dev_alloc(&sv->l.bpos, 8 * capM, s));
-            if (save) PS_TRY_CUDA(dev_alloc(&sv->l.cmask, 8 * capM, s)); // contributor masks, written by the forward rasterizer
+            if (save) { // contributor lists, written by the forward rasterizer
+                PS_TRY_CUDA(dev_alloc(&sv->l.cids, 8 * capM, s));
+                PS_TRY_CUDA(dev_alloc(&sv->l.cmask, 8 * capM, s));
+                PS_TRY_CUDA(dev_alloc(&sv->l.ccount, 8 * capW, s));
+            }
             PS_TRY_CUDA(cudaMemsetAsync(sv->l.fill, 0, T * sizeof(int32_t), s));
             { StageTimer tm(ctx, PS_STAGE_PARTITION, s); PS_TRY_LAUNCH(ps_launch_partition(g, sv->t, sv->l, bin_mode ? mask_env : 0, s)); }
             if (split) {

@@ -43,8 +43,9 @@ struct PsLists {
     uint32_t *vals;     // [M] view*N + Gaussian, sorted (tile, depth | row)
     uint32_t *blist;    // [8*M] per-block lists: tile with range [s, s+len) owns [8s, 8s+8len), block k at +k*len;
                         //       entries = view*N + Gaussian, in tile-list order
-    uint32_t *cmask;    // [8*M] or NULL: per block-list entry the 32-bit mask of the block's pixels it contributes to, written
-                        //       by the forward rasterizer for its backward (same layout as blist)
+    uint32_t *cids;     // [8*M] or NULL: contributor lists, written by the forward rasterizer for its backward, in the regions of
+    uint32_t *cmask;    //       blist: view*N + Gaussian and the 32-bit mask of the block's pixels it was composited into, for
+    int32_t *ccount;    //       every block-list entry with at least one such pixel, in list order; ccount [8*n_work] = how many
     uint32_t *bpos;     // [8*M] or NULL: position (relative to s) in the tile list of every block-list entry (last-id tap)
     int32_t *bcount;    // [8*n_work] length of every block list, indexed by work-list item
     const int32_t *n_lists; // device: number of non-empty lists (= cls[3 * PS_N_CLASSES]); kernels launched over an upper

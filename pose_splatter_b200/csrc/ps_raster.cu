@@ -191,7 +191,8 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                   int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
                   float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const uint32_t *__restrict__ bpos,
                   const int32_t *__restrict__ bcount, uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats,
-                  const int32_t *__restrict__ n_lists, uint32_t *__restrict__ cmask)
+                  const int32_t *__restrict__ n_lists, uint32_t *__restrict__ cmask, uint32_t *__restrict__ cids,
+                  int32_t *__restrict__ ccount)
 {
     __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
     // the grid may be sized from an upper bound of the number of non-empty lists (sync-free small calls)
@@ -199,7 +200,10 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bpos, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool done = !c.inside;
-    if (__all_sync(FULL, done)) return; // block entirely outside the image
+    if (__all_sync(FULL, done)) { // block entirely outside the image
+        if (ccount && lane == 0) ccount[blockIdx.x * W + wid] = 0;
+        return;
+    }
     const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
     const int len = c.nb;
     const int nchunks = (len + CH - 1) / CH;
@@ -215,14 +219,17 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
         cp_async_commit();
     };
     auto fetch_id = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
-    uint32_t idn, idnn;
+    uint32_t idn, idnn, id_c, id_c1; // ids of chunks ci + 2, ci + 3 (to be staged) and ci, ci + 1 (for the contributor list)
     {
         const uint32_t i0 = fetch_id(0), i1 = fetch_id(1);
         idn = fetch_id(2);
         idnn = fetch_id(3);
         issue(0, i0);
         issue(1, i1);
+        id_c = i0; id_c1 = i1;
     }
+    int n_cl = 0; // entries of this block's contributor list so far
+    const size_t cl_off = (size_t)(c.bl - blist);
 
     unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     const float pxf = (MODE == PS_MODE_3D) ? (float)c.px + 0.5f : (float)c.px;
@@ -232,6 +239,8 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
     int blastpos = 0; // 1 + index (in the block list) of the last contributor
     for (int ci = 0; ci < nchunks; ++ci) {
         issue(ci + 2, idn);
+        const uint32_t id_cur = id_c; // this lane's entry of chunk ci
+        id_c = id_c1; id_c1 = idn;
         idn = idnn;
         idnn = fetch_id(ci + 4);
         cp_async_wait_group<2>(); // chunk ci has landed (this lane's copies); the barrier makes all lanes' visible
@@ -314,11 +323,20 @@ raster_fwd_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, co
                 cm_mine = (two && lane == eb) ? cmb : cm_mine;
             }
         }
-        if (cmask && first + lane < len) cmask[(c.bl - blist) + first + lane] = cm_mine;
+        if (cmask) { // append the entries that contributed to some pixel, in list order: (id, pixel mask)
+            const uint32_t nzb = __ballot_sync(FULL, cm_mine != 0u);
+            if (cm_mine != 0u) {
+                const size_t o = cl_off + n_cl + __popc(nzb & ((1u << lane) - 1u));
+                cids[o] = id_cur;
+                cmask[o] = cm_mine;
+            }
+            n_cl += __popc(nzb);
+        }
         if (__all_sync(FULL, done)) break;
         __syncwarp(); // every lane is finished with stage st before chunk ci + 3 is copied into it
     }
     cp_async_wait_group<0>();
+    if (ccount && lane == 0) ccount[blockIdx.x * W + wid] = n_cl;
     if (c.inside) {
         const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
         const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
@@ -412,7 +430,8 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                    int32_t *__restrict__ n_contrib, int32_t *__restrict__ last, int32_t *__restrict__ blast,
                    float *__restrict__ t_pen, const uint32_t *__restrict__ blist, const uint32_t *__restrict__ bpos,
                    const int32_t *__restrict__ bcount, uint32_t *__restrict__ rgba8, unsigned long long *__restrict__ stats,
-                  const int32_t *__restrict__ n_lists, uint32_t *__restrict__ cmask)
+                  const int32_t *__restrict__ n_lists, uint32_t *__restrict__ cmask, uint32_t *__restrict__ cids,
+                  int32_t *__restrict__ ccount)
 {
     __shared__ float4 s_a[W][NS][CH], s_b[W][NS][CH], s_c[W][NS][CH];
     // the grid may be sized from an upper bound of the number of non-empty lists (sync-free small calls)
@@ -420,7 +439,10 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     const BlockCtx c = block_ctx<W>(g, offsets, worklist, blist, bpos, bcount);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool done = !c.inside;
-    if (__all_sync(FULL, done)) return;
+    if (__all_sync(FULL, done)) {
+        if (ccount && lane == 0) ccount[blockIdx.x * W + wid] = 0;
+        return;
+    }
     const Ring q = { s_a[wid], s_b[wid], s_c[wid] };
     const int len = c.nb;
     const int nchunks = (len + CH - 1) / CH;
@@ -436,14 +458,17 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
         cp_async_commit();
     };
     auto fetch_id = [&](int cj) -> uint32_t { return (cj * CH + lane < len) ? __ldg(c.bl + cj * CH + lane) : 0u; };
-    uint32_t idn, idnn;
+    uint32_t idn, idnn, id_c, id_c1; // ids of chunks ci + 2, ci + 3 (to be staged) and ci, ci + 1 (for the contributor list)
     {
         const uint32_t i0 = fetch_id(0), i1 = fetch_id(1);
         idn = fetch_id(2);
         idnn = fetch_id(3);
         issue(0, i0);
         issue(1, i1);
+        id_c = i0; id_c1 = i1;
     }
+    int n_cl = 0; // entries of this block's contributor list so far
+    const size_t cl_off = (size_t)(c.bl - blist);
     unsigned long long st_eval = 0, st_walk = 0, st_staged = 0;
     const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f;
     const float pxf = (float)c.px + half, pyf = (float)c.py + half;
@@ -453,6 +478,8 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     int blastpos = 0;
     for (int ci = 0; ci < nchunks; ++ci) {
         issue(ci + 2, idn);
+        const uint32_t id_cur = id_c; // this lane's entry of chunk ci
+        id_c = id_c1; id_c1 = idn;
         idn = idnn;
         idnn = fetch_id(ci + 4);
         cp_async_wait_group<2>();
@@ -542,13 +569,20 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             }
         }
         __syncwarp(); // lanes reconverge; every lane is finished with stage st before chunk ci + 3 is copied into it
-        if (cmask) { // (pixel, entry) -> (entry, pixel): lane e stores the pixels its entry contributes to
+        if (cmask) { // (pixel, entry) -> (entry, pixel); the contributing entries are appended, in list order: (id, pixel mask)
             const uint32_t cme = transpose32(cmp, lane);
-            if (first + lane < len) cmask[(c.bl - blist) + first + lane] = cme;
+            const uint32_t nzb = __ballot_sync(FULL, cme != 0u);
+            if (cme != 0u) {
+                const size_t o = cl_off + n_cl + __popc(nzb & ((1u << lane) - 1u));
+                cids[o] = id_cur;
+                cmask[o] = cme;
+            }
+            n_cl += __popc(nzb);
         }
         if (__all_sync(FULL, done)) break;
     }
     cp_async_wait_group<0>();
+    if (ccount && lane == 0) ccount[blockIdx.x * W + wid] = n_cl;
     if (c.inside) {
         const size_t p = ((size_t)c.view * g.H + c.py) * g.W + c.px;
         const float b0 = __ldg(background), b1 = __ldg(background + 1), b2 = __ldg(background + 2);
@@ -848,8 +882,9 @@ raster_bwd2_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 }
 
 // ---- backward v6: contributor masks from the forward, per-pixel chain, per-entry moments ------------------------------
-// The forward leaves, per block-list entry, the 32-bit mask of the block's pixels it contributed to (cmask).  The replay
-// therefore touches contributing (pixel, entry) pairs only -- no culling, no candidate tests, no ballots:
+// The forward leaves, per pixel block, the list of the entries it composited into at least one of the block's pixels, each
+// with the 32-bit mask of those pixels (cids / cmask / ccount: the contributor list, about half of the block list at c2).
+// The replay therefore touches contributing (pixel, entry) pairs only -- no culling, no candidate tests, no ballots:
 //   A (lane = pixel)  the chunk's 32 entry masks are transposed across the warp (five shuffles); every pixel lane walks
 //                     ITS OWN contributors in reverse list order, recomputes alpha with the arithmetic of the contract and
 //                     advances the two sequential per-pixel quantities (T by rcp.approx from the saved "T before the last
@@ -868,7 +903,8 @@ __global__ void __launch_bounds__(BW * 32, 16 / BW)
 raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets, const int32_t *__restrict__ worklist,
                    const float *__restrict__ background, const int32_t *__restrict__ last, const float *__restrict__ t_pen,
                    const float *__restrict__ d_rgb, const float *__restrict__ d_alpha, const uint32_t *__restrict__ blist,
-                   const uint32_t *__restrict__ cmask, const int32_t *__restrict__ bcount, float *__restrict__ acc,
+                   const uint32_t *__restrict__ cids, const uint32_t *__restrict__ cmask, const int32_t *__restrict__ ccount,
+                   const int32_t *__restrict__ bcount, float *__restrict__ acc,
                    const int32_t *__restrict__ n_lists, unsigned *__restrict__ next_task, unsigned long long *__restrict__ stats)
 {
     // cp.async: three planes of float4 (rec0 | rec1 | rec2); bulk: 48 contiguous bytes per entry (s_a[w][st][3 e + k])
@@ -905,14 +941,13 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
             S = __ldg(background) * w0 + __ldg(background + 1) * w1 + __ldg(background + 2) * w2 - d_alpha[p];
         }
     }
-    int wmax = my_last;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
-    if (wmax <= 0) continue;
+    // the forward's contributor list of this block: the entries composited into at least one of its pixels
+    const int len = __ldg(ccount + task);
+    if (len <= 0) continue;
     __syncwarp();
     s_w[wid][lane] = make_float4(w0, w1, w2, 0.0f);
-    const int len = wmax;
     const int nchunks = (len + CH - 1) / CH;
+    const uint32_t *cil = cids + (c.bl - blist);
     const uint32_t *cml = cmask + (c.bl - blist);
     // reverse step r handles chunk nchunks - 1 - r; its ring stage is r % NS; ids and masks run ahead in registers
     auto issue = [&](int r, uint32_t id) {
@@ -938,7 +973,7 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
     auto fetch = [&](int r, uint32_t &id, uint32_t &cm) {
         const int cj = nchunks - 1 - r;
         const bool ok = cj >= 0 && cj * CH + lane < len;
-        id = ok ? __ldg(c.bl + cj * CH + lane) : 0u;
+        id = ok ? __ldg(cil + cj * CH + lane) : 0u;
         cm = ok ? __ldg(cml + cj * CH + lane) : 0u;
     };
     uint32_t id0, cm0, id1, cm1, id2, cm2, id3, cm3; // steps r, r + 1, r + 2, r + 3
@@ -1199,7 +1234,7 @@ int ps_launch_raster_fwd(const PsGeometry &g, const PsTable &t, const PsLists &l
     // all-lanes walk of v4 is faster (5.25 vs 5.44 ms at c3).  With `stats` the SAME kernel runs with its pair
     // counters compiled in (bench.py's roofline numerator comes from the kernel it times).
     static const bool force_v4 = getenv("PS_FWD_V4") != nullptr; // A/B switch for measurements
-#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bpos, l.bcount, rgba8, stats, l.n_lists, l.cmask)
+#define PS_FWD(K, MODE, ST) K<MODE, ST, WPC><<<grid, RT_THREADS, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, background, rgb, alpha, n_contrib, last, blast, t_pen, l.blist, l.bpos, l.bcount, rgba8, stats, l.n_lists, l.cmask, l.cids, l.ccount)
     if (g.mode == PS_MODE_3D && !force_v4) {
         if (stats) PS_FWD(raster_fwd6_kernel, PS_MODE_3D, true); else PS_FWD(raster_fwd6_kernel, PS_MODE_3D, false);
     } else if (g.mode == PS_MODE_3D) {
@@ -1273,7 +1308,7 @@ int ps_launch_raster_bwd(const PsGeometry &g, const PsTable &t, const PsLists &l
 #define PS_BWD3(MODE, ST, BK, SLOT)                                                                                          \
         do {                                                                                                                 \
             const unsigned cap = persistent_ctas(raster_bwd3_kernel<MODE, WPC, ST, BK>, SLOT);                               \
-            raster_bwd3_kernel<MODE, WPC, ST, BK><<<want < cap ? want : cap, RT_THREADS, 0, s>>>(g, t, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.cmask, l.bcount, acc, l.n_lists, next_task, stats); \
+            raster_bwd3_kernel<MODE, WPC, ST, BK><<<want < cap ? want : cap, RT_THREADS, 0, s>>>(g, t, l.offsets, l.worklist, background, last, t_pen, d_rgb, d_alpha, l.blist, l.cids, l.cmask, l.ccount, l.bcount, acc, l.n_lists, next_task, stats); \
         } while (0)
         static const bool bulk = getenv("PS_BWD_BULK") != nullptr; // A/B switch: records staged by cp.async.bulk (TMA 1-D)
         if (bulk && !stats) { if (mi == 0) PS_BWD3(PS_MODE_3D, false, true, 8); else PS_BWD3(PS_MODE_2D, false, true, 9); }
