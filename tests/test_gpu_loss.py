@@ -41,7 +41,7 @@ def _check(rgb, alpha, timg, mask, sl, il):
         assert err <= GRAD_TOL * scale + 2e-7, f"{name}: max err {err:.3e} vs max-abs {scale:.3e}"
 
 
-@pytest.mark.parametrize("V,H,W", [(1, 11, 11), (2, 23, 31), (3, 64, 40), (1, 100, 145), (6, 256, 288)])
+@pytest.mark.parametrize("V,H,W", [(1, 11, 11), (2, 23, 31), (3, 64, 40), (1, 100, 145), (6, 256, 288), (2, 141, 403), (1, 300, 200)])
 def test_view_loss_matches_oracle(V, H, W):
     _check(*_inputs(10 + H, V, H, W), 0.8, 0.35)
 
