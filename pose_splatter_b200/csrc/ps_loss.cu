@@ -52,18 +52,28 @@ loss_reduce_kernel(LossDims d, const float *__restrict__ rgb, const float *__res
     const size_t npix = (size_t)d.H * d.W;
     const float *a = alpha + v * npix, *m = mask + v * npix, *q = rgb + 3 * v * npix, *t = timg + 3 * v * npix;
     float sI = 0.f, sU = 0.f, sM = 0.f, sL = 0.f;
-    for (size_t i = (size_t)blockIdx.x * LTHREADS + threadIdx.x; i < npix; i += (size_t)gridDim.x * LTHREADS) {
-        const float av = a[i], mv = m[i];
-        sI += av * mv;
-        sU += av + mv - av * mv;
-        sM += mv;
-        if (rgb) sL += fabsf(t[i] - q[3 * i]) + fabsf(t[npix + i] - q[3 * i + 1]) + fabsf(t[2 * npix + i] - q[3 * i + 2]);
+    if (!rgb && (npix & 3) == 0) { // alpha and mask alone (the SSIM kernels take the L1 sum): 16-byte loads
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *m4 = reinterpret_cast<const float4 *>(m);
+        for (size_t i = (size_t)blockIdx.x * LTHREADS + threadIdx.x; i < npix / 4; i += (size_t)gridDim.x * LTHREADS) {
+            const float4 av = __ldg(a4 + i), mv = __ldg(m4 + i);
+            sI += av.x * mv.x + av.y * mv.y + av.z * mv.z + av.w * mv.w;
+            sU += (av.x + mv.x - av.x * mv.x) + (av.y + mv.y - av.y * mv.y) + (av.z + mv.z - av.z * mv.z) + (av.w + mv.w - av.w * mv.w);
+            sM += mv.x + mv.y + mv.z + mv.w;
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * LTHREADS + threadIdx.x; i < npix; i += (size_t)gridDim.x * LTHREADS) {
+            const float av = a[i], mv = m[i];
+            sI += av * mv;
+            sU += av + mv - av * mv;
+            sM += mv;
+            if (rgb) sL += fabsf(t[i] - q[3 * i]) + fabsf(t[npix + i] - q[3 * i + 1]) + fabsf(t[2 * npix + i] - q[3 * i + 2]);
+        }
     }
     double r;
     r = block_sum((double)sI, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 0, r);
     r = block_sum((double)sU, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 1, r);
     r = block_sum((double)sM, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 2, r);
-    r = block_sum((double)sL, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 3, r);
+    if (rgb) { r = block_sum((double)sL, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 3, r); }
 }
 
 // ---- packed fp32: Blackwell issues two FMAs per instruction (fma.rn.f32x2 -> FFMA2); a plain three-register FFMA
@@ -364,26 +374,36 @@ loss_bwd_kernel(LossDims d, const float *__restrict__ rgb, const float *__restri
 // ---- strip-marching SSIM kernels (default) -----------------------------------------------------------------------------
 // The tiled kernels above stage a 42 x 42 input tile per 32 x 32 outputs behind CTA barriers and keep every intermediate in
 // shared memory: they run at a quarter of the FP32 pipe's rate, stalled on barriers and on the tile loads.  The marching
-// kernels turn the work around.  A CTA owns a strip of SW output columns of one (view, channel) and walks down a band of
-// rows, eight rows per step:
-//   ring      thread = column (SW + 10 of them): the next eight input rows arrive by 4-byte cp.async (zero-filled outside
-//             the image) in a 24-row ring in shared memory that only the owning thread ever reads -- no barrier, one step of
-//             compute between issue and use
+// kernels turn the work around.  A CTA owns a strip of SW = NT - 16 output columns of one (view, channel) and walks down a
+// band of rows, eight rows per step:
+//   ring      thread = column (SW + 10 of them): the next eight input rows arrive by 4-byte cp.async in a 24-row ring in
+//             shared memory that only the owning thread ever reads -- no barrier, one step of compute between issue and use
 //   vertical  thread = column: 18 rows of its own column from the ring -> 8 vertically filtered rows of every map, in
 //             registers (packed f32x2: two maps per FFMA2); written once to an exchange buffer
 //   horizontal thread = (row, 8 columns): 18-column windows fetched as 16-byte shared loads (rows strided so that the eight
 //             rows of a load phase fall into different banks) -> 8 outputs per map, then the pointwise part
 //   epilogue  thread = column again (through a small shared transpose): every global access is row-contiguous
 // Two barriers per eight rows; global loads and stores are coalesced; no halo is re-read along a strip (1.07x across strips).
+// NT is a template parameter: every shared-memory stride is a compile-time constant (the first version, with run-time
+// strides, issued more integer than FP32 instructions).
 constexpr int RB = 8;              // rows per marching step
 constexpr int WIN8 = RB + 2 * HALO; // 18 inputs -> 8 outputs
 
-struct MarchGeom { int SW, NT, RS2, RS1, OS, B; };
+template <int NT>
+struct March {
+    static constexpr int SW = NT - 16;   // output columns per strip (multiple of 8, SW + 10 <= NT)
+    static constexpr int RS2 = NT + 2;   // float2 per exchange row: == 2 (mod 4): 16-byte rows, phase lanes spread over the banks
+    static constexpr int RS1 = NT + 4;   // floats per exchange row: >= SW + 12, == 4 (mod 8)
+    static constexpr int OS = SW + 4;    // floats per output-transpose row: == 4 (mod 8)
+    static constexpr size_t OB = 3 * (size_t)RB * OS * sizeof(float);
+    static constexpr size_t SMEM_FWD = 3 * (size_t)RB * NT * sizeof(float2) + RB * (2 * RS2 * sizeof(float2) + RS1 * sizeof(float)) + OB;
+    static constexpr size_t SMEM_BWD = 3 * (size_t)RB * NT * (sizeof(float2) + sizeof(float)) + RB * (RS2 * sizeof(float2) + RS1 * sizeof(float)) + OB;
+};
 
-__device__ __forceinline__ void cp_async4_z(void *smem, const void *gmem, bool ok)
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(ok ? 4 : 0) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_l() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all_l() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -406,6 +426,8 @@ __device__ __forceinline__ void window8(const float2 (&in)[N], float2 (&out)[RB]
         out[o] = s;
     }
 }
+// one map alone: scalar FMAs.  (Packing output pairs (o, o + 1) into FFMA2 needs a shifted copy of the inputs for the odd
+// taps: measured slower -- the extra registers spill in the backward kernel, no gain in the forward.)
 template <int N>
 __device__ __forceinline__ void window8s(const float (&in)[N], float (&out)[RB], const float2 (&c)[6])
 {
@@ -417,6 +439,30 @@ __device__ __forceinline__ void window8s(const float (&in)[N], float (&out)[RB],
         for (int tp = 1; tp < 11; ++tp) s = fmaf(c[tp < 6 ? tp : 10 - tp].x, in[o + tp], s);
         out[o] = s;
     }
+}
+// 18 consecutive float2 / 20 consecutive floats of an exchange row as 16-byte shared loads
+__device__ __forceinline__ void load_row18(const float2 *src2, float2 (&in)[WIN8])
+{
+    const float4 *src = reinterpret_cast<const float4 *>(src2);
+#pragma unroll
+    for (int k = 0; k < WIN8 / 2; ++k) {
+        const float4 w = src[k];
+        in[2 * k] = make_float2(w.x, w.y); in[2 * k + 1] = make_float2(w.z, w.w);
+    }
+}
+__device__ __forceinline__ void load_row20(const float *src1, float (&f)[20])
+{
+    const float4 *src = reinterpret_cast<const float4 *>(src1);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float4 w = src[k];
+        f[4 * k] = w.x; f[4 * k + 1] = w.y; f[4 * k + 2] = w.z; f[4 * k + 3] = w.w;
+    }
+}
+__device__ __forceinline__ void store_row8(float *dst, const float (&g)[RB])
+{
+    float4 *o = reinterpret_cast<float4 *>(dst);
+    o[0] = make_float4(g[0], g[1], g[2], g[3]); o[1] = make_float4(g[4], g[5], g[6], g[7]);
 }
 
 __device__ __forceinline__ double block_sum_n(double v, double *scratch)
@@ -433,56 +479,74 @@ __device__ __forceinline__ double block_sum_n(double v, double *scratch)
     return t; // valid in thread 0
 }
 
-// SSIM forward of one (strip, band, view, channel); channel-0 CTAs also take the soft-IoU sums of their pixels.
-__global__ void __launch_bounds__(256, 2)
-ssim_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, const float *__restrict__ alpha,
-                  const float *__restrict__ timg, const float *__restrict__ mask, float coef_over_count, float c1, float c2,
-                  float *__restrict__ adj, double *__restrict__ stats)
+// SSIM forward of one (strip, band, view, channel) + the L1 sum of its pixels (the soft-IoU sums: loss_reduce_kernel).
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 160 ? 3 : 2)
+ssim_march_kernel(LossDims d, int band, const float *__restrict__ rgb, const float *__restrict__ timg, float coef_over_count,
+                  float c1, float c2, float *__restrict__ adj, double *__restrict__ stats)
 {
+    using G = March<NT>;
     extern __shared__ __align__(16) unsigned char march_smem[];
     __shared__ double scratch[8];
     float2 *ring = reinterpret_cast<float2 *>(march_smem);      // [3 * RB][NT]  (p, q) input rows, thread-private columns
-    float2 *ex01 = ring + 3 * RB * mg.NT;                        // [RB][RS2]     vertically filtered (p, q)
-    float2 *ex23 = ex01 + RB * mg.RS2;                           // [RB][RS2]     ... (pp, qq)
-    float *ex4 = reinterpret_cast<float *>(ex23 + RB * mg.RS2);  // [RB][RS1]     ... pq
-    float *ob = ex4 + RB * mg.RS1;                               // [3][RB][OS]   the three adjoints on their way out
-    const int t = threadIdx.x, NT = mg.NT;
+    float2 *ex01 = ring + 3 * RB * NT;                           // [RB][RS2]     vertically filtered (p, q)
+    float2 *ex23 = ex01 + RB * G::RS2;                           // [RB][RS2]     ... (pp, qq)
+    float *ex4 = reinterpret_cast<float *>(ex23 + RB * G::RS2);  // [RB][RS1]     ... pq
+    float *ob = ex4 + RB * G::RS1;                               // [3][RB][OS]   the three adjoints on their way out
+    const int t = threadIdx.x;
     const int ch = blockIdx.x % 3, strip = blockIdx.x / 3, v = blockIdx.z;
-    const int x0 = strip * mg.SW, yb = blockIdx.y * mg.B, yend = min(yb + mg.B, d.H);
+    const int x0 = strip * G::SW, yb = blockIdx.y * band, yend = min(yb + band, d.H);
     const int nb = (yend - yb + RB - 1) / RB;
     const size_t npix = (size_t)d.H * d.W;
     const int xc = x0 - HALO + t; // vertical pass: this thread's column
-    const bool col_on = t < mg.SW + 2 * HALO;
+    const bool col_on = t < G::SW + 2 * HALO;
     const bool col_in = col_on && xc >= 0 && xc < d.W;
-    const bool col_own = t >= HALO && t < HALO + mg.SW && xc < d.W;
-    const float *pch = timg + (3 * (size_t)v + ch) * npix; // target image, planar
-    const float *qch = rgb + 3 * (size_t)v * npix + ch;    // render, interleaved
+    const bool col_own = t >= HALO && t < HALO + G::SW && xc < d.W;
+    const float *pch = timg + (3 * (size_t)v + ch) * npix + xc; // target image, planar: this thread's column
+    const float *qch = rgb + 3 * ((size_t)v * npix + xc) + ch;  // render, interleaved
     float2 c[6];
     load_taps(c);
-    // unit u = input rows yb + RB (u - 1) .. + RB - 1; step i filters units i, i + 1, i + 2
-    auto stage = [&](int u) {
-        if (col_on && u <= nb + 1) {
-            float2 *dst = ring + (size_t)((u % 3) * RB) * NT + t;
+    if (col_on && !col_in) { // a column outside the image stays zero for the whole walk
 #pragma unroll
-            for (int k = 0; k < RB; ++k) {
-                const int y = yb + RB * (u - 1) + k;
-                const bool ok = col_in && y >= 0 && y < d.H;
-                const size_t pix = ok ? (size_t)y * d.W + xc : 0;
-                cp_async4_z(&dst[k * NT].x, pch + pix, ok);
-                cp_async4_z(&dst[k * NT].y, qch + 3 * pix, ok);
+        for (int k = 0; k < 3 * RB; ++k) ring[k * NT + t] = make_float2(0.f, 0.f);
+    }
+    // unit u = input rows yb + RB (u - 1) .. + RB - 1; step i filters units i, i + 1, i + 2
+    auto stage = [&](int u, int slot) {
+        if (col_in && u <= nb + 1) {
+            float2 *dst = ring + slot * RB * NT + t;
+            const int y0 = yb + RB * (u - 1);
+            if (y0 >= 0 && y0 + RB <= d.H) {
+                const float *pp = pch + (size_t)y0 * d.W, *qq = qch + 3 * (size_t)y0 * d.W;
+#pragma unroll
+                for (int k = 0; k < RB; ++k) {
+                    cp_async4(&dst[k * NT].x, pp);
+                    cp_async4(&dst[k * NT].y, qq);
+                    pp += d.W; qq += 3 * d.W;
+                }
+            } else { // a unit across the top / bottom edge of the image: rows outside are zero
+#pragma unroll
+                for (int k = 0; k < RB; ++k) {
+                    const int y = y0 + k;
+                    if (y >= 0 && y < d.H) {
+                        cp_async4(&dst[k * NT].x, pch + (size_t)y * d.W);
+                        cp_async4(&dst[k * NT].y, qch + 3 * (size_t)y * d.W);
+                    } else {
+                        dst[k * NT] = make_float2(0.f, 0.f);
+                    }
+                }
             }
         }
         cp_async_commit_l();
     };
-    stage(0); stage(1); stage(2);
-    float ssum = 0.f, sL = 0.f, sI = 0.f, sU = 0.f, sM = 0.f;
+    stage(0, 0); stage(1, 1); stage(2, 2);
+    float ssum = 0.f, sL = 0.f;
+    int s0 = 0, s1 = 1, s2 = 2; // ring slots of units i, i + 1, i + 2
     for (int i = 0; i < nb; ++i) {
         const int yo = yb + RB * i;
         cp_async_wait_all_l();
         float2 win[WIN8]; // rows yo - 5 .. yo + 12 of this thread's column
         if (col_on) {
-            const float2 *u0 = ring + (size_t)((i % 3) * RB) * NT + t, *u1 = ring + (size_t)(((i + 1) % 3) * RB) * NT + t,
-                         *u2 = ring + (size_t)(((i + 2) % 3) * RB) * NT + t;
+            const float2 *u0 = ring + s0 * RB * NT + t, *u1 = ring + s1 * RB * NT + t, *u2 = ring + s2 * RB * NT + t;
 #pragma unroll
             for (int k = 0; k < HALO; ++k) win[k] = u0[(RB - HALO + k) * NT];
 #pragma unroll
@@ -490,7 +554,8 @@ ssim_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, const
 #pragma unroll
             for (int k = 0; k < HALO; ++k) win[HALO + RB + k] = u2[k * NT];
         }
-        stage(i + 3); // into the slots of unit i, whose rows are in registers now
+        stage(i + 3, s0); // into the slot of unit i, whose rows are in registers now
+        { const int sx = s0; s0 = s1; s1 = s2; s2 = sx; }
         if (col_on) {
             if (col_own) {
 #pragma unroll
@@ -500,7 +565,7 @@ ssim_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, const
             float2 out[RB];
             window8(win, out, c);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) ex01[r * mg.RS2 + t] = out[r];
+            for (int r = 0; r < RB; ++r) ex01[r * G::RS2 + t] = out[r];
             {
                 float2 sq[WIN8];
 #pragma unroll
@@ -508,46 +573,27 @@ ssim_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, const
                 window8(sq, out, c);
             }
 #pragma unroll
-            for (int r = 0; r < RB; ++r) ex23[r * mg.RS2 + t] = out[r];
+            for (int r = 0; r < RB; ++r) ex23[r * G::RS2 + t] = out[r];
             float pq[WIN8], o4[RB];
 #pragma unroll
             for (int k = 0; k < WIN8; ++k) pq[k] = win[k].x * win[k].y;
             window8s(pq, o4, c);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) ex4[r * mg.RS1 + t] = o4[r];
+            for (int r = 0; r < RB; ++r) ex4[r * G::RS1 + t] = o4[r];
         }
         __syncthreads();
-        if (t < mg.SW) { // horizontal pass + SSIM: thread = (row, eight columns)
+        if (t < G::SW) { // horizontal pass + SSIM: thread = (row, eight columns)
             const int row = t & 7, cg = t >> 3;
             const int y = yo + row;
             float2 in[WIN8], m[RB], e[RB];
             float epq[RB];
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(ex01 + row * mg.RS2 + 8 * cg);
-#pragma unroll
-                for (int k = 0; k < WIN8 / 2; ++k) {
-                    const float4 w = src[k];
-                    in[2 * k] = make_float2(w.x, w.y); in[2 * k + 1] = make_float2(w.z, w.w);
-                }
-                window8(in, m, c);
-            }
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(ex23 + row * mg.RS2 + 8 * cg);
-#pragma unroll
-                for (int k = 0; k < WIN8 / 2; ++k) {
-                    const float4 w = src[k];
-                    in[2 * k] = make_float2(w.x, w.y); in[2 * k + 1] = make_float2(w.z, w.w);
-                }
-                window8(in, e, c);
-            }
+            load_row18(ex01 + row * G::RS2 + 8 * cg, in);
+            window8(in, m, c);
+            load_row18(ex23 + row * G::RS2 + 8 * cg, in);
+            window8(in, e, c);
             {
                 float f[20];
-                const float4 *src = reinterpret_cast<const float4 *>(ex4 + row * mg.RS1 + 8 * cg);
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float4 w = src[k];
-                    f[4 * k] = w.x; f[4 * k + 1] = w.y; f[4 * k + 2] = w.z; f[4 * k + 3] = w.w;
-                }
+                load_row20(ex4 + row * G::RS1 + 8 * cg, f);
                 window8s(f, epq, c);
             }
             float g1[RB], g2[RB], g3[RB];
@@ -574,96 +620,103 @@ ssim_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, const
                     g3[o] = coef_over_count * 2.f * N1 * inv;
                 }
             }
-            float4 *o1 = reinterpret_cast<float4 *>(ob + (0 * RB + row) * mg.OS + 8 * cg);
-            float4 *o2 = reinterpret_cast<float4 *>(ob + (1 * RB + row) * mg.OS + 8 * cg);
-            float4 *o3 = reinterpret_cast<float4 *>(ob + (2 * RB + row) * mg.OS + 8 * cg);
-            o1[0] = make_float4(g1[0], g1[1], g1[2], g1[3]); o1[1] = make_float4(g1[4], g1[5], g1[6], g1[7]);
-            o2[0] = make_float4(g2[0], g2[1], g2[2], g2[3]); o2[1] = make_float4(g2[4], g2[5], g2[6], g2[7]);
-            o3[0] = make_float4(g3[0], g3[1], g3[2], g3[3]); o3[1] = make_float4(g3[4], g3[5], g3[6], g3[7]);
+            store_row8(ob + (0 * RB + row) * G::OS + 8 * cg, g1);
+            store_row8(ob + (1 * RB + row) * G::OS + 8 * cg, g2);
+            store_row8(ob + (2 * RB + row) * G::OS + 8 * cg, g3);
         }
         __syncthreads();
-        if (t < mg.SW && x0 + t < d.W) { // epilogue: thread = column, row-contiguous stores
-            const int x = x0 + t;
-            float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix, *a2 = a1 + npix, *a3 = a2 + npix;
+        if (t < G::SW && x0 + t < d.W) { // epilogue: thread = column, row-contiguous stores
+            float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix + (size_t)yo * d.W + x0 + t;
+            const int nr = min(RB, yend - yo);
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                const int y = yo + r;
-                if (y >= yend) break;
-                const size_t pix = (size_t)y * d.W + x;
-                a1[pix] = ob[(0 * RB + r) * mg.OS + t];
-                a2[pix] = ob[(1 * RB + r) * mg.OS + t];
-                a3[pix] = ob[(2 * RB + r) * mg.OS + t];
-                if (ch == 0) {
-                    const float av = alpha[v * npix + pix], mv = mask[v * npix + pix];
-                    sI += av * mv;
-                    sU += av + mv - av * mv;
-                    sM += mv;
+                if (r < nr) {
+                    a1[0] = ob[(0 * RB + r) * G::OS + t];
+                    a1[npix] = ob[(1 * RB + r) * G::OS + t];
+                    a1[2 * npix] = ob[(2 * RB + r) * G::OS + t];
                 }
+                a1 += d.W;
             }
         }
     }
     double r;
     r = block_sum_n((double)ssum, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 4, r);
     r = block_sum_n((double)sL, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 3, r);
-    if (ch == 0) {
-        r = block_sum_n((double)sI, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 0, r);
-        r = block_sum_n((double)sU, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 1, r);
-        r = block_sum_n((double)sM, scratch); if (threadIdx.x == 0) atomicAdd(stats + v * NSTAT + 2, r);
-    }
 }
 
-// The adjoints filtered back (same window: the taps are symmetric) and combined with the L1 sign term; same marching
-// structure, maps (A1, A2) packed + A3.  Channel-0 CTAs also write d_alpha (IoU quotient rule).
-__global__ void __launch_bounds__(256, 2)
-loss_bwd_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, const float *__restrict__ timg,
-                      const float *__restrict__ mask, const float *__restrict__ adj, const double *__restrict__ stats,
-                      float img_lambda, float *__restrict__ d_rgb, float *__restrict__ d_alpha)
+// The adjoints filtered back (same window: the taps are symmetric) and combined with the L1 sign term -> d_rgb; same
+// marching structure, maps (A1, A2) packed + A3.  (d_alpha: iou_bwd_kernel.)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 160 ? 3 : 2)
+loss_bwd_march_kernel(LossDims d, int band, const float *__restrict__ rgb, const float *__restrict__ timg,
+                      const float *__restrict__ adj, const double *__restrict__ stats, float img_lambda, float *__restrict__ d_rgb)
 {
+    using G = March<NT>;
     extern __shared__ __align__(16) unsigned char march_smem[];
-    float2 *ring = reinterpret_cast<float2 *>(march_smem);      // [3 * RB][NT]  (A1, A2)
-    float *ring3 = reinterpret_cast<float *>(ring + 3 * RB * mg.NT); // [3 * RB][NT]  A3
-    float2 *ex01 = reinterpret_cast<float2 *>(ring3 + 3 * RB * mg.NT); // [RB][RS2]
-    float *ex2 = reinterpret_cast<float *>(ex01 + RB * mg.RS2);  // [RB][RS1]
-    float *ob = ex2 + RB * mg.RS1;                               // [3][RB][OS]
-    const int t = threadIdx.x, NT = mg.NT;
+    float2 *ring = reinterpret_cast<float2 *>(march_smem);             // [3 * RB][NT]  (A1, A2)
+    float *ring3 = reinterpret_cast<float *>(ring + 3 * RB * NT);      // [3 * RB][NT]  A3
+    float2 *ex01 = reinterpret_cast<float2 *>(ring3 + 3 * RB * NT);    // [RB][RS2]
+    float *ex2 = reinterpret_cast<float *>(ex01 + RB * G::RS2);        // [RB][RS1]
+    float *ob = ex2 + RB * G::RS1;                                     // [3][RB][OS]
+    const int t = threadIdx.x;
     const int ch = blockIdx.x % 3, strip = blockIdx.x / 3, v = blockIdx.z;
-    const int x0 = strip * mg.SW, yb = blockIdx.y * mg.B, yend = min(yb + mg.B, d.H);
+    const int x0 = strip * G::SW, yb = blockIdx.y * band, yend = min(yb + band, d.H);
     const int nb = (yend - yb + RB - 1) / RB;
     const size_t npix = (size_t)d.H * d.W;
     const int xc = x0 - HALO + t;
-    const bool col_on = t < mg.SW + 2 * HALO;
+    const bool col_on = t < G::SW + 2 * HALO;
     const bool col_in = col_on && xc >= 0 && xc < d.W;
-    const float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix, *a2 = a1 + npix, *a3 = a2 + npix;
-    const double I = stats[v * NSTAT + 0] + 1e-6, U = stats[v * NSTAT + 1] + 1e-6, msum = stats[v * NSTAT + 2];
+    const bool epi_on = t < G::SW && x0 + t < d.W;
+    const float *a1 = adj + ((3 * (size_t)v + ch) * 3 + 0) * npix + xc;
+    const double msum = stats[v * NSTAT + 2];
     const float l1 = img_lambda == 0.0f ? 0.0f : (float)((double)img_lambda / msum); // lambda 0: no 0 * 0 / 0 for an empty mask
-    const float iou_m = (float)(-1.0 / U), iou_c = (float)(I / (U * U)); // d(1 - I/U)/da = -m/U + I (1 - m) / U^2
     float2 c[6];
     load_taps(c);
-    auto stage = [&](int u) {
-        if (col_on && u <= nb + 1) {
-            float2 *dst = ring + (size_t)((u % 3) * RB) * NT + t;
-            float *dst3 = ring3 + (size_t)((u % 3) * RB) * NT + t;
+    if (col_on && !col_in) {
 #pragma unroll
-            for (int k = 0; k < RB; ++k) {
-                const int y = yb + RB * (u - 1) + k;
-                const bool ok = col_in && y >= 0 && y < d.H;
-                const size_t pix = ok ? (size_t)y * d.W + xc : 0;
-                cp_async4_z(&dst[k * NT].x, a1 + pix, ok);
-                cp_async4_z(&dst[k * NT].y, a2 + pix, ok);
-                cp_async4_z(&dst3[k * NT], a3 + pix, ok);
+        for (int k = 0; k < 3 * RB; ++k) { ring[k * NT + t] = make_float2(0.f, 0.f); ring3[k * NT + t] = 0.f; }
+    }
+    auto stage = [&](int u, int slot) {
+        if (col_in && u <= nb + 1) {
+            float2 *dst = ring + slot * RB * NT + t;
+            float *dst3 = ring3 + slot * RB * NT + t;
+            const int y0 = yb + RB * (u - 1);
+            if (y0 >= 0 && y0 + RB <= d.H) {
+                const float *pa = a1 + (size_t)y0 * d.W;
+#pragma unroll
+                for (int k = 0; k < RB; ++k) {
+                    cp_async4(&dst[k * NT].x, pa);
+                    cp_async4(&dst[k * NT].y, pa + npix);
+                    cp_async4(&dst3[k * NT], pa + 2 * npix);
+                    pa += d.W;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RB; ++k) {
+                    const int y = y0 + k;
+                    if (y >= 0 && y < d.H) {
+                        const float *pa = a1 + (size_t)y * d.W;
+                        cp_async4(&dst[k * NT].x, pa);
+                        cp_async4(&dst[k * NT].y, pa + npix);
+                        cp_async4(&dst3[k * NT], pa + 2 * npix);
+                    } else {
+                        dst[k * NT] = make_float2(0.f, 0.f);
+                        dst3[k * NT] = 0.f;
+                    }
+                }
             }
         }
         cp_async_commit_l();
     };
-    stage(0); stage(1); stage(2);
+    stage(0, 0); stage(1, 1); stage(2, 2);
+    int s0 = 0, s1 = 1, s2 = 2;
     for (int i = 0; i < nb; ++i) {
         const int yo = yb + RB * i;
         cp_async_wait_all_l();
         float2 win[WIN8];
         float win3[WIN8];
         if (col_on) {
-            const size_t b0 = (size_t)((i % 3) * RB) * NT + t, b1 = (size_t)(((i + 1) % 3) * RB) * NT + t,
-                         b2 = (size_t)(((i + 2) % 3) * RB) * NT + t;
+            const int b0 = s0 * RB * NT + t, b1 = s1 * RB * NT + t, b2 = s2 * RB * NT + t;
 #pragma unroll
             for (int k = 0; k < HALO; ++k) { win[k] = ring[b0 + (RB - HALO + k) * NT]; win3[k] = ring3[b0 + (RB - HALO + k) * NT]; }
 #pragma unroll
@@ -671,84 +724,101 @@ loss_bwd_march_kernel(LossDims d, MarchGeom mg, const float *__restrict__ rgb, c
 #pragma unroll
             for (int k = 0; k < HALO; ++k) { win[HALO + RB + k] = ring[b2 + k * NT]; win3[HALO + RB + k] = ring3[b2 + k * NT]; }
         }
-        stage(i + 3);
+        stage(i + 3, s0);
+        { const int sx = s0; s0 = s1; s1 = s2; s2 = sx; }
         if (col_on) {
             float2 out[RB];
             float o3[RB];
             window8(win, out, c);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) ex01[r * mg.RS2 + t] = out[r];
+            for (int r = 0; r < RB; ++r) ex01[r * G::RS2 + t] = out[r];
             window8s(win3, o3, c);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) ex2[r * mg.RS1 + t] = o3[r];
+            for (int r = 0; r < RB; ++r) ex2[r * G::RS1 + t] = o3[r];
         }
         __syncthreads();
-        if (t < mg.SW) {
+        // the epilogue's own inputs (render and target of this thread's column, eight rows) are fetched here: their
+        // latency hides behind the horizontal pass instead of stalling the epilogue
+        float eq[RB], ep[RB];
+        const int nr = min(RB, yend - yo);
+        if (epi_on) {
+            const float *qg = rgb + 3 * ((size_t)v * npix + (size_t)yo * d.W + x0 + t) + ch;
+            const float *pg = timg + (3 * (size_t)v + ch) * npix + (size_t)yo * d.W + x0 + t;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                eq[r] = r < nr ? __ldg(qg) : 0.f;
+                ep[r] = r < nr ? __ldg(pg) : 0.f;
+                qg += 3 * d.W; pg += d.W;
+            }
+        }
+        if (t < G::SW) {
             const int row = t & 7, cg = t >> 3;
             float2 in[WIN8], w12[RB];
             float w3[RB];
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(ex01 + row * mg.RS2 + 8 * cg);
-#pragma unroll
-                for (int k = 0; k < WIN8 / 2; ++k) {
-                    const float4 w = src[k];
-                    in[2 * k] = make_float2(w.x, w.y); in[2 * k + 1] = make_float2(w.z, w.w);
-                }
-                window8(in, w12, c);
-            }
+            load_row18(ex01 + row * G::RS2 + 8 * cg, in);
+            window8(in, w12, c);
             {
                 float f[20];
-                const float4 *src = reinterpret_cast<const float4 *>(ex2 + row * mg.RS1 + 8 * cg);
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float4 w = src[k];
-                    f[4 * k] = w.x; f[4 * k + 1] = w.y; f[4 * k + 2] = w.z; f[4 * k + 3] = w.w;
-                }
+                load_row20(ex2 + row * G::RS1 + 8 * cg, f);
                 window8s(f, w3, c);
             }
-            float4 *o1 = reinterpret_cast<float4 *>(ob + (0 * RB + row) * mg.OS + 8 * cg);
-            float4 *o2 = reinterpret_cast<float4 *>(ob + (1 * RB + row) * mg.OS + 8 * cg);
-            float4 *o3 = reinterpret_cast<float4 *>(ob + (2 * RB + row) * mg.OS + 8 * cg);
-            o1[0] = make_float4(w12[0].x, w12[1].x, w12[2].x, w12[3].x); o1[1] = make_float4(w12[4].x, w12[5].x, w12[6].x, w12[7].x);
-            o2[0] = make_float4(w12[0].y, w12[1].y, w12[2].y, w12[3].y); o2[1] = make_float4(w12[4].y, w12[5].y, w12[6].y, w12[7].y);
-            o3[0] = make_float4(w3[0], w3[1], w3[2], w3[3]); o3[1] = make_float4(w3[4], w3[5], w3[6], w3[7]);
+            float w1[RB], w2[RB];
+#pragma unroll
+            for (int o = 0; o < RB; ++o) { w1[o] = w12[o].x; w2[o] = w12[o].y; }
+            store_row8(ob + (0 * RB + row) * G::OS + 8 * cg, w1);
+            store_row8(ob + (1 * RB + row) * G::OS + 8 * cg, w2);
+            store_row8(ob + (2 * RB + row) * G::OS + 8 * cg, w3);
         }
         __syncthreads();
-        if (t < mg.SW && x0 + t < d.W) {
-            const int x = x0 + t;
+        if (epi_on) {
+            float *dg = d_rgb + 3 * ((size_t)v * npix + (size_t)yo * d.W + x0 + t) + ch;
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                const int y = yo + r;
-                if (y >= yend) break;
-                const size_t pix = (size_t)v * npix + (size_t)y * d.W + x;
-                const float q = rgb[3 * pix + ch], p = timg[(3 * (size_t)v + ch) * npix + (size_t)y * d.W + x];
-                const float diff = p - q;
-                const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                const float w1 = ob[(0 * RB + r) * mg.OS + t], w2 = ob[(1 * RB + r) * mg.OS + t], w3 = ob[(2 * RB + r) * mg.OS + t];
-                d_rgb[3 * pix + ch] = w1 + 2.f * q * w2 + p * w3 - l1 * sgn;
-                if (ch == 0) {
-                    const float m = mask[pix];
-                    d_alpha[pix] = iou_m * m + iou_c * (1.f - m);
+                if (r < nr) {
+                    const float q = eq[r], p = ep[r];
+                    const float diff = p - q;
+                    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                    const float w1 = ob[(0 * RB + r) * G::OS + t], w2 = ob[(1 * RB + r) * G::OS + t], w3 = ob[(2 * RB + r) * G::OS + t];
+                    *dg = w1 + 2.f * q * w2 + p * w3 - l1 * sgn;
                 }
+                dg += 3 * d.W;
             }
         }
     }
 }
 
-// strip / band geometry of the marching kernels for an image size
-MarchGeom march_geom(int H, int W, int band)
+// strip width of the marching kernels for an image width: the instantiation with the fewest threads over all strips
+int march_nt(int W)
 {
-    MarchGeom g;
-    const int SW_MAX = 192; // output columns per strip: SW + 10 threads, at most 224
-    const int n_strips = (W + SW_MAX - 1) / SW_MAX;
-    g.SW = (((W + n_strips - 1) / n_strips) + 7) / 8 * 8;
-    g.NT = (g.SW + 2 * HALO + 31) / 32 * 32;
-    g.RS2 = g.NT + 2;                 // float2 per exchange row: == 2 (mod 4): 16-byte rows whose phase lanes spread over the banks
-    g.RS1 = (g.SW + 12 + 7) / 8 * 8 + 4; // floats per exchange row: >= SW + 12, == 4 (mod 8)
-    g.OS = (g.SW + 7) / 8 * 8 + 4;    // floats per output-transpose row: == 4 (mod 8)
-    const int Hr = (H + RB - 1) / RB * RB;
-    g.B = band < Hr ? band : Hr;
-    return g;
+    const int cand[4] = { 64, 96, 160, 224 };
+    int best = 160;
+    long best_cost = -1;
+    for (int k = 0; k < 4; ++k) {
+        const int sw = cand[k] - 16;
+        const long cost = (long)((W + sw - 1) / sw) * cand[k];
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = cand[k]; }
+    }
+    return best;
+}
+
+template <int NT>
+int launch_march(const LossDims &d, int band, dim3 grid, const float *rgb, const float *timg, float coef, float c1, float c2,
+                 float *adj, double *stats, float img_lambda, float *d_rgb, cudaStream_t s)
+{
+    using G = March<NT>;
+    static bool attr_ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev < 64 ? dev : 63;
+    if (!attr_ready[di] || dev >= 64) { // above 48 KB of dynamic shared memory is opt-in, per device
+        if (cudaFuncSetAttribute(ssim_march_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_FWD) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(loss_bwd_march_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BWD) != cudaSuccess) return -1;
+        attr_ready[di] = true;
+    }
+    ssim_march_kernel<NT><<<grid, NT, G::SMEM_FWD, s>>>(d, band, rgb, timg, coef, c1, c2, adj, stats);
+    if (!d_rgb) return 1;
+    loss_bwd_march_kernel<NT><<<grid, NT, G::SMEM_BWD, s>>>(d, band, rgb, timg, adj, stats, img_lambda, d_rgb);
+    return 2;
 }
 
 __global__ void loss_finalize_kernel(LossDims d, const double *__restrict__ stats, float ssim_lambda, float img_lambda,
@@ -772,9 +842,19 @@ iou_bwd_kernel(LossDims d, const float *__restrict__ mask, const double *__restr
     const int v = blockIdx.y;
     const size_t npix = (size_t)d.H * d.W;
     const double I = stats[v * NSTAT + 0] + 1e-6, U = stats[v * NSTAT + 1] + 1e-6;
-    if (blockIdx.x == 0 && threadIdx.x == 0) losses[v] = (float)(1.0 - I / U);
+    if (losses && blockIdx.x == 0 && threadIdx.x == 0) losses[v] = (float)(1.0 - I / U);
     if (!d_alpha) return;
     const float iou_m = (float)(-1.0 / U), iou_c = (float)(I / (U * U));
+    if ((npix & 3) == 0) {
+        const float4 *m4 = reinterpret_cast<const float4 *>(mask + v * npix);
+        float4 *o4 = reinterpret_cast<float4 *>(d_alpha + v * npix);
+        for (size_t i = (size_t)blockIdx.x * LTHREADS + threadIdx.x; i < npix / 4; i += (size_t)gridDim.x * LTHREADS) {
+            const float4 m = __ldg(m4 + i);
+            o4[i] = make_float4(iou_m * m.x + iou_c * (1.f - m.x), iou_m * m.y + iou_c * (1.f - m.y),
+                                iou_m * m.z + iou_c * (1.f - m.z), iou_m * m.w + iou_c * (1.f - m.w));
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * LTHREADS + threadIdx.x; i < npix; i += (size_t)gridDim.x * LTHREADS) {
         const float m = mask[v * npix + i];
         d_alpha[v * npix + i] = iou_m * m + iou_c * (1.f - m);
@@ -810,29 +890,32 @@ int ps_launch_view_loss(int V, int H, int W, const float *rgb, const float *alph
     const double count = 3.0 * (double)(H - 2 * HALO) * (double)(W - 2 * HALO);
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f; // (k * data_range)^2, data_range = 1.0
     int n = 1;
-    (void)bx;
     static const int minb = getenv("PS_LOSS_MINB") ? atoi(getenv("PS_LOSS_MINB")) : 2; // A/B switch: registers bounded for 2 / 3 CTAs per SM
     const float coef = d_rgb ? (float)(-(double)ssim_lambda / count) : 0.0f;
     static const bool tiled = getenv("PS_LOSS_TILED") != nullptr; // A/B switch: the 32 x 32 tile kernels
     if (!tiled) {
-        static const int band = getenv("PS_LOSS_BAND") ? atoi(getenv("PS_LOSS_BAND")) : 128;
-        const MarchGeom mg = march_geom(H, W, band >= RB ? band / RB * RB : 128);
-        const size_t ex_f = (size_t)RB * (2 * mg.RS2 * sizeof(float2) + mg.RS1 * sizeof(float)) + 3 * (size_t)RB * mg.OS * sizeof(float);
-        const size_t ex_b = (size_t)RB * (mg.RS2 * sizeof(float2) + mg.RS1 * sizeof(float)) + 3 * (size_t)RB * mg.OS * sizeof(float);
-        const size_t smem_f = 3 * (size_t)RB * mg.NT * sizeof(float2) + ex_f;
-        const size_t smem_b = 3 * (size_t)RB * mg.NT * (sizeof(float2) + sizeof(float)) + ex_b;
-        static bool attr_ready[64] = {};
-        if (!attr_ready[di] || dev >= 64) { // above 48 KB of dynamic shared memory is opt-in, per device
-            if (cudaFuncSetAttribute(ssim_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) return -1;
-            if (cudaFuncSetAttribute(loss_bwd_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) return -1;
-            attr_ready[di] = true;
-        }
-        const int n_strips = (W + mg.SW - 1) / mg.SW, n_bands = (H + mg.B - 1) / mg.B;
-        const dim3 grid(3 * n_strips, n_bands, V);
-        ssim_march_kernel<<<grid, mg.NT, smem_f, s>>>(d, mg, rgb, alpha, timg, mask, coef, c1, c2, adj, stats);
+        static const int band_env = getenv("PS_LOSS_BAND") ? atoi(getenv("PS_LOSS_BAND")) : 128;
+        const int Hr = (H + RB - 1) / RB * RB;
+        int band = band_env >= RB ? band_env / RB * RB : 128;
+        band = band < Hr ? band : Hr;
+        static const int nt_env = getenv("PS_LOSS_NT") ? atoi(getenv("PS_LOSS_NT")) : 0; // A/B switch: strip width
+        const int nt = (nt_env == 64 || nt_env == 96 || nt_env == 160 || nt_env == 224) ? nt_env : march_nt(W);
+        const int sw = nt - 16;
+        const dim3 grid(3 * ((W + sw - 1) / sw), (H + band - 1) / band, V);
+        // soft-IoU sums of alpha and mask: one streaming pass of their own (0.9 GB at c2)
+        loss_reduce_kernel<<<dim3(bx, V), LTHREADS, 0, s>>>(d, nullptr, alpha, nullptr, mask, stats);
         n += 1;
+        int m = -1;
+        switch (nt) {
+        case 64: m = launch_march<64>(d, band, grid, rgb, timg, coef, c1, c2, adj, stats, img_lambda, d_rgb, s); break;
+        case 96: m = launch_march<96>(d, band, grid, rgb, timg, coef, c1, c2, adj, stats, img_lambda, d_rgb, s); break;
+        case 224: m = launch_march<224>(d, band, grid, rgb, timg, coef, c1, c2, adj, stats, img_lambda, d_rgb, s); break;
+        default: m = launch_march<160>(d, band, grid, rgb, timg, coef, c1, c2, adj, stats, img_lambda, d_rgb, s); break;
+        }
+        if (m < 0) return -1;
+        n += m;
         if (d_rgb) {
-            loss_bwd_march_kernel<<<grid, mg.NT, smem_b, s>>>(d, mg, rgb, timg, mask, adj, stats, img_lambda, d_rgb, d_alpha);
+            iou_bwd_kernel<<<dim3(bx, V), LTHREADS, 0, s>>>(d, mask, stats, nullptr, d_alpha);
             n += 1;
         }
         loss_finalize_kernel<<<(V + 127) / 128, 128, 0, s>>>(d, stats, ssim_lambda, img_lambda, losses);
