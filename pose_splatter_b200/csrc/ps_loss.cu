@@ -7,13 +7,14 @@
 // image only (its reflection padding is cropped away again), variances clamped at 0.  torchmetrics is not in the
 // reference tree: the algorithm is restated from its published source (oracle/loss_ref.py, parity unpinned).
 //
-// Four launches per call, all views batched:
-//   loss_reduce   per-view sums  I = sum a m, U = sum (a + m - a m), sum m, sum |t - rgb|       [HBM, one read]
-//   ssim_fwd      32x32-pixel tiles, separable 11-tap windows of (p, q, pp, qq, pq) in shared memory; per window
-//                 centre S and the three adjoints dS/d(mu_q), dS/d(E qq), dS/d(E pq) (scaled by -lambda / count)
-//   loss_bwd      the adjoints filtered back with the same window (its transpose: the taps are symmetric), combined
-//                 with the L1 sign term -> d_rgb [V,H,W,3]; IoU quotient rule -> d_alpha [V,H,W]
-//   loss_finalize losses [V,3] = (iou, ssim, img)
+// Launches per call, all views batched (default path; PS_LOSS_TILED=1 selects round 1's 32 x 32 tile kernels):
+//   loss_reduce     per-view sums  I = sum a m, U = sum (a + m - a m), sum m                      [HBM, one read, 16-byte loads]
+//   ssim_march      strip-marching SSIM: separable 11-tap windows of (p, q, pp, qq, pq), per window centre S and the
+//                   three adjoints dS/d(mu_q), dS/d(E qq), dS/d(E pq) (scaled by -lambda / count); also sum |t - rgb|
+//   loss_bwd_march  the adjoints filtered back with the same window (its transpose: the taps are symmetric), combined
+//                   with the L1 sign term -> d_rgb [V,H,W,3]
+//   iou_bwd         IoU quotient rule -> d_alpha [V,H,W]
+//   loss_finalize   losses [V,3] = (iou, ssim, img)
 #include "ps_internal.h"
 #include <cstdlib>
 
