@@ -709,6 +709,17 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                 "warp_instructions_per_launch": ncu_traffic(wl, dom, "inst_executed"),
                                 "note": "the rasterizers are bound by instruction issue on divergent lanes (per-pixel / per-entry walks over "
                                         "32-entry chunks), not by the FMA pipe or HBM: `frac` counts useful pair flops only"}}
+    if not fwd_only:
+        # the other rasterizer on the same terms (round 1's dominant kernel was the backward one: its fraction is tracked
+        # across rounds whichever of the two is slower now)
+        oth = "raster_bwd" if dom == "raster_fwd" else "raster_fwd"
+        ost = stats_all["bwd" if oth == "raster_bwd" else "fwd"]
+        oth_ms = stage_ms[oth][0]
+        oth_tf = (ost["pairs_evaluated"] * FLOPS_EVAL[oth] + ost["pairs_contributing"] * FLOPS_CONTRIB[oth]) / (oth_ms * 1e-3) / 1e12
+        roofline["other_rasterizer"] = {"kernel": oth, "achieved": oth_tf, "unit": "TFLOP/s", "frac": oth_tf / fp32_peak if fp32_peak else None,
+                                        "avg_launch_ms": oth_ms, "traffic": ncu_traffic(wl, oth),
+                                        "work": f"{ost['pairs_evaluated']} evaluated pairs x {FLOPS_EVAL[oth]:.0f} + "
+                                                f"{ost['pairs_contributing']} contributing pairs x {FLOPS_CONTRIB[oth]:.0f} FP32 ops per launch"}
     # the same kernel against the HBM roofline: per staged entry 4 B id + 48 B record (+ 4 B pixel mask in the backward, which
     # stages the forward's contributor list; the forward writes 8 B per entry of that list), per pixel OF A NON-EMPTY TILE
     # 24 B (saved state + cotangents; forward: 20 B written + 8 B saved), 36 B of atomics per contributing entry (backward)
