@@ -411,3 +411,29 @@ def test_3d_equal_depths_crowded_buckets_and_ties():
     p[:, 3:6] += 0.5
     d = dict(params=p[None], view_frame=torch.zeros(3, dtype=torch.int32))
     _compare("3d", d["params"], d["view_frame"], W, H, (0.1, 0.2, 0.3), vm[:3], Ks[:3])
+
+
+@pytest.mark.parametrize("wl", ["c2", "c3"])
+def test_contributor_list_counters_match_the_images(wl):
+    """The forward hands the backward a compact contributor list per pixel block.  Its counters must agree with what the
+    forward itself composited: the backward replays exactly the forward's contributing (pixel, entry) pairs (= the sum of
+    the per-pixel contributor counts), over no more entries than the forward staged, and every walked entry contributes."""
+    _, _capi, batched, synth = _mods()
+    d = synth.make_views(wl, 2, 6, seed=11)
+    W, H, mode = d["width"], d["height"], d["mode"]
+    p, vf = d["params"].to(DEV), d["view_frame"].to(DEV)
+    vm = d["viewmats"].to(DEV) if d["viewmats"] is not None else None
+    Ks = d["Ks"].to(DEV) if d["Ks"] is not None else None
+    bg = torch.ones(3, device=DEV)
+    w_rgb, w_a = synth.cotangents(len(vf), H, W, seed=7)
+    _capi.raster_stats(torch.device(DEV), reset=True)
+    _, _, counts, sv = batched.forward_raw(mode, p, vf, vm, Ks, bg, W, H, _capi.FLAG_SAVE_FOR_BACKWARD | _capi.FLAG_RASTER_STATS,
+                                           want_counts=True)
+    g = batched.backward_raw(sv, p, vf, vm, Ks, bg, w_rgb.to(DEV), w_a.to(DEV))
+    sv.release()
+    st = _capi.raster_stats(torch.device(DEV), reset=True)
+    total = int(counts.sum().item())
+    assert st["fwd"]["pairs_contributing"] == total > 0
+    assert st["bwd"]["pairs_contributing"] == total == st["bwd"]["pairs_evaluated"]
+    assert 0 < st["bwd"]["entries_walked"] <= st["bwd"]["entries_staged"] <= st["fwd"]["entries_staged"]
+    assert bool(torch.isfinite(g).all())
