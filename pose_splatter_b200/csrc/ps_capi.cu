@@ -158,6 +158,7 @@ struct ps_ctx {
     std::vector<PsMailbox> mail_free;
     std::vector<void *> mail_chunks;     // pinned allocations the slots live in
     unsigned long long *d_stats;         // [8] pair counters (PS_FLAG_RASTER_STATS): forward [0..3], backward [4..7]
+    cudaStream_t side;                   // the background fill of large forwards runs here, beside the binning kernels
     bool profiling;
     std::vector<PsSpan> pending;
     std::vector<cudaEvent_t> spare;
@@ -283,6 +284,7 @@ int ps_ctx_create(int device, ps_ctx **out)
     c->device = device;
     c->launches = 0;
     c->profiling = false;
+    c->side = nullptr;
     for (int i = 0; i < PS_N_STAGES; ++i) { c->stage_ms[i] = 0.0; c->stage_calls[i] = 0; }
     PS_CUDA(cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long)));
     PS_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
@@ -297,6 +299,7 @@ int ps_ctx_destroy(ps_ctx *ctx)
     cudaDeviceSynchronize();
     for (void *h : ctx->mail_chunks) cudaFreeHost(h);
     cudaFree(ctx->d_stats);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     for (auto &sp : ctx->pending) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->spare) cudaEventDestroy(e);
     if (ctx->device >= 0 && ctx->device < PS_MAX_DEVICES) {
@@ -362,6 +365,10 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
     g.activated = (d->flags & PS_FLAG_ACTIVATED_INPUTS) != 0 && d->mode == PS_MODE_3D;
 
     int rc = 0;
+    cudaEvent_t ev_scan = nullptr, ev_fill = nullptr;
+    bool filled = false; // the background fill already runs on the side stream
+    static const bool no_fork = getenv("PS_NO_FILL_FORK") != nullptr; // A/B switch: everything on the caller's stream
+    const bool fork_fill = !no_fork && !keep && (size_t)d->n_views * d->height * d->width > 0;
     uint32_t *rank_scratch = nullptr;
     int32_t *rank_flags = nullptr;
     long long *scan_scratch = nullptr;
@@ -421,6 +428,27 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             // the views of every frame (CSR): the 3D projection and the projection backward loop over them per Gaussian
             PS_TRY_LAUNCH(ps_launch_frame_csr(g, view_frame, sv->frame_off, csr_cursor, sv->frame_views, background, sv->bg, s));
             { StageTimer tm(ctx, PS_STAGE_PROJECT, s); PS_TRY_LAUNCH(ps_launch_project(g, params, view_frame, viewmats, Ks, sv->t, sv->l.offsets, sv->frame_off, sv->frame_views, s)); }
+            // The list lengths are scanned first: their total M (which sizes the lists) reaches the host while the GPU is
+            // still ranking depths, and the background fill of the empty tiles -- which needs nothing but the scanned
+            // offsets and only writes memory -- runs on a side stream beside the latency-bound binning kernels.
+            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, sv->mail.d, s)); }
+            if (!sync_free) {
+                PS_TRY_CUDA(cudaEventCreateWithFlags(&ev_scan, cudaEventDisableTiming));
+                PS_TRY_CUDA(cudaEventRecord(ev_scan, s));
+                if (fork_fill) {
+                    {
+                        std::lock_guard<std::mutex> lock(ctx->mu);
+                        if (!ctx->side && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) ctx->side = nullptr;
+                    }
+                    if (ctx->side) {
+                        PS_TRY_CUDA(cudaEventCreateWithFlags(&ev_fill, cudaEventDisableTiming));
+                        PS_TRY_CUDA(cudaStreamWaitEvent(ctx->side, ev_scan, 0));
+                        PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, nullptr, rgba8, ctx->side));
+                        PS_TRY_CUDA(cudaEventRecord(ev_fill, ctx->side));
+                        filled = true;
+                    }
+                }
+            }
             if (g.mode == PS_MODE_3D) {
                 PS_TRY_CUDA(dev_alloc(&sv->t.order, VN, s));
                 PS_TRY_CUDA(dev_alloc(&sv->t.rank, VN, s));
@@ -430,13 +458,12 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
                 StageTimer tm(ctx, PS_STAGE_RANK, s);
                 PS_TRY_LAUNCH(ps_launch_depth_rank(g, sv->t, rank_scratch, rank_flags, s));
             }
-            { StageTimer tm(ctx, PS_STAGE_SCAN, s); PS_TRY_LAUNCH(ps_launch_scan_lists(g, sv->l, scan_scratch, sv->mail.d, s)); }
             if (sync_free) {
                 sv->resolved = false;
                 sv->cap_M = (int64_t)worst;
                 sv->cap_work = (int)T;
             } else {
-                PS_TRY_CUDA(cudaStreamSynchronize(s)); // the one host sync of a large forward: M sizes the lists
+                PS_TRY_CUDA(cudaEventSynchronize(ev_scan)); // the one host wait of a large forward: M sizes the lists
                 sv->M = sv->mail.h[0];
                 sv->n_work = (int)sv->mail.h[1];
                 if (sv->M > 0x7fffffffLL) { rc = fail(1, "ps_forward: %lld tile intersections exceed 2^31", (long long)sv->M); goto out; }
@@ -484,12 +511,17 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             }
             if (keep) PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
-            PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, rgba8, s));
+            if (!filled) PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, rgba8, s));
             PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->cap_work, background, rgb, alpha, n_contrib,
                                                sv->last, sv->blast, sv->t_pen, rgba8, sv->stats ? ctx->d_stats : nullptr, s));
         }
     }
 out:
+    if (ev_fill) { // join: the caller's stream completes only after the side stream's fill
+        if (filled && cudaStreamWaitEvent(s, ev_fill, 0) != cudaSuccess && rc == 0) rc = fail(2, "ps_forward: cudaStreamWaitEvent failed");
+        cudaEventDestroy(ev_fill);
+    }
+    if (ev_scan) cudaEventDestroy(ev_scan);
     dev_free(rank_scratch, s);
     dev_free(rank_flags, s);
     dev_free(scan_scratch, s);

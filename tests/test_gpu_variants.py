@@ -23,6 +23,8 @@ VARIANTS = {
     "force_sync": {"PS_FORCE_SYNC": "1"},                     # small calls sized exactly from the mailbox
     "project_per_view": {"PS_PROJECT_PER_VIEW": "1"},         # one thread per (view, Gaussian) projection
     "rank_radix": {"PS_RANK_RADIX": "1"},                     # depth ranking by the radix kernel only
+    "no_fill_fork": {"PS_NO_FILL_FORK": "1"},                 # background fill on the caller's stream (no side stream)
+    "loss_tiled": {"PS_LOSS_TILED": "1"},                     # round-1 32 x 32 tile loss kernels
 }
 
 
@@ -30,7 +32,8 @@ VARIANTS = {
 def test_parity_slice_under_switch(name):
     env = dict(os.environ)
     env.update(VARIANTS[name])
-    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
-                        "-k", SLICE, "-p", "no:cacheprovider"], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
+    target, pick = ("test_gpu_loss.py", "view_loss") if name.startswith("loss_") else ("test_gpu_parity.py", SLICE)
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / target), "-m", "gpu", "-q", "-x",
+                        "-k", pick, "-p", "no:cacheprovider"], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
