@@ -192,6 +192,60 @@ def reference_2d_cpu(wl, reps=3):
                          "extrapolation": "linear in N (dense N*H*W cost); not a measurement" if n_fwd != N else "none: measured at the workload's N"}}
 
 
+def reference_2d_on_gpu(wl, dev, reps=3):
+    """Comparator of SURVEY 8d-d5: the reference's own GaussianRenderer2D run as it is with device='cuda' -- torch eager
+    kernels on this B200 (baseline/_ref copy, unmodified; none of this repo's code on its path).  Forward only (no_grad) at
+    the workload's N; forward + autograd backward at N = 1024 (its autograd memory is ~N*H*W*40 B)."""
+    import importlib.util
+    import torch
+    from pose_splatter_b200 import synth
+    path = ROOT / "baseline" / "_ref" / "reference_src" / "gaussian_renderer.py"
+    if not path.exists():
+        return {"unavailable": "baseline/_ref is missing: run __graft_entry__.build() where /root/reference exists"}
+    spec = importlib.util.spec_from_file_location("reference_gaussian_renderer_gpu", str(path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = synth.WORKLOADS[wl]
+    W, H, N = cfg["width"], cfg["height"], cfg["n"]
+    params = synth.make_views(wl, 1, 6, seed=99)["params"][0].to(dev)
+    r = mod.create_renderer("2d", W, H, device=str(dev), sigma_cutoff=3.0, kernel_size=5, batch_size=5)
+    r.set_background_color(torch.ones(3, device=dev))
+    w_rgb, w_a = synth.cotangents(1, H, W, seed=5)
+    w_rgb, w_a = w_rgb[0].to(dev), w_a[0].to(dev)
+
+    def fwd_bwd(n):
+        p = params[:n].clone().requires_grad_(True)
+        rgb, alpha = r.render(p, None, None)
+        ((rgb * w_rgb).sum() + (alpha * w_a).sum()).backward()
+
+    def fwd(n):
+        with torch.no_grad():
+            r.render(params[:n], None, None)
+
+    def median_seconds(fn, n):
+        fn(n)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn(n)
+            torch.cuda.synchronize(dev)
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+
+    try:
+        n_bwd = min(1024, N)
+        t_fwd, t_bwd = median_seconds(fwd, N), median_seconds(fwd_bwd, n_bwd)
+    except Exception as e:  # e.g. out of memory in the reference's dense temporaries
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    return {"kind": "reference", "what": "reference GaussianRenderer2D (pure PyTorch, device='cuda': torch eager on this B200), one view per call",
+            "workload": f"{wl}: {W}x{H}, camera 0 of the synthetic workload, 1 warm-up + {reps} repetitions, median, host wall clock around a device sync",
+            "fwd_only": {"n": N, "seconds": t_fwd, "views_per_s": 1.0 / t_fwd},
+            "fwd_bwd": {"n": n_bwd, "seconds": t_bwd, "views_per_s": 1.0 / t_bwd,
+                        "extrapolated_views_per_s_at_workload_n": (1.0 / t_bwd) * n_bwd / N, "workload_n": N,
+                        "extrapolation": "linear in N (dense N*H*W cost); not a measurement"}}
+
+
 def gsplat_comparator():
     """Extra comparator of north_star: the reference's gsplat path on one B200.  gsplat is not vendored in the reference
     and not installed in this image (no network); the repo-root gsplat/ package is this repo's own shim, not gsplat."""
@@ -830,6 +884,8 @@ def measure(args, wl, steps, world, rank, local, dev, primary):
                                "sample": f"{sample_views} views of the same workload (full N, full resolution, fwd+bwd), {dt:.1f} s on {cores} threads"}
         # the reference's own pure-PyTorch CPU path (2D only: its 3D arithmetic is gsplat, CUDA-only) beside the port
         out["cpu_baseline_reference"] = reference_2d_cpu("c3" if mode == "3d" else wl)
+        # ... and the same unmodified class as torch eager kernels on this GPU
+        out["reference_2d_on_b200"] = reference_2d_on_gpu("c3" if mode == "3d" else wl, dev)
     if primary:
         out["gsplat_b200"] = gsplat_comparator()
     if wl == "c4":
