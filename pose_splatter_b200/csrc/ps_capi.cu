@@ -369,6 +369,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
     bool filled = false; // the background fill already runs on the side stream
     static const bool no_fork = getenv("PS_NO_FILL_FORK") != nullptr; // A/B switch: everything on the caller's stream
     const bool fork_fill = !no_fork && !keep && (size_t)d->n_views * d->height * d->width > 0;
+    static const bool late_fork = getenv("PS_FILL_FORK_LATE") != nullptr; // A/B switch: the fill beside the rasterizer instead of the binning
     uint32_t *rank_scratch = nullptr;
     int32_t *rank_flags = nullptr;
     long long *scan_scratch = nullptr;
@@ -435,7 +436,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             if (!sync_free) {
                 PS_TRY_CUDA(cudaEventCreateWithFlags(&ev_scan, cudaEventDisableTiming));
                 PS_TRY_CUDA(cudaEventRecord(ev_scan, s));
-                if (fork_fill) {
+                if (fork_fill && !late_fork) {
                     {
                         std::lock_guard<std::mutex> lock(ctx->mu);
                         if (!ctx->side && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) ctx->side = nullptr;
@@ -511,6 +512,20 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
             }
             if (keep) PS_TRY_CUDA(dev_alloc(&sv->last, npix, s));
             StageTimer tm(ctx, PS_STAGE_RASTER_FWD, s);
+            if (!filled && fork_fill && late_fork && ev_scan) {
+                {
+                    std::lock_guard<std::mutex> lock(ctx->mu);
+                    if (!ctx->side && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) ctx->side = nullptr;
+                }
+                if (ctx->side) {
+                    PS_TRY_CUDA(cudaEventCreateWithFlags(&ev_fill, cudaEventDisableTiming));
+                    PS_TRY_CUDA(cudaEventRecord(ev_scan, s)); // re-used: everything the caller's stream holds so far
+                    PS_TRY_CUDA(cudaStreamWaitEvent(ctx->side, ev_scan, 0));
+                    PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, nullptr, rgba8, ctx->side));
+                    PS_TRY_CUDA(cudaEventRecord(ev_fill, ctx->side));
+                    filled = true;
+                }
+            }
             if (!filled) PS_TRY_LAUNCH(ps_launch_fill_empty(g, sv->l.offsets, background, rgb, alpha, n_contrib, sv->last, rgba8, s));
             PS_TRY_LAUNCH(ps_launch_raster_fwd(g, sv->t, sv->l, sv->cap_work, background, rgb, alpha, n_contrib,
                                                sv->last, sv->blast, sv->t_pen, rgba8, sv->stats ? ctx->d_stats : nullptr, s));
