@@ -233,6 +233,7 @@ struct ps_saved {
     PsLists l;
     ps_ctx *ctx;
     cudaStream_t stream;  // the forward's stream
+    cudaStream_t last_stream; // the stream of the last call that touched the saved buffers (forward, backward, tap)
     PsMailbox mail;
     bool resolved;        // M / n_work below are known on the host (sync-free small calls resolve them lazily)
     bool stats;           // the forward ran with PS_FLAG_RASTER_STATS: the backward counts its pairs too
@@ -249,6 +250,22 @@ struct ps_saved {
 };
 
 namespace {
+// A later call on another stream (a backward issued from a different torch stream, a release from whichever thread
+// drops the last reference) is ordered behind the work already queued on the saved buffers: without this the arena
+// could hand a released block to that stream while the previous stream's kernels still use it.
+int saved_order_after(ps_saved *sv, cudaStream_t s)
+{
+    if (sv->last_stream == s) return 0;
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return fail(2, "cudaEventCreate failed (cross-stream use of a saved forward)");
+    cudaError_t e = cudaEventRecord(ev, sv->last_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev, 0);
+    cudaEventDestroy(ev); // released by the runtime once the wait has been satisfied
+    if (e != cudaSuccess) return fail(2, "cross-stream ordering of a saved forward failed: %s", cudaGetErrorString(e));
+    sv->last_stream = s;
+    return 0;
+}
+
 // M and the list count of a sync-free forward, read once its stream has drained
 int saved_resolve(ps_saved *sv)
 {
@@ -353,6 +370,7 @@ static int forward_impl(ps_ctx *ctx, const ps_render_desc *d, const float *param
     memset(sv, 0, sizeof *sv);
     sv->ctx = ctx;
     sv->stream = s;
+    sv->last_stream = s;
     sv->stats = (d->flags & PS_FLAG_RASTER_STATS) != 0;
     PsGeometry &g = sv->g;
     g.mode = d->mode; g.W = d->width; g.H = d->height; g.F = d->n_frames; g.N = d->n_gauss; g.V = d->n_views;
@@ -583,6 +601,7 @@ static int backward_impl(ps_ctx *ctx, ps_saved *sv, const float *params, const f
     const int P = g.mode == PS_MODE_3D ? 14 : 9;
     const size_t n_out = (size_t)g.F * g.N * P;
     if (n_out == 0) return 0;
+    if (saved_order_after(sv, s)) return 2;
     if (!peers && !d_params) return fail(1, "ps_backward: NULL d_params");
     if (peers && (world < 1 || my_rank < 0 || my_rank >= world)) return fail(1, "ps_backward_peer: rank %d of %d", my_rank, world);
     const size_t VN = (size_t)g.V * g.N;
@@ -661,6 +680,8 @@ int ps_saved_copy(ps_ctx *ctx, const ps_saved *sv, int what, void *dst, size_t b
 {
     if (!ctx || !sv || !dst) return fail(1, "ps_saved_copy: NULL argument");
     if (int rc = saved_resolve(const_cast<ps_saved *>(sv))) return rc;
+    PS_CUDA(cudaSetDevice(ctx->device));
+    if (saved_order_after(const_cast<ps_saved *>(sv), (cudaStream_t)stream)) return 2;
     const PsGeometry &g = sv->g;
     const size_t VN = (size_t)g.V * g.N, npix = (size_t)g.V * g.H * g.W;
     const void *src = nullptr;
@@ -699,6 +720,7 @@ int ps_saved_release(ps_ctx *ctx, ps_saved *sv, void *stream)
 {
     if (!sv) return 0;
     if (ctx) cudaSetDevice(ctx->device);
+    if (saved_order_after(sv, (cudaStream_t)stream)) cudaStreamSynchronize(sv->last_stream); // cannot order: drain instead
     saved_free(sv, (cudaStream_t)stream);
     delete sv;
     return 0;

@@ -24,6 +24,7 @@ VARIANTS = {
     "project_per_view": {"PS_PROJECT_PER_VIEW": "1"},         # one thread per (view, Gaussian) projection
     "rank_radix": {"PS_RANK_RADIX": "1"},                     # depth ranking by the radix kernel only
     "no_fill_fork": {"PS_NO_FILL_FORK": "1"},                 # background fill on the caller's stream (no side stream)
+    "fill_fork_late": {"PS_FILL_FORK_LATE": "1"},             # background fill beside the forward rasterizer, not the binning
     "loss_tiled": {"PS_LOSS_TILED": "1"},                     # round-1 32 x 32 tile loss kernels
 }
 
@@ -33,6 +34,8 @@ def test_parity_slice_under_switch(name):
     env = dict(os.environ)
     env.update(VARIANTS[name])
     target, pick = ("test_gpu_loss.py", "view_loss") if name.startswith("loss_") else ("test_gpu_parity.py", SLICE)
+    if "fill_fork" in name:  # only calls too large for the sync-free path fork the fill: the 24-view batch at full N
+        pick = SLICE + " or test_batch_invariance_full_size_c2"
     r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / target), "-m", "gpu", "-q", "-x",
                         "-k", pick, "-p", "no:cacheprovider"], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
