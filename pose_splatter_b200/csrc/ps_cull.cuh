@@ -55,9 +55,12 @@ __device__ __forceinline__ uint32_t ps_block_mask8(float gx, float gy, float hA,
         const float s1 = ax[i] + (hC * t1 + bx_[i]) * t1;
         const float t2 = fminf(fmaxf(ty_[j], ux0[i]), ux1[i]);
         const float s2 = ay[j] + (hA * t2 + by_[j]) * t2;
-        const bool inx = cx[i] == 0.0f, iny = cy[j] == 0.0f;
-        const bool hit = (inx && iny) || (!inx && !(s1 > lim)) || (!iny && !(s2 > lim));
-        m8 |= hit ? (1u << k) : 0u;
+        // s1 / s2 = minimum of sigma over the block's vertical / horizontal edge nearest to the mean.  No guards on
+        // "mean inside the column / row range": there cx (cy) = 0 and s1 (s2) degenerates to sigma at the nearest point
+        // of the other axis, which is >= the other minimum, so testing both is the same decision (a superset by at most
+        // a rounding error); mean inside the block gives s1 = s2 = 0 <= lim.  NaN counts as a hit.
+        const bool miss = (s1 > lim) && (s2 > lim);
+        m8 |= miss ? 0u : (1u << k);
     }
     return m8;
 }

@@ -409,21 +409,32 @@ __device__ __forceinline__ uint32_t span_mask(float gx, float gy, float hA, floa
     return m;
 }
 
-// 32 x 32 bit-matrix transpose across the warp: lane l gives row l, gets column l
+// 32 x 32 bit-matrix transpose across the warp: lane l gives row l, gets column l.  Five butterfly stages; the two
+// byte-granular ones are one PRMT each (selector by the lane's bit), the three sub-byte ones a rotate and a bit-select:
+//   lower lane of a pair: x = (x & M) | ((y << J) & ~M),  upper lane: x = ((y >> J) & M) | (x & ~M)
+// (a rotation by J resp. 32 - J puts the wanted bits in place; the bits that wrap around fall under the discarded half
+// of the mask).  Emulated against the definition for all 1024 single-bit matrices and random ones.
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 {
+    uint32_t y = __shfl_xor_sync(FULL, x, 16);
+    x = __byte_perm(x, y, (lane & 16) ? 0x3276u : 0x5410u);
+    y = __shfl_xor_sync(FULL, x, 8);
+    x = __byte_perm(x, y, (lane & 8) ? 0x3715u : 0x6240u);
 #define PS_TSTAGE(J, M)                                                                          \
     {                                                                                            \
-        const uint32_t y = __shfl_xor_sync(FULL, x, J);                                          \
-        x = (lane & J) ? (((y >> J) & M) | (x & ~M)) : ((x & M) | ((y & M) << J));               \
+        y = __shfl_xor_sync(FULL, x, J);                                                         \
+        const bool up = (lane & J) != 0;                                                         \
+        const uint32_t t = __funnelshift_l(y, y, up ? 32 - J : J);                               \
+        const uint32_t m = up ? ~M : M;                                                          \
+        x = (x & m) | (t & ~m);                                                                  \
     }
-    PS_TSTAGE(16, 0x0000ffffu) PS_TSTAGE(8, 0x00ff00ffu) PS_TSTAGE(4, 0x0f0f0f0fu) PS_TSTAGE(2, 0x33333333u) PS_TSTAGE(1, 0x55555555u)
+    PS_TSTAGE(4, 0x0f0f0f0fu) PS_TSTAGE(2, 0x33333333u) PS_TSTAGE(1, 0x55555555u)
 #undef PS_TSTAGE
     return x;
 }
 
 template <int MODE, bool STATS, int W>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__(W * 32, 32 / W)
 raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                    const int32_t *__restrict__ worklist, const float *__restrict__ background,
                    float *__restrict__ rgb, float *__restrict__ alpha,
@@ -532,7 +543,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                     } else {
                         const float vis = psm_mul(aa, T);
                         cr = psm_fma(vis, r2a.x, cr); cg = psm_fma(vis, r2a.y, cg); cb = psm_fma(vis, r2a.z, cb);
-                        Tpen = T; T = nT; ++cnt; blastpos = first + ea + 1; cmp |= 1u << ea;
+                        Tpen = T; T = nT; cmp |= 1u << ea;
                     }
                 }
                 if (candb && !done && ab >= PS_ALPHA_MIN) {
@@ -542,7 +553,7 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                     } else {
                         const float vis = psm_mul(ab, T);
                         cr = psm_fma(vis, r2b.x, cr); cg = psm_fma(vis, r2b.y, cg); cb = psm_fma(vis, r2b.z, cb);
-                        Tpen = T; T = nT; ++cnt; blastpos = first + eb + 1; cmp |= 1u << eb;
+                        Tpen = T; T = nT; cmp |= 1u << eb;
                     }
                 }
             } else {
@@ -557,17 +568,20 @@ raster_fwd6_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
                 if (ina) {
                     const float contrib = psm_mul(gva, T);
                     cr = psm_fma(contrib, r2a.x, cr); cg = psm_fma(contrib, r2a.y, cg); cb = psm_fma(contrib, r2a.z, cb);
-                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); ++cnt; blastpos = first + ea + 1; cmp |= 1u << ea;
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gva)); cmp |= 1u << ea;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
                 if (inb && !done) {
                     const float contrib = psm_mul(gvb, T);
                     cr = psm_fma(contrib, r2b.x, cr); cg = psm_fma(contrib, r2b.y, cg); cb = psm_fma(contrib, r2b.z, cb);
-                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); ++cnt; blastpos = first + eb + 1; cmp |= 1u << eb;
+                    Tpen = T; T = psm_mul(T, psm_sub(1.0f, gvb)); cmp |= 1u << eb;
                     if (T <= PS_T_STOP_2D) done = true;
                 }
             }
         }
+        // this pixel's contributors of the chunk are the set bits of cmp: count and last position once per chunk
+        // instead of once per pair
+        if (cmp) { cnt += __popc(cmp); blastpos = first + 32 - __clz(cmp); }
         __syncwarp(); // lanes reconverge; every lane is finished with stage st before chunk ci + 3 is copied into it
         if (cmask) { // (pixel, entry) -> (entry, pixel); the contributing entries are appended, in list order: (id, pixel mask)
             const uint32_t cme = transpose32(cmp, lane);
@@ -1128,7 +1142,7 @@ raster_bwd3_kernel(PsGeometry g, PsTable t, const int32_t *__restrict__ offsets,
 // Split every non-empty tile list, in order, into the lists of its eight 8x4 pixel blocks.
 // m8s != NULL: the block masks were computed by the partition kernel and sorted along (one byte per list entry):
 // a pure streaming split of (id, mask) pairs, no record is touched.
-template <int MODE>
+template <int MODE, bool BPOS> // BPOS: also write the tile-list positions (last-id parity tap only)
 __global__ void __launch_bounds__(256)
 block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, const int32_t *__restrict__ offsets,
                    const int32_t *__restrict__ worklist, uint32_t *__restrict__ blist, uint32_t *__restrict__ bpos,
@@ -1136,7 +1150,7 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 {
     if ((int)blockIdx.x >= __ldg(n_lists)) return; // the grid may be an upper bound (sync-free small calls)
     __shared__ int s_cnt[8][8]; // [warp][block]
-    __shared__ int s_pre[8][8]; // [warp][block] output cursor of the round
+    __shared__ __align__(16) int s_pre[8][8]; // [warp][block] output cursor of the round
     __shared__ int s_run[8], s_tot[8];
     const int item = blockIdx.x;
     const int lin = worklist[item];
@@ -1145,7 +1159,7 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
     const int start = offsets[lin], len = offsets[lin + 1] - start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *out = blist + 8 * (size_t)start;
-    uint32_t *outp = bpos ? bpos + 8 * (size_t)start : nullptr;
+    uint32_t *outp = BPOS ? bpos + 8 * (size_t)start : nullptr;
     const uint32_t *list = vals + start;
     uint32_t inside8 = 0; // blocks that have at least one pixel inside the image
 #pragma unroll
@@ -1198,12 +1212,19 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
             if (w == 7) s_tot[k] = pre + s_cnt[7][k]; // running total after this round
         }
         __syncthreads();
+        {
+            // the warp's eight cursors in two 16-byte loads; offsets in 32 bits (8 * len < 2^27: a tile list holds at
+            // most one entry per Gaussian of the view, and N < 2^24)
+            const int4 pa = *reinterpret_cast<const int4 *>(&s_pre[wid][0]), pb = *reinterpret_cast<const int4 *>(&s_pre[wid][4]);
+            const int pre[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
+            const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if ((m8 >> k) & 1u) {
-                const size_t o = (size_t)k * len + s_pre[wid][k] + __popc(bal[k] & ((1u << lane) - 1u));
-                out[o] = id_cur;
-                if (outp) outp[o] = (uint32_t)j;
+            for (int k = 0; k < 8; ++k) {
+                if ((m8 >> k) & 1u) {
+                    const uint32_t o = (uint32_t)k * (uint32_t)len + (uint32_t)pre[k] + (uint32_t)__popc(bal[k] & below);
+                    out[o] = id_cur;
+                    if (BPOS) outp[o] = (uint32_t)j;
+                }
             }
         }
         if (threadIdx.x < 8) s_run[threadIdx.x] = s_tot[threadIdx.x];
@@ -1219,8 +1240,10 @@ block_lists_kernel(PsGeometry g, PsTable t, const uint32_t *__restrict__ vals, c
 int ps_launch_block_lists(const PsGeometry &g, const PsTable &t, const PsLists &l, int n_work, const uint8_t *m8s, cudaStream_t s)
 {
     if (n_work <= 0) return 0;
-    if (g.mode == PS_MODE_3D) block_lists_kernel<PS_MODE_3D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount, m8s, l.n_lists);
-    else block_lists_kernel<PS_MODE_2D><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount, m8s, l.n_lists);
+#define PS_BL(MODE, BPOS) block_lists_kernel<MODE, BPOS><<<n_work, 256, 0, s>>>(g, t, l.vals, l.offsets, l.worklist, l.blist, l.bpos, l.bcount, m8s, l.n_lists)
+    if (g.mode == PS_MODE_3D) { if (l.bpos) PS_BL(PS_MODE_3D, true); else PS_BL(PS_MODE_3D, false); }
+    else { if (l.bpos) PS_BL(PS_MODE_2D, true); else PS_BL(PS_MODE_2D, false); }
+#undef PS_BL
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -1,0 +1,75 @@
+"""The conservative footprint tests of pose_splatter_b200/csrc/ps_cull.cuh, built for the host (tests/host_cull.cpp): they may
+only drop (pixel block, splat) pairs that cannot pass the rasterizers' own per-pixel test.  Checked by brute force over the
+32 pixel centres of every block with the contract's sigma arithmetic: exact blocks are a subset of ps_block_mask8 (the block
+split, 3D pixel centres at +0.5 and 2D at integers) and of the bounding-rectangle masks of PS_BIN_MODE=bytes|split; the
+exact-mask test must also stay tight (it decides how many entries the rasterizers stage)."""
+import ctypes
+import subprocess
+
+import numpy as np
+
+from helpers import ROOT
+
+
+def _lib():
+    so, src = ROOT / "tests" / "_host_cull.so", ROOT / "tests" / "host_cull.cpp"
+    hdrs = [ROOT / "pose_splatter_b200" / "csrc" / h for h in ("ps_cull.cuh", "ps_contract.cuh")]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), str(src)], check=True)
+    return ctypes.CDLL(str(so))
+
+
+def _masks(lib, splats, half, tx, ty, W, H):
+    n = len(splats)
+    outs = [np.zeros(n, np.uint32) for _ in range(3)]
+    fp, up = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint32)
+    lib.hc_block_masks(splats.ctypes.data_as(fp), n, ctypes.c_float(half), tx, ty, W, H, *[o.ctypes.data_as(up) for o in outs])
+    return outs
+
+
+def _splats(rng, n, tx, ty, needle):
+    """Records as the 3D projection stores them: mean, halved conic of (R diag(s^2) R^T + 0.3 I)^-1, thr = log(255 o)."""
+    sx, sy = np.exp(rng.uniform(-2.5, 3.0, n)), np.exp(rng.uniform(-2.5, 3.0, n))
+    if needle:
+        sx = sx * 0.02
+    th = rng.uniform(0, np.pi, n)
+    c, s = np.cos(th), np.sin(th)
+    a, b, d = c * c * sx * sx + s * s * sy * sy + 0.3, c * s * (sx * sx - sy * sy), s * s * sx * sx + c * c * sy * sy + 0.3
+    det = a * d - b * b
+    thr = np.log(255 * np.exp(rng.uniform(np.log(1 / 255), 0, n)))
+    reach = 10 + 3.5 * np.sqrt(np.maximum(a, d))
+    gx, gy = tx * 16 + 8 + rng.uniform(-1, 1, n) * reach, ty * 16 + 8 + rng.uniform(-1, 1, n) * reach
+    return np.stack([gx, gy, 0.5 * d / det, -b / det, 0.5 * a / det, thr], 1).astype(np.float32)
+
+
+def _bits(x):
+    return int(np.unpackbits(x.view(np.uint8)).sum())
+
+
+def test_block_masks_never_drop_a_block_the_pixel_test_accepts():
+    lib = _lib()
+    rng = np.random.default_rng(7)
+    kept = exact = 0
+    for rep in range(12):
+        tx, ty = int(rng.integers(0, 18)), int(rng.integers(0, 16))
+        sp = _splats(rng, 40000, tx, ty, needle=rep % 4 == 0)
+        for half in (0.5, 0.0):
+            mask8, rect8, exact8 = _masks(lib, sp, half, tx, ty, 288, 256)
+            assert not (exact8 & ~mask8).any(), "ps_block_mask8 dropped a block with a passing pixel"
+            assert not (exact8 & ~rect8).any(), "the bounding-rectangle mask dropped a block with a passing pixel"
+            kept += _bits(mask8)
+            exact += _bits(exact8)
+    assert exact > 100000 and kept <= 1.03 * exact, (kept, exact)  # measured: 1.015
+
+
+def test_block_masks_degenerate_records_count_as_hits():
+    lib = _lib()
+    nan, inf = float("nan"), float("inf")
+    sp = np.array([[8.0, 8.0, nan, 0.0, 1.0, 3.0], [8.0, 8.0, 1.0, nan, 1.0, 3.0], [8.0, 8.0, 1.0, 0.0, 1.0, nan],
+                   [nan, 8.0, 1.0, 0.0, 1.0, 3.0], [8.0, 8.0, 0.0, 0.0, 0.0, 3.0], [8.0, 8.0, -1.0, 0.0, -1.0, 3.0],
+                   [8.0, 8.0, inf, 0.0, inf, 3.0]], np.float32)
+    mask8, _, exact8 = _masks(lib, sp, 0.5, 0, 0, 288, 256)
+    assert not (exact8 & ~mask8).any()
+    assert (mask8[[0, 1, 2]] == 0xFF).all(), mask8  # NaN in the conic / threshold: every block is kept, the exact test decides
+    # (a NaN mean -- row 3 -- never passes the pixel test, sigma is NaN: any mask is correct; the projection culls it anyway)
+    assert mask8[4] == 0xFF and mask8[5] == 0xFF      # flat / concave "conics": sigma <= thr everywhere
