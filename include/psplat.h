@@ -123,7 +123,10 @@ int ps_forward_rgba8(ps_ctx *ctx, const ps_render_desc *desc, const float *param
  * d_alpha [V,H,W].  Replaces autograd through :183-211 / :314-427 (gsplat's
  * rasterize_to_pixels_bwd + fully_fused_projection_bwd in 3D).  params / viewmats / Ks must hold what the forward
  * was given; `background` is ignored (the forward kept its own copy; may be NULL).  d_params is overwritten (not
- * accumulated into).
+ * accumulated into).  `stream` may differ from the forward's: the call is then ordered (one event) behind the work
+ * already queued on the saved buffers; the same holds for ps_saved_copy and ps_saved_release, so a block released on one
+ * stream never reaches a new owner while another stream still reads it.  Ordering the caller's own tensors (params,
+ * cotangents, outputs) across streams stays the caller's job.
  */
 int ps_backward(ps_ctx *ctx, ps_saved *saved, const float *params, const int32_t *view_frame, const float *viewmats,
                 const float *Ks, const float *background, const float *d_rgb, const float *d_alpha, float *d_params,
