@@ -56,3 +56,62 @@ def test_npz_replay_renders_the_same_image(tmp_path):
     # q * rsqrt(q.q) instead of q / (|q| + 1e-8) on this path
     assert (rgb0 - rgb1).abs().max().item() < 1e-2 and (rgb0 - rgb1).abs().mean().item() < 1e-5  # a 1/255 alpha-threshold flip is 4e-3
     assert (a0 - a1).abs().max().item() < 1e-2 and (a0 - a1).abs().mean().item() < 1e-5
+
+
+# ---- RenderSequenceWriter (host logic; the device path differs only by the pinned buffers and the copy stream) ----------
+def _frames(T, C, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (T, C, h, w, 4), dtype=torch.uint8, generator=g)
+
+
+def test_render_sequence_writer_slabs_and_ragged_puts(tmp_path):
+    from pose_splatter_b200 import formats
+    T, C, h, w = 137, 3, 9, 7
+    frames = _frames(T, C, h, w)
+    fn = tmp_path / "renders.npy"
+    with formats.RenderSequenceWriter(fn, T, C, h, w, write_batch_frames=50, n_buffers=2) as out:
+        f = 0
+        for n in (1, 49, 3, 60, 24):                       # slab boundaries crossed, partial last slab
+            piece = frames[f:f + n]
+            out.put(piece if n % 2 else piece.reshape(n * C, h, w, 4))   # both accepted layouts
+            f += n
+        assert f == T and out.next_frame == T
+    back = formats.load_render_sequence(fn)
+    assert back.shape == (T, C, h, w, 4) and back.dtype == np.uint8
+    assert np.array_equal(np.asarray(back), frames.numpy())
+
+
+def test_render_sequence_writer_ranges_of_two_ranks_share_one_map(tmp_path):
+    from pose_splatter_b200 import formats
+    T, C, h, w = 40, 2, 5, 6
+    frames = _frames(T, C, h, w, seed=1)
+    fn = tmp_path / "renders.npy"
+    a = formats.RenderSequenceWriter(fn, T, C, h, w, write_batch_frames=8, first_frame=0)
+    b = formats.RenderSequenceWriter(fn, T, C, h, w, write_batch_frames=8, first_frame=25, create=False)
+    b.put(frames[25:40])
+    a.put(frames[0:25])
+    a.close()
+    b.close()
+    assert np.array_equal(np.asarray(formats.load_render_sequence(fn)), frames.numpy())
+
+
+def test_render_sequence_writer_errors(tmp_path):
+    from pose_splatter_b200 import formats
+    out = formats.RenderSequenceWriter(tmp_path / "r.npy", 4, 2, 3, 3)
+    with pytest.raises(ValueError, match="uint8"):
+        out.put(torch.zeros(1, 2, 3, 3, 4))
+    with pytest.raises(ValueError, match="Expected"):
+        out.put(torch.zeros(1, 2, 3, 5, 4, dtype=torch.uint8))
+    out.put(torch.zeros(3, 2, 3, 3, 4, dtype=torch.uint8))
+    with pytest.raises(ValueError, match="exceed"):
+        out.put(torch.zeros(2, 2, 3, 3, 4, dtype=torch.uint8))
+    out.close()
+    with pytest.raises(RuntimeError, match="after close"):
+        out.put(torch.zeros(1, 2, 3, 3, 4, dtype=torch.uint8))
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError, match="h5py is not installed"):
+            formats.RenderSequenceWriter(tmp_path / "r.h5", 4, 2, 3, 3)
+    with pytest.raises(ValueError, match="positive"):
+        formats.RenderSequenceWriter(tmp_path / "z.npy", 0, 2, 3, 3)
