@@ -202,6 +202,12 @@ class RenderSequenceWriter:
         self._data = None
         self._check()
 
+    def __del__(self):  # a writer dropped without close() still flushes what it was given
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- nothing to report to at collection time
+            pass
+
     def __enter__(self):
         return self
 
