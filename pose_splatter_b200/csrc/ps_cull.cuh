@@ -6,6 +6,7 @@
 #include "ps_contract.cuh"
 
 #define PS_THR_SLACK 0.01f      // slack on sigma <= log(255*opacity): covers the rounding of exp / log / sigma
+#define PS_CONIC_ERR 1.0e-6f    // 16 ulp of the term magnitudes: rounding of the conic coefficients and of the form's evaluation
 #define PS_SLOT_MASK_SHIFT 24   // list slot word = depth rank (3D) / row index (2D) in the low 24 bits | 8-bit block mask
 
 // 2D: q = dxr^2 iax + dyr^2 iay with (dxr, dyr) = R (dx, dy) is the quadratic form hA dx^2 + B dx dy + hC dy^2
@@ -24,9 +25,14 @@ __device__ __forceinline__ void ps_conic2d(const float4 &r1, float &hA, float &B
 // 4 vertical and 8 horizontal lines.  NaN / inf (degenerate conics) count as a hit.
 __device__ __forceinline__ uint32_t ps_block_mask8(float gx, float gy, float hA, float B, float hC, float thr, float half, int tx, int ty)
 {
-    const float lim = thr * 1.0001f + 2.0f * PS_THR_SLACK;
     const float kx = __fdividef(-B, 2.0f * hC), ky = __fdividef(-B, 2.0f * hA);
     const float X0 = ((float)(tx * PS_TILE) + half) - gx, Y0 = ((float)(ty * PS_TILE) + half) - gy;
+    // The quadratic form of a needle (2D rows with sigma_x << sigma_y, giant 3D splats) is evaluated here as a sum of
+    // terms that nearly cancel, where the exact per-pixel test rotates first: the threshold is widened by a bound of that
+    // rounding error over the tile (PS_CONIC_ERR * the sum of the term magnitudes), which is nothing (< 1e-3) for
+    // ordinary splats and opens the test up for ill-conditioned ones instead of dropping their blocks.
+    const float xm = fmaxf(fabsf(X0), fabsf(X0 + 15.0f)), ym = fmaxf(fabsf(Y0), fabsf(Y0 + 15.0f));
+    const float lim = thr * 1.0001f + 2.0f * PS_THR_SLACK + PS_CONIC_ERR * ((hA * xm + fabsf(B) * ym) * xm + hC * ym * ym);
     float ux0[2], ux1[2], cx[2], tx_[2], ax[2], bx_[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -63,6 +69,30 @@ __device__ __forceinline__ uint32_t ps_block_mask8(float gx, float gy, float hA,
         m8 |= miss ? 0u : (1u << k);
     }
     return m8;
+}
+
+// Can the splat pass sigma <= thr (3D) / q <= L (2D, conic from ps_conic2d) anywhere on the pixel centres [x0, x1] x [y0, y1]?
+// Same argument as ps_block_mask8 for one box (the rasterizers' re-cull against the box of the pixels that are still live);
+// the threshold carries the same bound of the form's rounding error.  NaN / inf (degenerate conics) count as a hit.
+__device__ __forceinline__ bool ps_ellipse_hits_box(float gx, float gy, float hA, float B, float hC, float thr, float x0,
+                                                    float x1, float y0, float y1)
+{
+    const float ux0 = x0 - gx, ux1 = x1 - gx;
+    const float uy0 = y0 - gy, uy1 = y1 - gy;
+    const float cx = fminf(fmaxf(0.0f, ux0), ux1), cy = fminf(fmaxf(0.0f, uy0), uy1);
+    if (cx == 0.0f && cy == 0.0f) return true;
+    float best = 3.0e38f;
+    if (cx != 0.0f) {
+        const float t = fminf(fmaxf(__fdividef(-B * cx, 2.0f * hC), uy0), uy1);
+        best = hA * cx * cx + (hC * t + B * cx) * t;
+    }
+    if (cy != 0.0f) {
+        const float t = fminf(fmaxf(__fdividef(-B * cy, 2.0f * hA), ux0), ux1);
+        const float sv = hC * cy * cy + (hA * t + B * cy) * t;
+        best = (sv < best || !(best == best)) ? sv : best;
+    }
+    const float xm = fmaxf(fabsf(ux0), fabsf(ux1)), ym = fmaxf(fabsf(uy0), fabsf(uy1));
+    return !(best > thr * 1.0001f + 2.0f * PS_THR_SLACK + PS_CONIC_ERR * ((hA * xm + fabsf(B) * ym) * xm + hC * ym * ym));
 }
 
 // Bounding box of the footprint {u : hA ux^2 + B ux uy + hC uy^2 <= lim} around the mean, half-widths in pixels

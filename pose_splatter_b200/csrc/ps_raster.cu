@@ -115,30 +115,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, unsi
                  ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// 3D: can the splat pass sigma <= thr anywhere on the pixel centres [x0, x1] x [y0, y1]?
-// sigma(u) = hA ux^2 + hC uy^2 + B ux uy (u = pixel - mean) is convex with its minimum at u = 0, so over a
-// box that does not contain 0 the minimum lies on an edge facing the mean; along such an edge it is a 1-D
-// parabola.  NaN / inf (degenerate conics) count as a hit.
-__device__ __forceinline__ bool ellipse_hits_box(float gx, float gy, float hA, float B, float hC, float thr, float x0,
-                                                 float x1, float y0, float y1)
-{
-    const float ux0 = x0 - gx, ux1 = x1 - gx;
-    const float uy0 = y0 - gy, uy1 = y1 - gy;
-    const float cx = fminf(fmaxf(0.0f, ux0), ux1), cy = fminf(fmaxf(0.0f, uy0), uy1);
-    if (cx == 0.0f && cy == 0.0f) return true;
-    float best = 3.0e38f;
-    if (cx != 0.0f) {
-        const float t = fminf(fmaxf(__fdividef(-B * cx, 2.0f * hC), uy0), uy1);
-        best = hA * cx * cx + (hC * t + B * cx) * t;
-    }
-    if (cy != 0.0f) {
-        const float t = fminf(fmaxf(__fdividef(-B * cy, 2.0f * hA), ux0), ux1);
-        const float sv = hC * cy * cy + (hA * t + B * cy) * t;
-        best = (sv < best || !(best == best)) ? sv : best;
-    }
-    return !(best > thr * 1.0001f + 2.0f * THR_SLACK);
-}
-
 // bounding box (in block-local pixel coordinates) of the lanes set in `active` (lane = y * 8 + x); active != 0
 __device__ __forceinline__ void active_box(uint32_t active, int &x0, int &x1, int &y0, int &y1)
 {
@@ -177,7 +153,7 @@ __device__ __forceinline__ uint32_t cull_chunk(const Ring &q, int st, int lane, 
         const float half = (MODE == PS_MODE_3D) ? 0.5f : 0.0f; // pixel centres: +0.5 in 3D, integers in 2D
         float hA = a1.x, B = a1.y, hC = a1.z;
         if (MODE == PS_MODE_2D) ps_conic2d(a1, hA, B, hC);
-        hit = ellipse_hits_box(a0.x, a0.y, hA, B, hC, a0.z, (float)(c.bx + ax0) + half, (float)(c.bx + ax1) + half,
+        hit = ps_ellipse_hits_box(a0.x, a0.y, hA, B, hC, a0.z, (float)(c.bx + ax0) + half, (float)(c.bx + ax1) + half,
                                (float)(c.by + ay0) + half, (float)(c.by + ay1) + half);
     }
     return __ballot_sync(FULL, hit);

@@ -41,4 +41,46 @@ void hc_block_masks(const float *splats, int n, float half, int tx, int ty, int 
         exact8[i] = m;
     }
 }
+
+// 2D records: splats [n,7] = u v L cos sin 1/ax 1/ay (rec0.xyz, rec1); integer pixel centres; exact test q <= L (ps_q2d)
+void hc_block_masks_2d(const float *splats, int n, int tx, int ty, uint32_t *mask8, uint32_t *exact8)
+{
+    for (int i = 0; i < n; ++i) {
+        const float *s = splats + 7 * (size_t)i;
+        const float4 r1 = { s[3], s[4], s[5], s[6] };
+        float hA, B, hC;
+        ps_conic2d(r1, hA, B, hC);
+        mask8[i] = ps_block_mask8(s[0], s[1], hA, B, hC, s[2], 0.0f, tx, ty);
+        uint32_t m = 0;
+        for (int k = 0; k < 8; ++k)
+            for (int p = 0; p < 32 && !((m >> k) & 1u); ++p) {
+                const float px = (float)(tx * PS_TILE + (k & 1) * 8 + (p & 7));
+                const float py = (float)(ty * PS_TILE + (k >> 1) * 4 + (p >> 3));
+                float a, b;
+                if (ps_q2d(s[0], s[1], s[3], s[4], s[5], s[6], px, py, &a, &b) <= s[2]) m |= 1u << k;
+            }
+        exact8[i] = m;
+    }
+}
+
+// the rasterizers' re-cull of one entry against a box of live pixels: splats as above (2D records), boxes [n,4] =
+// x0 x1 y0 y1 (integer pixel coordinates, inclusive); hit [n] = ps_ellipse_hits_box, exact [n] = any pixel with q <= L
+void hc_box_hits_2d(const float *splats, const int *boxes, int n, uint8_t *hit, uint8_t *exact)
+{
+    for (int i = 0; i < n; ++i) {
+        const float *s = splats + 7 * (size_t)i;
+        const int *b = boxes + 4 * (size_t)i;
+        const float4 r1 = { s[3], s[4], s[5], s[6] };
+        float hA, B, hC;
+        ps_conic2d(r1, hA, B, hC);
+        hit[i] = ps_ellipse_hits_box(s[0], s[1], hA, B, hC, s[2], (float)b[0], (float)b[1], (float)b[2], (float)b[3]) ? 1 : 0;
+        uint8_t e = 0;
+        for (int y = b[2]; y <= b[3] && !e; ++y)
+            for (int x = b[0]; x <= b[1] && !e; ++x) {
+                float a, c;
+                if (ps_q2d(s[0], s[1], s[3], s[4], s[5], s[6], (float)x, (float)y, &a, &c) <= s[2]) e = 1;
+            }
+        exact[i] = e;
+    }
+}
 }

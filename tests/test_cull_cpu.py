@@ -73,3 +73,29 @@ def test_block_masks_degenerate_records_count_as_hits():
     assert (mask8[[0, 1, 2]] == 0xFF).all(), mask8  # NaN in the conic / threshold: every block is kept, the exact test decides
     # (a NaN mean -- row 3 -- never passes the pixel test, sigma is NaN: any mask is correct; the projection culls it anyway)
     assert mask8[4] == 0xFF and mask8[5] == 0xFF      # flat / concave "conics": sigma <= thr everywhere
+
+
+def test_block_masks_2d_records_never_drop_a_block_the_footprint_test_accepts():
+    """2D mode: the record holds (cos, sin, 1/ax, 1/ay) with ax = 2 sigma^2 + 1e-8 and the threshold L = ln(o / tau); the
+    block split turns it into a conic (ps_conic2d) and the rasterizers test q <= L at integer pixel centres (ps_q2d)."""
+    lib = _lib()
+    rng = np.random.default_rng(11)
+    fp, up = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint32)
+    kept = exact = 0
+    for rep in range(10):
+        n = 40000
+        tx, ty = int(rng.integers(0, 36)), int(rng.integers(0, 32))
+        sx, sy = np.exp(rng.uniform(-3.0, 2.5, n)), np.exp(rng.uniform(-3.0, 2.5, n))
+        if rep % 3 == 0:
+            sx = sx * 0.03
+        th = rng.uniform(-7.0, 7.0, n)
+        L = np.log(np.exp(rng.uniform(np.log(2.0 ** -27), 0, n)) * 2.0 ** 28)
+        reach = 10 + np.sqrt(2 * L) * np.maximum(sx, sy)
+        u, v = tx * 16 + 8 + rng.uniform(-1, 1, n) * reach, ty * 16 + 8 + rng.uniform(-1, 1, n) * reach
+        sp = np.stack([u, v, L, np.cos(th), np.sin(th), 1 / (2 * sx * sx + 1e-8), 1 / (2 * sy * sy + 1e-8)], 1).astype(np.float32)
+        mask8, exact8 = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        lib.hc_block_masks_2d(sp.ctypes.data_as(fp), n, tx, ty, mask8.ctypes.data_as(up), exact8.ctypes.data_as(up))
+        assert not (exact8 & ~mask8).any(), "ps_block_mask8 (2D records) dropped a block with a pixel inside the footprint"
+        kept += _bits(mask8)
+        exact += _bits(exact8)
+    assert exact > 100000 and kept <= 1.05 * exact, (kept, exact)
