@@ -133,3 +133,47 @@ def test_box_recull_never_drops_an_entry_with_a_passing_live_pixel():
         assert ex.sum() > 20 and not (ex & ~hit & 1).any(), f"re-cull dropped a passing entry (needle {needle})"
         if not needle:
             assert hit.sum() <= 1.05 * ex.sum()
+
+
+def test_2d_pixel_rectangle_contains_every_passing_pixel():
+    """ps_project2d lists a row on the tiles of its pixel rectangle: every integer pixel of the image
+    that passes q <= L in the contract's arithmetic must lie inside it, needles included; unlisted rows pass nowhere."""
+    from helpers import hc_project, host_contract
+    hc = host_contract()
+    fp = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(4)
+    W, H = 96, 80
+    ys, xs = np.mgrid[0:H, 0:W]
+    px, py = xs.ravel().astype(np.float32), ys.ravel().astype(np.float32)
+    q = np.zeros(W * H, np.float32)
+    total = 0
+    for needle in (0, 0.03, 0.003, 0.0003):
+        n = 500
+        lsx, lsy = rng.uniform(-3, 2.5, n), rng.uniform(-3, 2.5, n)
+        if needle:
+            lsx, lsy = np.log(needle) + rng.uniform(-0.3, 0.3, n), rng.uniform(0, 3.0, n)
+        rows = np.stack([rng.uniform(-10, W + 10, n), rng.uniform(-10, H + 10, n), lsx, lsy, rng.uniform(-7, 7, n),
+                         rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.normal(0, 3, n)], 1).astype(np.float32)
+        rec, tile, _ = hc_project("2d", rows, W, H)
+        for i in range(n):
+            o = 1 / (1 + np.exp(-np.float64(rows[i, 8])))
+            if o <= 2.0 ** -28:
+                continue
+            listed = tile[i, 2] > tile[i, 0] and tile[i, 3] > tile[i, 1]
+            if listed:
+                g = np.array([rows[i, 0], rows[i, 1], rec[i, 4], rec[i, 5], rec[i, 6], rec[i, 7]], np.float32)
+            else:  # no record was written: rebuild its pair constants from the row
+                ax = np.float32(2) * np.exp(rows[i, 2]) ** 2 + np.float32(1e-8)
+                ay = np.float32(2) * np.exp(rows[i, 3]) ** 2 + np.float32(1e-8)
+                g = np.array([rows[i, 0], rows[i, 1], np.cos(rows[i, 4]), np.sin(rows[i, 4]), 1 / ax, 1 / ay], np.float32)
+            hc.hc_pairs2d(g.ctypes.data_as(fp), px.ctypes.data_as(fp), py.ctypes.data_as(fp), W * H, q.ctypes.data_as(fp))
+            passing = np.nonzero(q <= np.float32(np.log(o * 2.0 ** 28)))[0]
+            total += len(passing)
+            if not len(passing):
+                continue
+            assert listed, f"row {i} (needle {needle}) passes at {len(passing)} pixels but is listed nowhere"
+            b0, b1 = rec[i, 2].view(np.uint32), rec[i, 3].view(np.uint32)
+            x0, y0, x1, y1 = int(b0 & 0xFFFF), int(b0 >> 16), int(b1 & 0xFFFF), int(b1 >> 16)
+            pxs, pys = passing % W, passing // W
+            assert pxs.min() >= x0 and pxs.max() <= x1 and pys.min() >= y0 and pys.max() <= y1, (i, needle)
+    assert total > 50000
